@@ -1,0 +1,116 @@
+/* msclip_b200 — C ABI of the B200-native MS-CLIP-S encode-and-contrast path.
+ *
+ * This is the drop-in boundary.  The reference (Hxyou/MSCLIP) is pure Python and
+ * has no FFI of its own; the entry points below are what a binding for its model API
+ * (lib/models/clip_openai_pe_res_v1.py, "M.py") binds, one per reference method:
+ *
+ *   msclip_create               <- get_clip_model(config) -> CLIP(...)            M.py:3182-3227, 2700-2852
+ *   msclip_set_weight           <- model.load_state_dict(sd), one call per key    tools/zero_shot.py:223-224
+ *   msclip_finalize_weights     <- model.to(device) / .eval()                     tools/zero_shot.py:225-228
+ *   msclip_encode_image         <- CLIP.encode_image(image, norm)                 M.py:2979-2985
+ *   msclip_encode_text          <- CLIP.encode_text(text, norm)                   M.py:3043-3079
+ *   msclip_similarity_logits    <- logit_scale.exp() * I @ T.t()                  M.py:3136, 3141/3146; zero_shot.py:266
+ *   msclip_forward              <- CLIP.forward(image, text) -> logits            M.py:3126-3155
+ *   msclip_contrastive_loss     <- gather_tensors x2 + logits + symmetric CE      M.py:3139-3141, comm.py:140-154
+ *   msclip_forward_loss         <- forward + loss in one call (the benchmarked step)
+ *   msclip_comm_*               <- lib/utils/comm.py gather_tensors replacement: peer shard registration
+ *
+ * Conventions: plain pointers and sizes only (no torch / CUDA types); `stream` is a cudaStream_t passed
+ * as void* (NULL = default stream); every call is stream-ordered and returns 0 on success, non-zero on
+ * failure with a message available from msclip_last_error() (thread-local).  Data pointers may be device
+ * pointers or host pointers (pageable or pinned) — the library inspects them with
+ * cudaPointerGetAttributes and stages host data through pinned buffers itself; a call with a host
+ * output pointer returns after the result has landed.  The library borrows caller memory only for the
+ * duration of a call and owns its workspace and its re-packed weights.
+ * There is no CPU fallback: every compute entry point fails if no sm_100 device is present.
+ */
+#ifndef MSCLIP_B200_H_
+#define MSCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct msclip_ctx* msclip_handle;
+
+/* dtype codes for msclip_set_weight / image inputs */
+enum { MSCLIP_F32 = 0, MSCLIP_BF16 = 1, MSCLIP_F16 = 2, MSCLIP_I64 = 3 };
+
+/* The MS-CLIP-S envelope (experiments/model/b32-yfcc-msclips.yaml, b16-yfcc-msclips.yaml). */
+typedef struct msclip_config {
+  int32_t patch_size;          /* 32 or 16 */
+  int32_t layers;              /* vision layer 0 is the conv stem; text has `layers` blocks */
+  int32_t width;               /* 768 */
+  int32_t embed_dim;           /* 512 */
+  int32_t image_resolution;    /* 224 */
+  int32_t context_length;      /* 77 */
+  int32_t vocab_size;          /* 49408 */
+  int32_t early_strides[4];    /* EARLY_CONV_RES_STRIDES: {2,2,2,2} (B/32) or {2,2,2,1} (B/16) */
+  int32_t parallel_strides[5]; /* PARALLEL_STRIDES: {2,2,2,2,2} or {2,2,2,2,1} */
+  int32_t t2b_kernels[5];      /* PRALLEL_T2B_KERNELS (= strides): {16,8,4,2,1} or {8,4,2,1,1} */
+} msclip_config;
+
+const char* msclip_version(void);
+const char* msclip_last_error(void);
+/* number of visible CUDA devices with compute capability 10.x (0 on a CPU-only box; never fails) */
+int msclip_device_count(void);
+
+int msclip_create(const msclip_config* cfg, msclip_handle* out);
+int msclip_destroy(msclip_handle h);
+
+/* Hand over one entry of the reference state_dict (same key names, SURVEY.md section 8c "state-dict
+ * contract"); data is copied.  dtype must be MSCLIP_F32 except for num_batches_tracked (MSCLIP_I64,
+ * ignored).  Unknown keys and shape mismatches are errors (load_state_dict(strict=True) behaviour). */
+int msclip_set_weight(msclip_handle h, const char* key, const void* data, int dtype, int ndim, const int64_t* shape);
+/* Validate that every key arrived, fold BatchNorm, fold the 1/8 query scaling, re-pack to bf16 K-major. */
+int msclip_finalize_weights(msclip_handle h, void* stream);
+/* exp(logit_scale) of the loaded weights (M.py:3136) */
+int msclip_logit_scale_exp(msclip_handle h, float* out);
+
+/* image: [batch, 3, R, R] NCHW of `image_dtype`; out: [batch, embed_dim] f32. */
+int msclip_encode_image(msclip_handle h, const void* image, int image_dtype, int batch, float* out, int normalize,
+                        void* stream);
+/* tokens: [batch, context_length] int64; out: [batch, embed_dim] f32.  Out-of-range ids are an error. */
+int msclip_encode_text(msclip_handle h, const int64_t* tokens, int batch, float* out, int normalize, void* stream);
+/* logits[n_img, n_txt] = scale * img_feat . txt_feat^T (f32 in, f32 out; split-bf16 tensor-core product). */
+int msclip_similarity_logits(msclip_handle h, const float* img_feat, int n_img, const float* txt_feat, int n_txt,
+                             float scale, float* logits, void* stream);
+/* CLIP.forward for one process: logits[batch, batch] = exp(logit_scale) * I . T^T. */
+int msclip_forward(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int batch,
+                   float* logits, void* stream);
+
+/* ---- sharded contrastive loss (data parallel, one process per GPU) -----------------------------------
+ * Each rank owns `b_local` pairs; global row index = rank * b_local + i (rank order of gather_tensors,
+ * comm.py:150-153).  The embedding exchange is NOT a collective: every rank publishes its normalised
+ * bf16 embeddings in a library-owned, IPC-exported buffer and the loss kernel of every other rank loads
+ * them over NVLink.  Setup (once):
+ *   1. msclip_comm_init(h, rank, world, max_b_local)              allocates the exchange buffer
+ *   2. msclip_comm_export(h, handle_bytes[64])                    -> exchange the 64-byte handles out of band
+ *   3. msclip_comm_import(h, all_handles[world*64])               (torch.distributed / MPI / files ...)
+ * world == 1 needs none of this. */
+int msclip_comm_init(msclip_handle h, int rank, int world, int max_b_local);
+int msclip_comm_export(msclip_handle h, void* handle_out_64);
+int msclip_comm_import(msclip_handle h, const void* handles_world_x_64);
+
+/* Loss of the features produced by the LAST msclip_encode_image / msclip_encode_text calls of this handle
+ * (kept on the device in bf16), batch b_local each.  partial_out[2] (host or device) receives this rank's
+ * partial sums: loss = sum over ranks (partial[0] + partial[1]) / (2 * world * b_local).
+ * With world == 1 loss_out (optional, may be NULL) receives the final loss. */
+int msclip_contrastive_loss(msclip_handle h, int b_local, float scale, float* partial_out, float* loss_out,
+                            void* stream);
+/* encode_image + encode_text + msclip_contrastive_loss with scale = exp(logit_scale). */
+int msclip_forward_loss(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int b_local,
+                        float* partial_out, float* loss_out, void* stream);
+
+/* Number of kernels this handle has launched since creation (for the benchmark's gpu_launches claim). */
+int64_t msclip_launch_count(msclip_handle h);
+/* Bytes of device memory currently owned by the handle (weights + workspace). */
+int64_t msclip_device_bytes(msclip_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCLIP_B200_H_ */

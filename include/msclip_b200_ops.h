@@ -1,0 +1,64 @@
+/* msclip_b200 — single-kernel entry points of the C ABI (device pointers only, stream-ordered).
+ *
+ * These expose the individual sm_100a kernels behind the model-level calls of msclip_b200.h so that each
+ * one can be parity-tested against the operation of the reference it replaces
+ * (lib/models/clip_openai_pe_res_v1.py = "M.py"):
+ *
+ *   msclip_op_gemm            F.linear + fused epilogue             M.py:612, 747, 794-798, 2690, 3074
+ *   msclip_op_layernorm       LayerNorm.forward                     M.py:204-219
+ *   msclip_op_attention       Attention_CUST.forward core           M.py:707-738
+ *   msclip_op_im2col_first    gather for the 3x3/s2 first convs     M.py:1952, 2154 (EarlyconvRes / branch)
+ *   msclip_op_im2col_nhwc     gather for the later convs            M.py:1920-1936, 1842-1861
+ *   msclip_op_patch_pool      Lateral_Adapter.top2bottom_dw_conv    M.py:1756
+ *   msclip_op_adapter_fuse_ln Lateral_Adapter tail                  M.py:1760-1777
+ *   msclip_op_contrastive_lse similarity + symmetric CE partials    M.py:3141 + north-star loss
+ *   msclip_num_keys / msclip_key_info   the state-dict contract     SURVEY.md section 8c
+ */
+#ifndef MSCLIP_B200_OPS_H_
+#define MSCLIP_B200_OPS_H_
+
+#include "msclip_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* epilogue codes of msclip_op_gemm */
+enum {
+  MSCLIP_EPI_BF16 = 0,       /* bf16 out = alpha*acc + bias */
+  MSCLIP_EPI_QGELU_BF16 = 1, /* bf16 out = quickgelu(alpha*acc + bias) */
+  MSCLIP_EPI_RELU_BF16 = 2,  /* bf16 out = relu(alpha*acc + bias) */
+  MSCLIP_EPI_RESID_F32 = 3,  /* f32 out = resid + alpha*acc + bias (resid may alias out) */
+  MSCLIP_EPI_F32 = 4         /* f32 out = alpha*acc + bias */
+};
+
+/* out[m,n] = epi(alpha * a[m,k] . w[n,k]^T + bias[n]); a, w bf16 with row pitches lda, ldw (elements). */
+int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, float alpha,
+                   const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epilogue,
+                   void* stream);
+/* y[r,:] (bf16) = LN(x[r*row_stride,:]) over 768 columns, eps 1e-12 inside the sqrt. */
+int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
+                        void* stream);
+/* qkv bf16 [batch*seq_len, 3*64*heads] (q already scaled) -> out bf16 [batch*seq_len, 64*heads]. */
+int msclip_op_attention(const void* qkv_bf16, void* out_bf16, int batch, int seq_len, int heads, int causal,
+                        void* stream);
+int msclip_op_im2col_first(const void* img, int dtype, void* out_bf16, int batch, int height, int width, void* stream);
+int msclip_op_im2col_nhwc(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
+                          int ksize, int stride, int pad, void* out_bf16, int64_t out_ld, int out_off, void* stream);
+int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
+                         int k, const float* w, const float* bias, void* out_bf16, void* stream);
+int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
+                              const float* b, float* x_out, int batch, int grid, void* stream);
+/* parts2[0] = sum_i (lse_j s_ij - s_ii), parts2[1] = sum_j (lse_i s_ij - s_jj), s = scale * img . txt^T */
+int msclip_op_contrastive_lse(const void* img_bf16, const void* txt_bf16, int b, float scale, void* workspace,
+                              float* parts2, void* stream);
+size_t msclip_op_contrastive_lse_workspace(int b);
+
+/* state-dict contract of a handle: number of keys, and key / rank / shape (up to 4 dims) of entry i. */
+int msclip_num_keys(msclip_handle h);
+int msclip_key_info(msclip_handle h, int index, const char** key, int* ndim, int64_t* shape4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCLIP_B200_OPS_H_ */

@@ -1,0 +1,77 @@
+"""Build libmsclip_b200.so in-tree with nvcc for sm_100a (no torch involved).
+
+    python -m msclip_b200.build [--force]
+
+The shared library is the product's only compute path: it is git-ignored but travels to the GPU box
+with the working tree.  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ_DIR = os.path.join(CSRC, "build")
+LIB_PATH = os.path.join(HERE, "libmsclip_b200.so")
+SOURCES = ["runtime.cu", "gemm.cu", "elementwise.cu", "conv.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
+HEADERS = ["common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
+           os.path.join("..", "..", "include", "msclip_b200_ops.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _mtime(path: str) -> float:
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def needs_build() -> bool:
+    lib = _mtime(LIB_PATH)
+    if lib == 0.0:
+        return True
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(_mtime(d) > lib for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    newest_header = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if not force and _mtime(obj) > max(_mtime(os.path.join(CSRC, src)), newest_header):
+            return obj
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose=True)
+    print("built", path)

@@ -1,0 +1,79 @@
+"""Data-parallel plumbing for the contrastive step (one process per GPU).
+
+Mirrors lib/utils/comm.py of the reference for the one collective on the path:
+
+* ``gather_tensors(t)``  (comm.py:140-154) — rank-ordered all-gather; kept as the reference-compatible
+  (and comparator) path used by ``CLIP.forward`` when logits must be materialised.
+* ``setup_peer_exchange`` — the B200-native replacement: no collective at all on the data path.  Every
+  rank's library handle owns an exchange buffer; its CUDA IPC handle is swapped once through
+  ``torch.distributed`` (plumbing), after which the fused loss kernel of each rank reads the peers'
+  embeddings straight over NVLink.
+
+``shard_range`` is the row-ownership rule both paths share: global row = rank * b_local + i.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def rank_world(group=None) -> Tuple[int, int]:
+    """(rank, world) — degrades to (0, 1) without an initialised process group (comm.py:16-30)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_range(rank: int, world: int, global_batch: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of the global batch owned by ``rank`` (equal shards, rank order)."""
+    if global_batch % world:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    b = global_batch // world
+    return rank * b, (rank + 1) * b
+
+
+def gather_tensors(tensor: torch.Tensor, group=None) -> torch.Tensor:
+    """Rank-ordered concat of every rank's tensor along dim 0; the local shard is re-inserted so it
+    keeps its identity (comm.py:145-153)."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return tensor
+    parts = [torch.empty_like(tensor) for _ in range(world)]
+    dist.all_gather(parts, tensor.contiguous(), group=group)
+    parts[rank] = tensor
+    return torch.cat(parts, dim=0)
+
+
+def exchange_bytes(payload: bytes, group=None) -> bytes:
+    """All-gather a fixed-size byte string from every rank, rank-ordered (works on gloo and nccl)."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return payload
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return b"".join(bytes(p.cpu().tolist()) for p in parts)
+
+
+def setup_peer_exchange(handle, max_b_local: int, group=None):
+    """comm_init -> export IPC handle -> all-gather the 64-byte handles -> import.  Returns
+    (rank, world, max_b_local)."""
+    rank, world = rank_world(group)
+    L = _lib.lib()
+    _lib.check(L.msclip_comm_init(handle, rank, world, int(max_b_local)), "msclip_comm_init")
+    if world > 1:
+        buf = (C.c_uint8 * 64)()
+        _lib.check(L.msclip_comm_export(handle, buf), "msclip_comm_export")
+        everyone = exchange_bytes(bytes(buf), group)
+        assert len(everyone) == 64 * world
+        arr = (C.c_uint8 * len(everyone)).from_buffer_copy(everyone)
+        _lib.check(L.msclip_comm_import(handle, arr), "msclip_comm_import")
+        dist.barrier(group)
+    return rank, world, int(max_b_local)

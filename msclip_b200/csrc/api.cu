@@ -1,0 +1,220 @@
+// extern "C" surface declared in include/msclip_b200.h and include/msclip_b200_ops.h.
+#include "engine.h"
+
+#include <new>
+
+#include "../../include/msclip_b200_ops.h"
+#include "common.cuh"
+
+using namespace msclip;
+
+static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* msclip_version(void) { return "msclip_b200 0.1.0 (sm_100a)"; }
+const char* msclip_last_error(void) { return get_last_error(); }
+
+int msclip_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+int msclip_create(const msclip_config* cfg, msclip_handle* out) {
+  MSCLIP_REQUIRE(cfg != nullptr && out != nullptr, "msclip_create: null argument");
+  MSCLIP_REQUIRE(cfg->patch_size == 16 || cfg->patch_size == 32, "MS-CLIP-S envelope: patch_size must be 16 or 32");
+  MSCLIP_REQUIRE(cfg->width == 768, "MS-CLIP-S envelope: width must be 768 (12 heads of 64)");
+  MSCLIP_REQUIRE(cfg->embed_dim == 512, "MS-CLIP-S envelope: embed_dim must be 512");
+  MSCLIP_REQUIRE(cfg->layers >= 1 && cfg->layers <= 64, "layers out of range");
+  MSCLIP_REQUIRE(cfg->image_resolution == 224, "MS-CLIP-S envelope: image_resolution must be 224");
+  MSCLIP_REQUIRE(cfg->context_length >= 1 && cfg->context_length <= 208, "context_length must be in [1, 208]");
+  MSCLIP_REQUIRE(cfg->vocab_size >= 2, "vocab_size out of range");
+  MSCLIP_REQUIRE(cfg->parallel_strides[0] == 2, "the first parallel-branch conv must have stride 2 (it shares the stem's im2col)");
+  int g = cfg->image_resolution / 2;
+  for (int i = 0; i < 4; ++i) {
+    MSCLIP_REQUIRE(cfg->early_strides[i] == 1 || cfg->early_strides[i] == 2, "early-conv strides must be 1 or 2");
+    g /= cfg->early_strides[i];
+  }
+  MSCLIP_REQUIRE(g == cfg->image_resolution / cfg->patch_size, "early-conv strides do not produce the patch grid");
+  int r = cfg->image_resolution;
+  for (int j = 0; j < 5; ++j) {
+    MSCLIP_REQUIRE(cfg->parallel_strides[j] == 1 || cfg->parallel_strides[j] == 2, "parallel strides must be 1 or 2");
+    r /= cfg->parallel_strides[j];
+    MSCLIP_REQUIRE(cfg->t2b_kernels[j] >= 1 && r % cfg->t2b_kernels[j] == 0 && r / cfg->t2b_kernels[j] == g,
+                   "lateral adapter kernel does not land on the token grid");
+  }
+  msclip_ctx* h = new (std::nothrow) msclip_ctx();
+  MSCLIP_REQUIRE(h != nullptr, "out of host memory");
+  h->cfg = *cfg;
+  h->grid = g;
+  h->l_img = g * g + 1;
+  h->heads = cfg->width / 64;
+  build_spec(h);
+  *out = h;
+  return 0;
+}
+
+int msclip_destroy(msclip_handle h) {
+  delete h;
+  return 0;
+}
+
+int msclip_num_keys(msclip_handle h) { return h ? static_cast<int>(h->spec.size()) : -1; }
+
+int msclip_key_info(msclip_handle h, int index, const char** key, int* ndim, int64_t* shape4) {
+  MSCLIP_REQUIRE(h != nullptr && index >= 0 && index < static_cast<int>(h->spec.size()), "msclip_key_info: bad index");
+  auto it = h->spec.begin();
+  std::advance(it, index);
+  *key = it->first.c_str();
+  *ndim = static_cast<int>(it->second.size());
+  for (size_t i = 0; i < it->second.size() && i < 4; ++i) shape4[i] = it->second[i];
+  return 0;
+}
+
+int msclip_set_weight(msclip_handle h, const char* key, const void* data, int dtype, int ndim, const int64_t* shape) {
+  MSCLIP_REQUIRE(h != nullptr && key != nullptr, "msclip_set_weight: null argument");
+  auto it = h->spec.find(key);
+  MSCLIP_REQUIRE(it != h->spec.end(), std::string("unexpected state-dict key: ") + key);
+  MSCLIP_REQUIRE(ndim == static_cast<int>(it->second.size()), std::string("rank mismatch for ") + key);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    MSCLIP_REQUIRE(shape[i] == it->second[i], std::string("size mismatch for ") + key);
+    n *= static_cast<size_t>(shape[i]);
+  }
+  const std::string k(key);
+  const bool counter = k.size() > 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0;
+  RawTensor& t = h->raw[k];
+  if (t.dev) {
+    cudaFree(t.dev);
+    t.dev = nullptr;
+  }
+  t.shape = it->second;
+  t.numel = counter ? 0 : n;
+  h->finalized = false;
+  if (counter) return 0;  // BatchNorm's step counter does not enter the eval-mode forward
+  MSCLIP_REQUIRE(dtype == MSCLIP_F32, std::string("weights must be float32: ") + key);
+  MSCLIP_REQUIRE(data != nullptr, std::string("null data for ") + key);
+  MSCLIP_CHECK_CUDA(cudaMalloc(&t.dev, (n > 0 ? n : 1) * 4));
+  MSCLIP_CHECK_CUDA(cudaMemcpy(t.dev, data, n * 4, cudaMemcpyDefault));
+  return 0;
+}
+
+int msclip_finalize_weights(msclip_handle h, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_finalize(h, as_stream(stream));
+}
+
+int msclip_logit_scale_exp(msclip_handle h, float* out) {
+  MSCLIP_REQUIRE(h != nullptr && out != nullptr && h->finalized, "msclip_logit_scale_exp: weights not finalized");
+  *out = expf(h->logit_scale);
+  return 0;
+}
+
+int msclip_encode_image(msclip_handle h, const void* image, int image_dtype, int batch, float* out, int normalize,
+                        void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_encode_image(h, image, image_dtype, batch, out, normalize, as_stream(stream));
+}
+
+int msclip_encode_text(msclip_handle h, const int64_t* tokens, int batch, float* out, int normalize, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_encode_text(h, tokens, batch, out, normalize, as_stream(stream));
+}
+
+int msclip_similarity_logits(msclip_handle h, const float* img_feat, int n_img, const float* txt_feat, int n_txt,
+                             float scale, float* logits, void* stream) {
+  return engine_similarity_logits(h, img_feat, n_img, txt_feat, n_txt, scale, logits, as_stream(stream));
+}
+
+int msclip_forward(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int batch,
+                   float* logits, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_forward(h, image, image_dtype, tokens, batch, logits, as_stream(stream));
+}
+
+int msclip_comm_init(msclip_handle h, int rank, int world, int max_b_local) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return comm_init(h, rank, world, max_b_local);
+}
+int msclip_comm_export(msclip_handle h, void* handle_out_64) {
+  MSCLIP_REQUIRE(h != nullptr && handle_out_64 != nullptr, "null argument");
+  return comm_export(h, handle_out_64);
+}
+int msclip_comm_import(msclip_handle h, const void* handles) {
+  MSCLIP_REQUIRE(h != nullptr && handles != nullptr, "null argument");
+  return comm_import(h, handles);
+}
+
+int msclip_contrastive_loss(msclip_handle h, int b_local, float scale, float* partial_out, float* loss_out,
+                            void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_contrastive_loss(h, b_local, scale, partial_out, loss_out, as_stream(stream));
+}
+
+int msclip_forward_loss(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int b_local,
+                        float* partial_out, float* loss_out, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_forward_loss(h, image, image_dtype, tokens, b_local, partial_out, loss_out, as_stream(stream));
+}
+
+int64_t msclip_launch_count(msclip_handle) { return launch_count(); }
+int64_t msclip_device_bytes(msclip_handle h) {
+  return h ? static_cast<int64_t>(h->weight_bytes + h->ws_bytes + h->xchg_bytes) : 0;
+}
+
+// ---- single-kernel entry points (device pointers only) --------------------------------------------------
+int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, float alpha,
+                   const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epilogue,
+                   void* stream) {
+  return launch_gemm_scaled(static_cast<const bf16*>(a), lda, static_cast<const bf16*>(w), ldw, m, n, k, alpha, bias,
+                            out, ldo, resid, ldr, epilogue, as_stream(stream));
+}
+int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
+                        void* stream) {
+  return launch_layernorm_bf16(x, row_stride, w, b, static_cast<bf16*>(y_bf16), rows, as_stream(stream));
+}
+int msclip_op_attention(const void* qkv_bf16, void* out_bf16, int batch, int seq_len, int heads, int causal,
+                        void* stream) {
+  return launch_attention(static_cast<const bf16*>(qkv_bf16), static_cast<bf16*>(out_bf16), batch, seq_len, heads,
+                          causal, as_stream(stream));
+}
+int msclip_op_im2col_first(const void* img, int dtype, void* out_bf16, int batch, int height, int width, void* stream) {
+  return launch_im2col_first(img, dtype, static_cast<bf16*>(out_bf16), batch, height, width, as_stream(stream));
+}
+int msclip_op_im2col_nhwc(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
+                          int ksize, int stride, int pad, void* out_bf16, int64_t out_ld, int out_off, void* stream) {
+  return launch_im2col_nhwc(static_cast<const bf16*>(in_bf16), batch, height, width, cpix, c_off, channels, ksize, stride,
+                            pad, static_cast<bf16*>(out_bf16), out_ld, out_off, as_stream(stream));
+}
+int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
+                         int k, const float* w, const float* bias, void* out_bf16, void* stream) {
+  return launch_patch_pool(static_cast<const bf16*>(in_bf16), batch, height, width, cpix, c_off, channels, k, w, bias,
+                           static_cast<bf16*>(out_bf16), as_stream(stream));
+}
+int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
+                              const float* b, float* x_out, int batch, int grid, void* stream) {
+  return launch_adapter_fuse_ln(x, t, dw_w9, dw_bias, w, b, x_out, batch, grid, as_stream(stream));
+}
+int msclip_op_contrastive_lse(const void* img_bf16, const void* txt_bf16, int b, float scale, void* workspace,
+                              float* parts2, void* stream) {
+  // single-process form: shard tables with one entry each, built in the caller-provided workspace tail
+  const size_t need = contrastive_loss_workspace_bytes(1, b);
+  const void** tab = reinterpret_cast<const void**>(static_cast<uint8_t*>(workspace) + ((need + 15) & ~size_t(15)));
+  const void* host_tab[2] = {img_bf16, txt_bf16};
+  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice, as_stream(stream)));
+  return launch_contrastive_loss_ex(static_cast<const bf16*>(img_bf16), static_cast<const bf16*>(txt_bf16),
+                                    reinterpret_cast<const bf16* const*>(tab), reinterpret_cast<const bf16* const*>(tab + 1),
+                                    nullptr, 0, 1, b, 512, scale, workspace, parts2, as_stream(stream));
+}
+size_t msclip_op_contrastive_lse_workspace(int b) { return ((contrastive_loss_workspace_bytes(1, b) + 15) & ~size_t(15)) + 64; }
+
+}  // extern "C"

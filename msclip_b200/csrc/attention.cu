@@ -1,0 +1,239 @@
+// Fused self-attention for the short sequences of MS-CLIP-S (L = 50 / 77 causal / 197, head_dim 64):
+// softmax(q k^T [+ causal mask]) v per (batch, head), replacing the two bmm + softmax + five copies of
+// Attention_CUST.forward (M.py:707-738).  The 1/sqrt(64) scaling of q (M.py:707) is folded into the packed
+// QKV weights, heads are addressed by pointer arithmetic on the [B*L, 3*768] QKV matrix (M.py:709-711),
+// scores never leave registers and the softmax is fp32 with quad shuffles.
+//
+// One CTA per (batch, head); Q/K/V head slices are staged once in padded shared memory; every warp owns
+// 16 query rows and walks the keys in chunks (online softmax across chunks for L = 197).
+// Attention is 1-2 % of the path's FLOPs and the per-head problems are far
+// smaller than one 128-row tcgen05 tile, so the contractions use warp-level mma.sync m16n8k16 (bf16 in,
+// fp32 accumulate); the GEMMs that carry the other 98 % are tcgen05 (gemm.cu).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msclip {
+
+namespace {
+
+constexpr int kHeadDim = 64;
+constexpr int kLds = 72;  // padded smem row pitch in elements (144 B): conflict-free ldmatrix
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
+__global__ void __launch_bounds__(QPAD * 2)
+attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int heads) {
+  constexpr int KVPAD = KC * NCHUNK;
+  constexpr int NT = KC / 8;  // score n-tiles per chunk
+  static_assert(QPAD % 16 == 0 && KC % 16 == 0 && KVPAD >= QPAD, "tile shapes");
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  bf16* sq = reinterpret_cast<bf16*>(att_smem);
+  bf16* sk = sq + QPAD * kLds;
+  bf16* sv = sk + KVPAD * kLds;
+
+  const int b = blockIdx.x / heads;
+  const int h = blockIdx.x % heads;
+  const int width = heads * kHeadDim;
+  const long long pitch = 3ll * width;
+  const bf16* base = qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim;
+
+  // stage Q, K, V head slices (rows >= L are zero)
+  for (int i = threadIdx.x; i < (QPAD + 2 * KVPAD) * 8; i += blockDim.x) {
+    const int c = i & 7;
+    int row = i >> 3;
+    int which = 0;
+    if (row >= QPAD) {
+      row -= QPAD;
+      which = 1;
+      if (row >= KVPAD) {
+        row -= KVPAD;
+        which = 2;
+      }
+    }
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < L) v = *reinterpret_cast<const uint4*>(base + row * pitch + which * width + c * 8);
+    bf16* dst = which == 0 ? sq : (which == 1 ? sk : sv);
+    *reinterpret_cast<uint4*>(dst + row * kLds + c * 8) = v;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = warp * 16;
+  if (m0 >= L) return;
+  const int g = lane >> 2, t = lane & 3;
+  const int mi = lane >> 3, r8 = lane & 7;
+
+  uint32_t qf[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    ldmatrix_x4(qf[kk], smem_u32(sq + (m0 + r8 + 8 * (mi & 1)) * kLds + kk * 16 + 8 * (mi >> 1)));
+
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  const int row_lo = m0 + g, row_hi = m0 + g + 8;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    const int kv0 = ch * KC;
+    if (kv0 >= L) break;
+    if (CAUSAL && kv0 > m0 + 15) break;
+    // number of 16-wide key groups this warp needs in this chunk
+    int ng = KC / 16;
+    {
+      int last = L - 1;
+      if (CAUSAL && m0 + 15 < last) last = m0 + 15;
+      const int need = (last - kv0) / 16 + 1;
+      if (need < ng) ng = need;
+    }
+    float s[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int jp = 0; jp < NT / 2; ++jp) {
+      if (jp < ng) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t kf[4];
+          ldmatrix_x4(kf, smem_u32(sk + (kv0 + 16 * jp + r8 + 8 * (mi >> 1)) * kLds + kk * 16 + 8 * (mi & 1)));
+          mma_bf16_16816(s[2 * jp], qf[kk], kf[0], kf[1]);
+          mma_bf16_16816(s[2 * jp + 1], qf[kk], kf[2], kf[3]);
+        }
+      }
+    }
+    // mask + chunk max
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = kv0 + 8 * j + 2 * t + (e & 1);
+        const int row = (e < 2) ? row_lo : row_hi;
+        const bool ok = (j < 2 * ng) && col < L && (!CAUSAL || col <= row);
+        if (!ok) s[j][e] = -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
+      }
+    }
+    float alpha[2], mnew[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+      mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+      mnew[hh] = fmaxf(m_run[hh], mx[hh]);
+      // rows of the padding region may be fully masked in a chunk: keep the maths finite
+      const float msafe = (mnew[hh] == -INFINITY) ? 0.f : mnew[hh];
+      alpha[hh] = exp2f((m_run[hh] - msafe) * kLog2e);
+      m_run[hh] = mnew[hh];
+      mnew[hh] = msafe;
+    }
+    float ls[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f((s[j][e] - mnew[e >> 1]) * kLog2e);
+        s[j][e] = pv;
+        ls[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) l_run[hh] = l_run[hh] * alpha[hh] + ls[hh];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= alpha[0];
+      o[j][1] *= alpha[0];
+      o[j][2] *= alpha[1];
+      o[j][3] *= alpha[1];
+    }
+    // O += P V
+#pragma unroll
+    for (int kk2 = 0; kk2 < NT / 2; ++kk2) {
+      if (kk2 < ng) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * kk2][0], s[2 * kk2][1]);
+        pa[1] = pack_bf16(s[2 * kk2][2], s[2 * kk2][3]);
+        pa[2] = pack_bf16(s[2 * kk2 + 1][0], s[2 * kk2 + 1][1]);
+        pa[3] = pack_bf16(s[2 * kk2 + 1][2], s[2 * kk2 + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, smem_u32(sv + (kv0 + 16 * kk2 + r8 + 8 * (mi & 1)) * kLds + 16 * dp + 8 * (mi >> 1)));
+          mma_bf16_16816(o[2 * dp], pa, vf[0], vf[1]);
+          mma_bf16_16816(o[2 * dp + 1], pa, vf[2], vf[3]);
+        }
+      }
+    }
+  }
+
+  // quad-reduce the row sums, normalise, store
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 1);
+    l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
+  }
+  const float inv_lo = 1.0f / l_run[0], inv_hi = 1.0f / l_run[1];
+  bf16* obase = out + static_cast<long long>(b) * L * width + h * kHeadDim;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = 8 * j + 2 * t;
+    if (row_lo < L)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(row_lo) * width + col) =
+          pack_bf16(o[j][0] * inv_lo, o[j][1] * inv_lo);
+    if (row_hi < L)
+      *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(row_hi) * width + col) =
+          pack_bf16(o[j][2] * inv_hi, o[j][3] * inv_hi);
+  }
+}
+
+template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
+int launch_variant(const bf16* qkv, bf16* out, int batch, int L, int heads, cudaStream_t stream) {
+  constexpr int smem = (QPAD + 2 * KC * NCHUNK) * kLds * 2;
+  static bool configured = false;
+  if (!configured) {
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<QPAD, KC, NCHUNK, CAUSAL>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  attention_kernel<QPAD, KC, NCHUNK, CAUSAL><<<batch * heads, QPAD * 2, smem, stream>>>(qkv, out, L, heads);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int launch_attention(const bf16* qkv, bf16* out, int batch, int L, int heads, int causal, cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  MSCLIP_REQUIRE(L >= 1 && L <= 208, "attention: sequence length must be in [1, 208]");
+  MSCLIP_REQUIRE(heads >= 1, "attention: heads must be positive");
+  if (L <= 64)
+    return causal ? launch_variant<64, 64, 1, true>(qkv, out, batch, L, heads, stream)
+                  : launch_variant<64, 64, 1, false>(qkv, out, batch, L, heads, stream);
+  if (L <= 80)
+    return causal ? launch_variant<80, 80, 1, true>(qkv, out, batch, L, heads, stream)
+                  : launch_variant<80, 80, 1, false>(qkv, out, batch, L, heads, stream);
+  return causal ? launch_variant<208, 112, 2, true>(qkv, out, batch, L, heads, stream)
+                : launch_variant<208, 112, 2, false>(qkv, out, batch, L, heads, stream);
+}
+
+}  // namespace msclip

@@ -1,0 +1,337 @@
+// HBM-bound row kernels of the MS-CLIP-S path: LayerNorm (M.py:204-219), token / image embedding
+// (M.py:3047-3048, 2418-2426), the lateral-adapter tail (M.py:1760-1777), EOT pooling
+// (M.py:3057-3060) and the final L2 normalisation (M.py:2982-2983, 3076-3077).
+// One warp owns one 768-wide row: 6 float4 per lane, statistics by warp shuffle in fp32, two-pass
+// (mean, then centred variance) exactly like the reference's (x-u).pow(2).mean().
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msclip {
+
+namespace {
+
+constexpr int kD = 768;
+constexpr int kVec = kD / 128;  // float4 per lane
+constexpr float kLnEps = 1e-12f;  // M.py:205
+constexpr int kRowsPerBlock = 8;  // 8 warps per CTA
+
+__device__ __forceinline__ void load_row(const float* __restrict__ src, int lane, float4 (&v)[kVec]) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) v[i] = s4[lane + 32 * i];
+}
+
+// in-register LayerNorm of one row held as 6 float4 per lane; returns normalised*w+b in place
+__device__ __forceinline__ void layer_norm_row(float4 (&v)[kVec], const float* __restrict__ w,
+                                               const float* __restrict__ b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    v[i].x -= mean;
+    v[i].y -= mean;
+    v[i].z -= mean;
+    v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kD) + kLnEps);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const float4 ww = __ldg(w4 + lane + 32 * i);
+    const float4 bb = __ldg(b4 + lane + 32 * i);
+    v[i].x = ww.x * (v[i].x * rstd) + bb.x;
+    v[i].y = ww.y * (v[i].y * rstd) + bb.y;
+    v[i].z = ww.z * (v[i].z * rstd) + bb.z;
+    v[i].w = ww.w * (v[i].w * rstd) + bb.w;
+  }
+}
+
+__device__ __forceinline__ void store_row_bf16(bf16* __restrict__ dst, int lane, const float4 (&v)[kVec]) {
+  uint2* d2 = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) d2[lane + 32 * i] = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+}
+__device__ __forceinline__ void store_row_f32(float* __restrict__ dst, int lane, const float4 (&v)[kVec]) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) d4[lane + 32 * i] = v[i];
+}
+
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+layernorm_bf16_kernel(const float* __restrict__ x, int row_stride, const float* __restrict__ w,
+                      const float* __restrict__ b, bf16* __restrict__ y, int rows) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
+       r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
+    const long long src = r * row_stride;
+    float4 v[kVec];
+    load_row(x + src * kD, lane, v);
+    layer_norm_row(v, w, b, lane);
+    store_row_bf16(y + r * kD, lane, v);
+  }
+}
+
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+eot_layernorm_bf16_kernel(const float* __restrict__ x, const int64_t* __restrict__ tok, int L,
+                          const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ y, int batch) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (r >= batch) return;
+  // argmax over the token ids, first occurrence on ties (torch.argmax, M.py:3059)
+  long long best = INT64_MIN;
+  int best_i = 0x7fffffff;
+  for (int j = lane; j < L; j += 32) {
+    const long long t = tok[static_cast<long long>(r) * L + j];
+    if (t > best) {
+      best = t;
+      best_i = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  float4 v[kVec];
+  load_row(x + (static_cast<long long>(r) * L + best_i) * kD, lane, v);
+  layer_norm_row(v, w, b, lane);
+  store_row_bf16(y + static_cast<long long>(r) * kD, lane, v);
+}
+
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+text_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb, const float* __restrict__ pos,
+                  float* __restrict__ x, long long rows, int L, int vocab, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
+       r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
+    long long t = tok[r];
+    if (t < 0 || t >= vocab) {  // nn.Embedding raises; we flag and clamp so the kernel stays in bounds
+      if (lane == 0) atomicExch(err, 1);
+      t = 0;
+    }
+    const int l = static_cast<int>(r % L);
+    float4 v[kVec], p[kVec];
+    load_row(emb + t * kD, lane, v);
+    load_row(pos + static_cast<long long>(l) * kD, lane, p);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      v[i].x += p[i].x;
+      v[i].y += p[i].y;
+      v[i].z += p[i].z;
+      v[i].w += p[i].w;
+    }
+    store_row_f32(x + r * kD, lane, v);
+  }
+}
+
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+image_embed_ln_pre_kernel(const float* __restrict__ grid, const float* __restrict__ cls, const float* __restrict__ pos,
+                          const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ x,
+                          long long rows, int L) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
+       r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
+    const long long bi = r / L;
+    const int l = static_cast<int>(r % L);
+    float4 v[kVec], p[kVec];
+    load_row(l == 0 ? cls : grid + (bi * (L - 1) + (l - 1)) * kD, lane, v);
+    load_row(pos + static_cast<long long>(l) * kD, lane, p);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      v[i].x += p[i].x;
+      v[i].y += p[i].y;
+      v[i].z += p[i].z;
+      v[i].w += p[i].w;
+    }
+    layer_norm_row(v, w, b, lane);
+    store_row_f32(x + r * kD, lane, v);
+  }
+}
+
+// dw_w9: [9][768] (BN scale folded), dw_bias: [768] (BN shift).  Tap (dy,dx) index = (dy+1)*3 + (dx+1).
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ dw_w9,
+                       const float* __restrict__ dw_bias, const float* __restrict__ w, const float* __restrict__ b,
+                       float* __restrict__ x_out, long long rows, int g) {
+  const int lane = threadIdx.x & 31;
+  const int L = g * g + 1;
+  for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
+       r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
+    const long long bi = r / L;
+    const int l = static_cast<int>(r % L);
+    float4 v[kVec];
+    if (l == 0) {
+      load_row(x + r * kD, lane, v);  // cls + cls (PRALLEL_T2B_USECLS, M.py:1770-1771)
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) {
+        v[i].x += v[i].x;
+        v[i].y += v[i].y;
+        v[i].z += v[i].z;
+        v[i].w += v[i].w;
+      }
+    } else {
+      const int gy = (l - 1) / g, gx = (l - 1) % g;
+      load_row(dw_bias, lane, v);
+#pragma unroll 1
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = gy + dy;
+        if (yy < 0 || yy >= g) continue;
+#pragma unroll 1
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = gx + dx;
+          if (xx < 0 || xx >= g) continue;
+          float4 a[kVec], k[kVec];
+          load_row(x + (bi * L + 1 + yy * g + xx) * kD, lane, a);
+          load_row(dw_w9 + ((dy + 1) * 3 + (dx + 1)) * kD, lane, k);
+#pragma unroll
+          for (int i = 0; i < kVec; ++i) {
+            v[i].x = fmaf(a[i].x, k[i].x, v[i].x);
+            v[i].y = fmaf(a[i].y, k[i].y, v[i].y);
+            v[i].z = fmaf(a[i].z, k[i].z, v[i].z);
+            v[i].w = fmaf(a[i].w, k[i].w, v[i].w);
+          }
+        }
+      }
+      float4 tt[kVec];
+      load_row(t + (bi * (L - 1) + (l - 1)) * kD, lane, tt);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) {
+        v[i].x += tt[i].x;
+        v[i].y += tt[i].y;
+        v[i].z += tt[i].z;
+        v[i].w += tt[i].w;
+      }
+    }
+    layer_norm_row(v, w, b, lane);
+    store_row_f32(x_out + r * kD, lane, v);
+  }
+}
+
+// one warp per row of width E (multiple of 4, <= 1024)
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+l2norm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int rows, int E,
+              int normalise) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * E);
+  const int n4 = E / 4;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < n4 ? x4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float inv = normalise ? 1.0f / sqrtf(warp_sum(s)) : 1.0f;  // no eps, like x / x.norm()
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + 32 * i;
+    if (c >= n4) continue;
+    const float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(r) * E)[c] = o;
+    if (out_bf16)
+      reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(r) * E)[c] =
+          make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+  }
+}
+
+inline int row_grid(long long rows) {
+  long long blocks = (rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  const long long cap = static_cast<long long>(num_sms()) * 16;  // grid-stride beyond 16 CTAs / SM
+  return static_cast<int>(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const float* b, bf16* y, int rows,
+                          cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  layernorm_bf16_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, row_stride, w, b, y, rows);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_eot_layernorm_bf16(const float* x, const int64_t* tok, int L, const float* w, const float* b, bf16* y,
+                              int batch, cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  eot_layernorm_bf16_kernel<<<(batch + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(
+      x, tok, L, w, b, y, batch);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int* token_error_flag() {
+  static int* flag = nullptr;
+  if (!flag) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+int launch_text_embed(const int64_t* tok, const float* tok_emb, const float* pos, float* x, int batch, int L,
+                      int vocab, cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  int* flag = token_error_flag();
+  MSCLIP_REQUIRE(flag != nullptr, "cudaMalloc of the token error flag failed");
+  const long long rows = static_cast<long long>(batch) * L;
+  text_embed_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(tok, tok_emb, pos, x, rows, L, vocab, flag);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int check_token_error(cudaStream_t stream) {
+  int* flag = token_error_flag();
+  if (!flag) return 0;
+  int h = 0;
+  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  MSCLIP_CHECK_CUDA(cudaStreamSynchronize(stream));
+  if (h) {
+    cudaMemsetAsync(flag, 0, sizeof(int), stream);
+    set_last_error("encode_text: token id out of range [0, vocab)");
+    return 3;
+  }
+  return 0;
+}
+
+int launch_image_embed_ln_pre(const float* grid, const float* cls, const float* pos, const float* w, const float* b,
+                              float* x, int batch, int L, cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  const long long rows = static_cast<long long>(batch) * L;
+  image_embed_ln_pre_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(grid, cls, pos, w, b, x, rows, L);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
+                           const float* b, float* x_out, int batch, int g, cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  MSCLIP_REQUIRE(x != x_out, "adapter tail cannot run in place (3x3 neighbourhood reads)");
+  const long long rows = static_cast<long long>(batch) * (g * g + 1);
+  adapter_fuse_ln_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, t, dw_w9, dw_bias, w, b, x_out, rows, g);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_l2norm(const float* x, float* out_f32, bf16* out_bf16, int rows, int E, int normalise,
+                  cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  MSCLIP_REQUIRE(E % 4 == 0 && E <= 1024, "l2norm: width must be a multiple of 4 and <= 1024");
+  l2norm_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(x, out_f32, out_bf16,
+                                                                                              rows, E, normalise);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace msclip

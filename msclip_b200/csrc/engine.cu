@@ -1,0 +1,967 @@
+// Engine implementation: state-dict intake and re-packing, workspace management, and the kernel
+// sequences of encode_image / encode_text / forward / contrastive loss.  See engine.h.
+#include "engine.h"
+
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+
+#include "common.cuh"
+
+using namespace msclip;
+
+namespace msclip {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches.fetch_add(n); }
+
+bool is_device_pointer(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ------------------------------------------------------------------------------------ state-dict spec
+static void spec_bn(msclip_ctx* h, const std::string& p, int64_t c) {
+  h->spec[p + ".weight"] = {c};
+  h->spec[p + ".bias"] = {c};
+  h->spec[p + ".running_mean"] = {c};
+  h->spec[p + ".running_var"] = {c};
+  h->spec[p + ".num_batches_tracked"] = {};
+}
+static void spec_ln(msclip_ctx* h, const std::string& p, int64_t c) {
+  h->spec[p + ".weight"] = {c};
+  h->spec[p + ".bias"] = {c};
+}
+static void spec_block(msclip_ctx* h, const std::string& p, int64_t w) {
+  h->spec[p + ".attn.in_proj_weight"] = {3 * w, w};
+  h->spec[p + ".attn.in_proj_bias"] = {3 * w};
+  h->spec[p + ".attn.out_proj.weight"] = {w, w};
+  h->spec[p + ".attn.out_proj.bias"] = {w};
+  spec_ln(h, p + ".ln_1", w);
+  h->spec[p + ".mlp.c_fc.weight"] = {4 * w, w};
+  h->spec[p + ".mlp.c_fc.bias"] = {4 * w};
+  h->spec[p + ".mlp.c_proj.weight"] = {w, 4 * w};
+  h->spec[p + ".mlp.c_proj.bias"] = {w};
+  spec_ln(h, p + ".ln_2", w);
+}
+
+// The reference's CLIP.state_dict() key set (checked against the key lists exported
+// from the reference itself, tests/golden/state_dict_keys_*.json).
+void build_spec(msclip_ctx* h) {
+  const msclip_config& c = h->cfg;
+  const int64_t w = c.width, e = c.embed_dim;
+  h->spec.clear();
+  h->spec["positional_embedding"] = {c.context_length, w};
+  h->spec["text_projection"] = {w, e};
+  h->spec["logit_scale"] = {};
+  const std::string v = "visual.";
+  h->spec[v + "class_embedding"] = {w};
+  h->spec[v + "positional_embedding"] = {h->l_img, w};
+  h->spec[v + "proj"] = {w, e};
+  spec_ln(h, v + "ln_pre", w);
+  const std::string s = v + "transformer.resblocks.0.";
+  const int64_t c0 = w / 16;
+  h->spec[s + "conv1.weight"] = {c0, 3, 3, 3};
+  spec_bn(h, s + "bn1", c0);
+  int64_t ch = c0;
+  for (int i = 0; i < 4; ++i) {
+    const std::string p = s + "resnet_stage.conv_" + std::to_string(i) + ".";
+    h->spec[p + "conv1.weight"] = {2 * ch, ch, 3, 3};
+    spec_bn(h, p + "bn1", 2 * ch);
+    h->spec[p + "downsample.0.weight"] = {2 * ch, ch, 1, 1};
+    spec_bn(h, p + "downsample.1", 2 * ch);
+    ch *= 2;
+  }
+  h->spec[s + "last_conv.weight"] = {w, w, 1, 1};
+  for (int i = 1; i < c.layers; ++i) spec_block(h, v + "transformer.resblocks." + std::to_string(i), w);
+  const std::string pb = v + "transformer.parallel_branch_v.";
+  h->spec[pb + "0.conv.weight"] = {c0, 3, 3, 3};
+  spec_bn(h, pb + "0.bn", c0);
+  const int64_t dims[5] = {w / 16, w / 8, w / 4, w / 2, w};
+  for (int j = 1; j < 5; ++j) {
+    const int64_t cin = dims[j - 1], cout = dims[j], mid = cout / 2;
+    const std::string p = pb + std::to_string(j) + ".resnet_stage.conv_0.";
+    h->spec[p + "conv1.weight"] = {mid, cin, 1, 1};
+    spec_bn(h, p + "bn1", mid);
+    h->spec[p + "conv2.weight"] = {mid, mid, 3, 3};
+    spec_bn(h, p + "bn2", mid);
+    h->spec[p + "conv3.weight"] = {cout, mid, 1, 1};
+    spec_bn(h, p + "bn3", cout);
+    h->spec[p + "residual_conv.weight"] = {cout, cin, 1, 1};
+    spec_bn(h, p + "residual_bn", cout);
+  }
+  const std::string la = v + "transformer.parallel_lateral_adapter.";
+  for (int j = 0; j < 5; ++j) {
+    const int64_t cj = dims[j], k = c.t2b_kernels[j];
+    const std::string p = la + std::to_string(j) + ".";
+    h->spec[p + "top2bottom_dw_conv.conv.weight"] = {cj, 1, k, k};
+    spec_bn(h, p + "top2bottom_dw_conv.bn", cj);
+    h->spec[p + "top2bottom_pw_conv.conv.weight"] = {w, cj, 1, 1};
+    h->spec[p + "bottom_dw_conv.conv.weight"] = {w, 1, 3, 3};
+    spec_bn(h, p + "bottom_dw_conv.bn", w);
+    spec_ln(h, p + "ln_adapt", w);
+  }
+  spec_ln(h, v + "ln_post", w);
+  for (int i = 0; i < c.layers; ++i) spec_block(h, "transformer.resblocks." + std::to_string(i), w);
+  h->spec["token_embedding.weight"] = {c.vocab_size, w};
+  spec_ln(h, "ln_final", w);
+}
+
+// ------------------------------------------------------------------------------------ packing helpers
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>((u + r) >> 16);
+}
+
+struct Packer {
+  msclip_ctx* h;
+  cudaStream_t stream;
+  int rc = 0;
+
+  void* dalloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      set_last_error("cudaMalloc of " + std::to_string(bytes) + " bytes for packed weights failed");
+      rc = 1;
+      return nullptr;
+    }
+    h->weight_allocs.push_back(p);
+    h->weight_bytes += bytes;
+    return p;
+  }
+  const RawTensor& raw(const std::string& k) { return h->raw.at(k); }
+  std::vector<float> host(const std::string& k) {
+    const RawTensor& t = raw(k);
+    std::vector<float> v(t.numel);
+    if (t.numel && cudaMemcpy(v.data(), t.dev, t.numel * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_last_error("D2H copy of " + k + " failed");
+      rc = 1;
+    }
+    return v;
+  }
+  float* up_f32(const std::vector<float>& v) {
+    float* d = static_cast<float*>(dalloc(std::max<size_t>(v.size(), 4) * 4));
+    if (d && cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1;
+    return d;
+  }
+  bf16* up_bf16(const std::vector<float>& v) {
+    std::vector<uint16_t> b(v.size());
+    for (size_t i = 0; i < v.size(); ++i) b[i] = f2bf(v[i]);
+    bf16* d = static_cast<bf16*>(dalloc(std::max<size_t>(b.size(), 8) * 2));
+    if (d && cudaMemcpy(d, b.data(), b.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1;
+    return d;
+  }
+  float* keep_f32(const std::string& k) {  // device-to-device copy of an fp32 tensor
+    const RawTensor& t = raw(k);
+    float* d = static_cast<float*>(dalloc(std::max<size_t>(t.numel, 4) * 4));
+    if (d && cudaMemcpyAsync(d, t.dev, t.numel * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) rc = 1;
+    return d;
+  }
+  // nn.Linear weight [N,K] -> bf16 [N,K]; optional per-row scale (device)
+  bf16* linear(const std::string& k, const float* row_scale) {
+    const RawTensor& t = raw(k);
+    const int N = static_cast<int>(t.shape[0]), K = static_cast<int>(t.shape[1]);
+    bf16* d = static_cast<bf16*>(dalloc(static_cast<size_t>(N) * K * 2));
+    if (d && launch_pack_bf16(t.dev, K, 1, row_scale, d, K, N, K, stream)) rc = 1;
+    return d;
+  }
+  // x @ P with P [K,N] -> stored transposed [N,K] so the GEMM sees a K-major B operand
+  bf16* transposed(const std::string& k) {
+    const RawTensor& t = raw(k);
+    const int K = static_cast<int>(t.shape[0]), N = static_cast<int>(t.shape[1]);
+    bf16* d = static_cast<bf16*>(dalloc(static_cast<size_t>(N) * K * 2));
+    if (d && launch_pack_bf16(t.dev, 1, N, nullptr, d, K, N, K, stream)) rc = 1;
+    return d;
+  }
+  // eval-mode BatchNorm as per-channel scale / shift
+  void bn(const std::string& p, float eps, std::vector<float>& scale, std::vector<float>& shift) {
+    const std::vector<float> g = host(p + ".weight"), b = host(p + ".bias"), m = host(p + ".running_mean"),
+                             v = host(p + ".running_var");
+    scale.resize(g.size());
+    shift.resize(g.size());
+    for (size_t i = 0; i < g.size(); ++i) {
+      scale[i] = g[i] / std::sqrt(v[i] + eps);
+      shift[i] = b[i] - m[i] * scale[i];
+    }
+  }
+  // conv weight [N,C,kh,kw] * scale[n] -> dst[n*ldk + koff + (ky*kw+kx)*C + c]
+  void conv_into(const std::string& k, const std::vector<float>& scale, std::vector<float>& dst, int ldk, int koff) {
+    const RawTensor& t = raw(k);
+    const std::vector<float> w = host(k);
+    const int N = static_cast<int>(t.shape[0]), C = static_cast<int>(t.shape[1]), kh = static_cast<int>(t.shape[2]),
+              kw = static_cast<int>(t.shape[3]);
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < C; ++c)
+        for (int y = 0; y < kh; ++y)
+          for (int x = 0; x < kw; ++x)
+            dst[static_cast<size_t>(n) * ldk + koff + (y * kw + x) * C + c] +=
+                w[((static_cast<size_t>(n) * C + c) * kh + y) * kw + x] * (scale.empty() ? 1.f : scale[n]);
+  }
+};
+
+static void pack_block(Packer& P, const std::string& p, BlockWeights& bw, const float* qscale_dev,
+                       const BlockWeights* share_from) {
+  const std::string& shared_p = p;
+  const int w = P.h->cfg.width;
+  if (share_from) {  // text blocks 1.. alias the vision block's attention / MLP parameters (M.py:2808-2830)
+    bw = *share_from;
+  } else {
+    bw.w_qkv = P.linear(shared_p + ".attn.in_proj_weight", qscale_dev);
+    std::vector<float> b = P.host(shared_p + ".attn.in_proj_bias");
+    for (int i = 0; i < w; ++i) b[i] *= 0.125f;  // q = (x W_q^T + b_q) * 64^-0.5 (M.py:612, 707)
+    bw.b_qkv = P.up_f32(b);
+    bw.w_o = P.linear(shared_p + ".attn.out_proj.weight", nullptr);
+    bw.b_o = P.keep_f32(shared_p + ".attn.out_proj.bias");
+    bw.w_fc1 = P.linear(shared_p + ".mlp.c_fc.weight", nullptr);
+    bw.b_fc1 = P.keep_f32(shared_p + ".mlp.c_fc.bias");
+    bw.w_fc2 = P.linear(shared_p + ".mlp.c_proj.weight", nullptr);
+    bw.b_fc2 = P.keep_f32(shared_p + ".mlp.c_proj.bias");
+  }
+  bw.ln1_w = P.keep_f32(p + ".ln_1.weight");
+  bw.ln1_b = P.keep_f32(p + ".ln_1.bias");
+  bw.ln2_w = P.keep_f32(p + ".ln_2.weight");
+  bw.ln2_b = P.keep_f32(p + ".ln_2.bias");
+}
+
+int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
+  for (const auto& kv : h->spec)
+    MSCLIP_REQUIRE(h->raw.count(kv.first) == 1, "finalize_weights: missing state-dict key " + kv.first);
+  for (void* p : h->weight_allocs) cudaFree(p);
+  h->weight_allocs.clear();
+  h->weight_bytes = 0;
+  const msclip_config& c = h->cfg;
+  const int w = c.width;
+  Packer P{h, stream};
+
+  {
+    std::vector<float> ls = P.host("logit_scale");
+    h->logit_scale = ls.empty() ? 0.f : ls[0];
+  }
+  std::vector<float> qs(3 * w, 1.0f);
+  for (int i = 0; i < w; ++i) qs[i] = 0.125f;
+  float* qscale = P.up_f32(qs);
+
+  // ---- transformer blocks
+  h->vblocks.assign(c.layers, BlockWeights());
+  h->tblocks.assign(c.layers, BlockWeights());
+  for (int i = 1; i < c.layers; ++i) {
+    const std::string p = "visual.transformer.resblocks." + std::to_string(i);
+    pack_block(P, p, h->vblocks[i], qscale, nullptr);
+  }
+  for (int i = 0; i < c.layers; ++i) {
+    const std::string p = "transformer.resblocks." + std::to_string(i);
+    pack_block(P, p, h->tblocks[i], qscale, i >= 1 ? &h->vblocks[i] : nullptr);
+  }
+  // ---- embeddings, final LayerNorms, projections
+  h->cls = P.keep_f32("visual.class_embedding");
+  h->vpos = P.keep_f32("visual.positional_embedding");
+  h->ln_pre_w = P.keep_f32("visual.ln_pre.weight");
+  h->ln_pre_b = P.keep_f32("visual.ln_pre.bias");
+  h->ln_post_w = P.keep_f32("visual.ln_post.weight");
+  h->ln_post_b = P.keep_f32("visual.ln_post.bias");
+  h->vproj = P.transposed("visual.proj");
+  h->tok_emb = P.keep_f32("token_embedding.weight");
+  h->tpos = P.keep_f32("positional_embedding");
+  h->ln_final_w = P.keep_f32("ln_final.weight");
+  h->ln_final_b = P.keep_f32("ln_final.bias");
+  h->tproj = P.transposed("text_projection");
+
+  // ---- first convs of the stem and of the parallel branch share one im2col: N = 48 + 48, K = 27 -> 32
+  const int c0 = w / 16;
+  {
+    std::vector<float> sc, sh, W(static_cast<size_t>(2 * c0) * 32, 0.f), B(2 * c0);
+    const char* keys[2] = {"visual.transformer.resblocks.0.conv1.weight",
+                           "visual.transformer.parallel_branch_v.0.conv.weight"};
+    const char* bns[2] = {"visual.transformer.resblocks.0.bn1", "visual.transformer.parallel_branch_v.0.bn"};
+    for (int t = 0; t < 2; ++t) {
+      P.bn(bns[t], 1e-5f, sc, sh);
+      const std::vector<float> wt = P.host(keys[t]);  // [c0, 3, 3, 3]: k = c*9 + ky*3 + kx is the natural order
+      for (int n = 0; n < c0; ++n) {
+        for (int k = 0; k < 27; ++k) W[static_cast<size_t>(t * c0 + n) * 32 + k] = wt[n * 27 + k] * sc[n];
+        B[t * c0 + n] = sh[n];
+      }
+    }
+    h->first.w = P.up_bf16(W);
+    h->first.b = P.up_f32(B);
+    h->first.N = 2 * c0;
+    h->first.K = 32;
+  }
+  // ---- stem stages: BN(conv3x3_s(x)) + BN(conv1x1_s(x)) == one 3x3 conv (the 1x1 stride-s tap is the
+  //      centre tap of the 3x3 stride-s pad-1 window), M.py:1920-1936
+  {
+    int ch = c0;
+    for (int i = 0; i < 4; ++i) {
+      const std::string p = "visual.transformer.resblocks.0.resnet_stage.conv_" + std::to_string(i) + ".";
+      std::vector<float> s3, b3, s1, b1;
+      P.bn(p + "bn1", 1e-5f, s3, b3);
+      P.bn(p + "downsample.1", 1e-5f, s1, b1);
+      const int N = 2 * ch, K = 9 * ch;
+      std::vector<float> W(static_cast<size_t>(N) * K, 0.f), B(N);
+      P.conv_into(p + "conv1.weight", s3, W, K, 0);
+      P.conv_into(p + "downsample.0.weight", s1, W, K, 4 * ch);  // centre tap (ky = kx = 1)
+      for (int n = 0; n < N; ++n) B[n] = b3[n] + b1[n];
+      h->stem[i].w = P.up_bf16(W);
+      h->stem[i].b = P.up_f32(B);
+      h->stem[i].N = N;
+      h->stem[i].K = K;
+      ch *= 2;
+    }
+    std::vector<float> W(static_cast<size_t>(w) * w, 0.f);
+    P.conv_into("visual.transformer.resblocks.0.last_conv.weight", {}, W, w, 0);
+    h->last_conv.w = P.up_bf16(W);
+    h->last_conv.b = nullptr;
+    h->last_conv.N = w;
+    h->last_conv.K = w;
+  }
+  // ---- parallel-branch bottlenecks (ConvResBlock, BN eps 1e-6, M.py:1825-1861)
+  const int dims[5] = {w / 16, w / 8, w / 4, w / 2, w};
+  for (int j = 1; j < 5; ++j) {
+    const int cin = dims[j - 1], cout = dims[j], mid = cout / 2;
+    const std::string p = "visual.transformer.parallel_branch_v." + std::to_string(j) + ".resnet_stage.conv_0.";
+    std::vector<float> sc, sh, sc2, sh2;
+    {
+      P.bn(p + "bn1", 1e-6f, sc, sh);
+      std::vector<float> W(static_cast<size_t>(mid) * cin, 0.f);
+      P.conv_into(p + "conv1.weight", sc, W, cin, 0);
+      h->br1[j] = {P.up_bf16(W), P.up_f32(sh), mid, cin};
+    }
+    {
+      P.bn(p + "bn2", 1e-6f, sc, sh);
+      std::vector<float> W(static_cast<size_t>(mid) * 9 * mid, 0.f);
+      P.conv_into(p + "conv2.weight", sc, W, 9 * mid, 0);
+      h->br2[j] = {P.up_bf16(W), P.up_f32(sh), mid, 9 * mid};
+    }
+    {  // conv3 on the main path and the strided 1x1 shortcut become one GEMM over K = [y2 | x_strided]
+      P.bn(p + "bn3", 1e-6f, sc, sh);
+      P.bn(p + "residual_bn", 1e-6f, sc2, sh2);
+      const int K = mid + cin;
+      std::vector<float> W(static_cast<size_t>(cout) * K, 0.f), B(cout);
+      P.conv_into(p + "conv3.weight", sc, W, K, 0);
+      P.conv_into(p + "residual_conv.weight", sc2, W, K, mid);
+      for (int n = 0; n < cout; ++n) B[n] = sh[n] + sh2[n];
+      h->br3[j] = {P.up_bf16(W), P.up_f32(B), cout, K};
+    }
+  }
+  // ---- lateral adapters (M.py:1556-1637)
+  for (int j = 0; j < 5; ++j) {
+    const std::string p = "visual.transformer.parallel_lateral_adapter." + std::to_string(j) + ".";
+    AdapterWeights& a = h->adapters[j];
+    a.C = dims[j];
+    a.k = c.t2b_kernels[j];
+    std::vector<float> sc, sh;
+    P.bn(p + "top2bottom_dw_conv.bn", 1e-5f, sc, sh);
+    {
+      const std::vector<float> wt = P.host(p + "top2bottom_dw_conv.conv.weight");  // [C,1,k,k]
+      std::vector<float> W(static_cast<size_t>(a.k) * a.k * a.C);
+      for (int ch = 0; ch < a.C; ++ch)
+        for (int t = 0; t < a.k * a.k; ++t) W[static_cast<size_t>(t) * a.C + ch] = wt[static_cast<size_t>(ch) * a.k * a.k + t] * sc[ch];
+      a.dw_w = P.up_f32(W);
+      a.dw_b = P.up_f32(sh);
+    }
+    {
+      std::vector<float> W(static_cast<size_t>(w) * a.C, 0.f);
+      P.conv_into(p + "top2bottom_pw_conv.conv.weight", {}, W, a.C, 0);
+      a.pw = P.up_bf16(W);
+    }
+    P.bn(p + "bottom_dw_conv.bn", 1e-5f, sc, sh);
+    {
+      const std::vector<float> wt = P.host(p + "bottom_dw_conv.conv.weight");  // [768,1,3,3]
+      std::vector<float> W(static_cast<size_t>(9) * w);
+      for (int ch = 0; ch < w; ++ch)
+        for (int t = 0; t < 9; ++t) W[static_cast<size_t>(t) * w + ch] = wt[static_cast<size_t>(ch) * 9 + t] * sc[ch];
+      a.bdw_w9 = P.up_f32(W);
+      a.bdw_b = P.up_f32(sh);
+    }
+    a.ln_w = P.keep_f32(p + "ln_adapt.weight");
+    a.ln_b = P.keep_f32(p + "ln_adapt.bias");
+  }
+  MSCLIP_CHECK_CUDA(cudaStreamSynchronize(stream));
+  if (P.rc) return P.rc;
+  for (auto& kv : h->raw) cudaFree(kv.second.dev);
+  h->raw.clear();
+  h->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ workspace
+static int ws_get(msclip_ctx* h, const char* name, size_t bytes, void** out) {
+  DevBuf& b = h->ws[name];
+  if (b.bytes < bytes) {
+    if (b.p) {
+      MSCLIP_CHECK_CUDA(cudaDeviceSynchronize());  // growth only: nobody may still be reading the old buffer
+      cudaFree(b.p);
+      h->ws_bytes -= b.bytes;
+      b.p = nullptr;
+      b.bytes = 0;
+    }
+    const size_t want = (bytes + 255) & ~size_t(255);
+    if (cudaMalloc(&b.p, want) != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error(std::string("workspace allocation failed for ") + name + " (" + std::to_string(want) + " bytes)");
+      return 1;
+    }
+    b.bytes = want;
+    h->ws_bytes += want;
+  }
+  *out = b.p;
+  return 0;
+}
+#define WS(var, type, name, count) \
+  type* var = nullptr;             \
+  MSCLIP_TRY(ws_get(h, name, static_cast<size_t>(count) * sizeof(type), reinterpret_cast<void**>(&var)))
+
+static int ensure_streams(msclip_ctx* h) {
+  if (!h->copy_stream) {
+    MSCLIP_CHECK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    MSCLIP_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    MSCLIP_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+static int require_ready(msclip_ctx* h) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  MSCLIP_REQUIRE(h->finalized, "weights are not finalized (call msclip_set_weight for every key, then msclip_finalize_weights)");
+  return 0;
+}
+
+// exchange buffer layout helpers ------------------------------------------------------------------------
+static size_t xchg_feat_bytes(const msclip_ctx* h) { return static_cast<size_t>(h->max_b_local) * h->cfg.embed_dim * 2; }
+static bf16* xchg_slot(const msclip_ctx* h, void* base, int parity, int modality) {
+  return reinterpret_cast<bf16*>(static_cast<uint8_t*>(base) + (parity * 2 + modality) * xchg_feat_bytes(h));
+}
+static uint32_t* xchg_flags(const msclip_ctx* h, void* base) {
+  return reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(base) + 4 * xchg_feat_bytes(h));
+}
+
+static int upload_tables(msclip_ctx* h) {
+  const int W = h->world;
+  std::vector<void*> t(static_cast<size_t>(4) * W + W);
+  for (int par = 0; par < 2; ++par)
+    for (int mod = 0; mod < 2; ++mod)
+      for (int r = 0; r < W; ++r) t[(par * 2 + mod) * W + r] = xchg_slot(h, h->peer_base[r], par, mod);
+  for (int r = 0; r < W; ++r) t[4 * W + r] = xchg_flags(h, h->peer_base[r]);
+  if (h->shard_tables) cudaFree(h->shard_tables);
+  MSCLIP_CHECK_CUDA(cudaMalloc(&h->shard_tables, t.size() * sizeof(void*)));
+  MSCLIP_CHECK_CUDA(cudaMemcpy(h->shard_tables, t.data(), t.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  h->peer_flag_tables = reinterpret_cast<uint32_t**>(static_cast<void**>(h->shard_tables) + 4 * W);
+  return 0;
+}
+
+int comm_init(msclip_ctx* h, int rank, int world, int max_b_local) {
+  MSCLIP_REQUIRE(world >= 1 && rank >= 0 && rank < world && max_b_local >= 1, "comm_init: bad rank/world/batch");
+  if (h->xchg) {
+    MSCLIP_CHECK_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < static_cast<int>(h->peer_base.size()); ++r)
+      if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    cudaFree(h->xchg);
+    h->xchg = nullptr;
+  }
+  h->rank = rank;
+  h->world = world;
+  h->max_b_local = max_b_local;
+  h->xchg_bytes = 4 * xchg_feat_bytes(h) + 256;
+  MSCLIP_CHECK_CUDA(cudaMalloc(&h->xchg, h->xchg_bytes));
+  MSCLIP_CHECK_CUDA(cudaMemset(h->xchg, 0, h->xchg_bytes));
+  h->peer_base.assign(world, nullptr);
+  h->peer_base[rank] = h->xchg;
+  h->epoch = 0;
+  h->last_img_batch = h->last_txt_batch = -1;
+  if (world == 1) MSCLIP_TRY(upload_tables(h));
+  return 0;
+}
+
+int comm_export(msclip_ctx* h, void* handle_out) {
+  MSCLIP_REQUIRE(h->xchg != nullptr, "comm_export: call msclip_comm_init first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  MSCLIP_CHECK_CUDA(cudaIpcGetMemHandle(&hd, h->xchg));
+  memcpy(handle_out, &hd, 64);
+  return 0;
+}
+
+int comm_import(msclip_ctx* h, const void* handles) {
+  MSCLIP_REQUIRE(h->xchg != nullptr, "comm_import: call msclip_comm_init first");
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) continue;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const uint8_t*>(handles) + 64 * r, 64);
+    void* p = nullptr;
+    MSCLIP_CHECK_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_base[r] = p;
+  }
+  return upload_tables(h);
+}
+
+// world == 1 needs no msclip_comm_* calls: the exchange buffer is created (and grown) on demand
+static int ensure_xchg(msclip_ctx* h, int batch) {
+  if (h->xchg == nullptr || (h->world == 1 && batch > h->max_b_local)) return comm_init(h, 0, 1, std::max(batch, 256));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ shared block
+static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, bf16* hbuf,
+                     bf16* qkv, bf16* attn, bf16* fc1, cudaStream_t s) {
+  const int w = h->cfg.width;
+  const int M = batch * L;
+  MSCLIP_TRY(launch_layernorm_bf16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
+  MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, qkv, 3 * w, nullptr, 0, EPI_BF16, s));
+  MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
+  MSCLIP_TRY(launch_gemm(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, x, w, EPI_RESID_F32, s));
+  MSCLIP_TRY(launch_layernorm_bf16(x, 1, bw.ln2_w, bw.ln2_b, hbuf, M, s));
+  MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
+  MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, x, w, EPI_RESID_F32, s));
+  count_launch(7);
+  return 0;
+}
+
+static const int kLateral[5] = {2, 4, 6, 8, 10};  // PARALLEL_LATERAL_LAYER, b32-yfcc-msclips.yaml:18
+static const int kConvChunk = 256;                 // images per pass through the conv stages
+static const int kTowerChunk = 4096;               // sequences per pass through the transformer
+
+// image tower for `batch` images already on the device; feat_bf16 (optional) receives the bf16 copy of
+// the normalised features for the loss kernel
+static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, float* out_dev, int normalize,
+                        bf16* feat_bf16, cudaStream_t s) {
+  const msclip_config& c = h->cfg;
+  const int w = c.width, R = c.image_resolution, g = h->grid, L = h->l_img, c0 = w / 16;
+  const int H1 = R / 2;
+  const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
+  int n_active = 0;
+  for (int j = 0; j < 5; ++j)
+    if (kLateral[j] < c.layers) n_active = j + 1;
+  const int dims[5] = {w / 16, w / 8, w / 4, w / 2, w};
+  const int nbmax = std::min(batch, kConvChunk);
+  const size_t px1 = static_cast<size_t>(H1) * H1;  // pixels after the first conv
+
+  WS(col0, bf16, "col0", nbmax * px1 * 32);
+  WS(a1, bf16, "a1", nbmax * px1 * 2 * c0);
+  // largest im2col matrix and activation of the later stages (stage 0 of the stem dominates)
+  size_t col_max = 0, act_max = 0;
+  {
+    int Hc = H1, ch = c0;
+    for (int i = 0; i < 4; ++i) {
+      const int Ho = Hc / c.early_strides[i];
+      col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * 9 * ch);
+      act_max = std::max(act_max, static_cast<size_t>(Ho) * Ho * 2 * ch);
+      Hc = Ho;
+      ch *= 2;
+    }
+    Hc = H1;
+    for (int j = 1; j < 5; ++j) {
+      const int cin = dims[j - 1];
+      const int Ho = Hc / c.parallel_strides[j];
+      col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * 9 * cin);
+      act_max = std::max(act_max, static_cast<size_t>(Hc) * Hc * cin);       // y1
+      act_max = std::max(act_max, static_cast<size_t>(Ho) * Ho * 2 * cin);   // cat / p_j
+      Hc = Ho;
+    }
+  }
+  WS(col, bf16, "col", nbmax * col_max);
+  WS(actA, bf16, "actA", nbmax * act_max);
+  WS(actB, bf16, "actB", nbmax * act_max);
+  WS(actC, bf16, "actC", nbmax * act_max);
+  WS(gridtmp, float, "gridtmp", static_cast<size_t>(batch) * g * g * w);
+  bf16* pooled[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int j = 0; j < n_active; ++j) {
+    const std::string nm = "pooled" + std::to_string(j);
+    MSCLIP_TRY(ws_get(h, nm.c_str(), static_cast<size_t>(batch) * g * g * dims[j] * 2, reinterpret_cast<void**>(&pooled[j])));
+  }
+
+  for (int b0 = 0; b0 < batch; b0 += kConvChunk) {
+    const int nb = std::min(kConvChunk, batch - b0);
+    const uint8_t* img_c = static_cast<const uint8_t*>(img) + static_cast<size_t>(b0) * 3 * R * R * esz;
+    // first convs (stem conv1+bn1+ReLU, M.py:1993 | branch stage 0, M.py:2260-2273): one GEMM, N = 48 + 48
+    MSCLIP_TRY(launch_im2col_first(img_c, dtype, col0, nb, R, R, s));
+    MSCLIP_TRY(launch_gemm(col0, 32, h->first.w, 32, static_cast<int>(nb * px1), 2 * c0, 32, h->first.b, a1, 2 * c0,
+                           nullptr, 0, EPI_RELU_BF16, s));
+    count_launch(2);
+    // ---- stem: 4 residual stride blocks, then the 1x1 last_conv (M.py:1995-2000)
+    {
+      const bf16* cur = a1;
+      int cpix = 2 * c0, ch = c0, Hc = H1;
+      bf16* outs[2] = {actA, actB};
+      for (int i = 0; i < 4; ++i) {
+        const int st = c.early_strides[i], Ho = Hc / st;
+        MSCLIP_TRY(launch_im2col_nhwc(cur, nb, Hc, Hc, cpix, 0, ch, 3, st, 1, col, 9 * ch, 0, s));
+        bf16* o = outs[i & 1];
+        MSCLIP_TRY(launch_gemm(col, 9 * ch, h->stem[i].w, 9 * ch, nb * Ho * Ho, 2 * ch, 9 * ch, h->stem[i].b, o, 2 * ch,
+                               nullptr, 0, EPI_RELU_BF16, s));
+        count_launch(2);
+        cur = o;
+        cpix = 2 * ch;
+        ch *= 2;
+        Hc = Ho;
+      }
+      MSCLIP_REQUIRE(Hc == g && ch == w, "stem output does not land on the token grid");
+      MSCLIP_TRY(launch_gemm(cur, w, h->last_conv.w, w, nb * g * g, w, w, nullptr,
+                             gridtmp + static_cast<size_t>(b0) * g * g * w, w, nullptr, 0, EPI_F32, s));
+      count_launch(1);
+    }
+    // ---- parallel branch (M.py:2436-2442) -> only the patch-pooled features the adapters need are kept
+    if (n_active > 0) {
+      const bf16* p = a1;
+      int cpix = 2 * c0, coff = c0, Hc = H1;
+      MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, coff, dims[0], h->adapters[0].k, h->adapters[0].dw_w,
+                                   h->adapters[0].dw_b, pooled[0] + static_cast<size_t>(b0) * g * g * dims[0], s));
+      count_launch(1);
+      bf16* pbuf[2] = {actA, actB};
+      for (int j = 1; j < n_active; ++j) {
+        const int cin = dims[j - 1], st = c.parallel_strides[j], Ho = Hc / st;
+        // y1 = relu(bn1(conv1x1(p)))
+        MSCLIP_TRY(launch_gemm(p + coff, cpix, h->br1[j].w, cin, nb * Hc * Hc, cin, cin, h->br1[j].b, actC, cin, nullptr,
+                               0, EPI_RELU_BF16, s));
+        // y2 = relu(bn2(conv3x3_s(y1)))  -> columns [0, cin) of the concatenated operand
+        MSCLIP_TRY(launch_im2col_nhwc(actC, nb, Hc, Hc, cin, 0, cin, 3, st, 1, col, 9 * cin, 0, s));
+        bf16* cat = actC;  // y1 is dead once its im2col exists
+        MSCLIP_TRY(launch_gemm(col, 9 * cin, h->br2[j].w, 9 * cin, nb * Ho * Ho, cin, 9 * cin, h->br2[j].b, cat, 2 * cin,
+                               nullptr, 0, EPI_RELU_BF16, s));
+        // strided shortcut input -> columns [cin, 2cin)
+        MSCLIP_TRY(launch_im2col_nhwc(p, nb, Hc, Hc, cpix, coff, cin, 1, st, 0, cat, 2 * cin, cin, s));
+        // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p)))
+        bf16* pn = pbuf[j & 1];
+        MSCLIP_TRY(launch_gemm(cat, 2 * cin, h->br3[j].w, 2 * cin, nb * Ho * Ho, 2 * cin, 2 * cin, h->br3[j].b, pn,
+                               2 * cin, nullptr, 0, EPI_RELU_BF16, s));
+        p = pn;
+        cpix = 2 * cin;
+        coff = 0;
+        Hc = Ho;
+        MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, 0, dims[j], h->adapters[j].k, h->adapters[j].dw_w,
+                                     h->adapters[j].dw_b, pooled[j] + static_cast<size_t>(b0) * g * g * dims[j], s));
+        count_launch(6);
+      }
+    }
+  }
+
+  // ---- tokens + transformer, in chunks of sequences
+  const int tb = std::min(batch, kTowerChunk);
+  const size_t Mmax = static_cast<size_t>(tb) * std::max(L, c.context_length);
+  WS(x, float, "x", Mmax * w);
+  WS(x2, float, "x2", Mmax * w);
+  WS(hbuf, bf16, "h", Mmax * w);
+  WS(qkv, bf16, "qkv", Mmax * 3 * w);
+  WS(attn, bf16, "attn", Mmax * w);
+  WS(fc1, bf16, "fc1", Mmax * 4 * w);
+  WS(pool_ln, bf16, "pool_ln", static_cast<size_t>(tb) * w);
+  WS(feat_raw, float, "feat_raw", static_cast<size_t>(tb) * c.embed_dim);
+  for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
+    const int nb = std::min(kTowerChunk, batch - b0);
+    float* xc = x;
+    float* xo = x2;
+    float* gt = gridtmp + static_cast<size_t>(b0) * g * g * w;
+    MSCLIP_TRY(launch_image_embed_ln_pre(gt, h->cls, h->vpos, h->ln_pre_w, h->ln_pre_b, xc, nb, L, s));
+    count_launch(1);
+    for (int idx = 1; idx < c.layers; ++idx) {
+      for (int j = 0; j < n_active; ++j) {
+        if (kLateral[j] != idx) continue;
+        const AdapterWeights& a = h->adapters[j];
+        // t = pw_conv(BN(dw_conv(top)))  (M.py:1756-1759); the stem output in gridtmp is dead by now
+        MSCLIP_TRY(launch_gemm(pooled[j] + static_cast<size_t>(b0) * g * g * a.C, a.C, a.pw, a.C, nb * g * g, w, a.C,
+                               nullptr, gt, w, nullptr, 0, EPI_F32, s));
+        MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, s));
+        count_launch(2);
+        std::swap(xc, xo);
+      }
+      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, s));
+    }
+    // CLS -> ln_post -> proj -> L2 norm (M.py:2685-2690, 2982-2983)
+    MSCLIP_TRY(launch_layernorm_bf16(xc, L, h->ln_post_w, h->ln_post_b, pool_ln, nb, s));
+    MSCLIP_TRY(launch_gemm(pool_ln, w, h->vproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
+                           EPI_F32, s));
+    MSCLIP_TRY(launch_l2norm(feat_raw, out_dev + static_cast<size_t>(b0) * c.embed_dim,
+                             feat_bf16 ? feat_bf16 + static_cast<size_t>(b0) * c.embed_dim : nullptr, nb, c.embed_dim,
+                             normalize, s));
+    count_launch(3);
+  }
+  return 0;
+}
+
+static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_dev, int normalize, bf16* feat_bf16,
+                      cudaStream_t s) {
+  const msclip_config& c = h->cfg;
+  const int w = c.width, L = c.context_length;
+  const int tb = std::min(batch, kTowerChunk);
+  const size_t Mmax = static_cast<size_t>(tb) * std::max(h->l_img, L);
+  WS(x, float, "x", Mmax * w);
+  WS(hbuf, bf16, "h", Mmax * w);
+  WS(qkv, bf16, "qkv", Mmax * 3 * w);
+  WS(attn, bf16, "attn", Mmax * w);
+  WS(fc1, bf16, "fc1", Mmax * 4 * w);
+  WS(pool_ln, bf16, "pool_ln", static_cast<size_t>(tb) * w);
+  WS(feat_raw, float, "feat_raw", static_cast<size_t>(tb) * c.embed_dim);
+  for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
+    const int nb = std::min(kTowerChunk, batch - b0);
+    const int64_t* tk = tok + static_cast<size_t>(b0) * L;
+    MSCLIP_TRY(launch_text_embed(tk, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, s));
+    count_launch(1);
+    for (int idx = 0; idx < c.layers; ++idx) MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, s));
+    MSCLIP_TRY(launch_eot_layernorm_bf16(x, tk, L, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
+    MSCLIP_TRY(launch_gemm(pool_ln, w, h->tproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
+                           EPI_F32, s));
+    MSCLIP_TRY(launch_l2norm(feat_raw, out_dev + static_cast<size_t>(b0) * c.embed_dim,
+                             feat_bf16 ? feat_bf16 + static_cast<size_t>(b0) * c.embed_dim : nullptr, nb, c.embed_dim,
+                             normalize, s));
+    count_launch(3);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ public operations
+// parity of the exchange buffer the *next* loss call will read
+static int next_parity(const msclip_ctx* h) { return static_cast<int>((h->epoch + 1) & 1); }
+
+int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, float* out, int normalize,
+                        cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  MSCLIP_REQUIRE(batch >= 0 && image != nullptr && out != nullptr, "encode_image: bad arguments");
+  MSCLIP_REQUIRE(dtype == MSCLIP_F32 || dtype == MSCLIP_BF16 || dtype == MSCLIP_F16, "encode_image: unsupported image dtype");
+  if (batch == 0) return 0;
+  MSCLIP_TRY(ensure_streams(h));
+  const msclip_config& c = h->cfg;
+  const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
+  const size_t img_bytes = static_cast<size_t>(batch) * 3 * c.image_resolution * c.image_resolution * esz;
+  const void* img_dev = image;
+  if (!is_device_pointer(image)) {
+    // host input: stage on the copy stream so the transfer overlaps whatever the compute stream is doing
+    WS(stage, uint8_t, "img_stage", img_bytes);
+    MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_main, s));
+    MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(stage, image, img_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_copy, h->copy_stream));
+    MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_copy, 0));
+    img_dev = stage;
+  }
+  const bool out_dev_ptr = is_device_pointer(out);
+  float* out_dev = out;
+  if (!out_dev_ptr) {
+    WS(o, float, "img_out", static_cast<size_t>(batch) * c.embed_dim);
+    out_dev = o;
+  }
+  bf16* fb = nullptr;
+  if (normalize) {
+    MSCLIP_TRY(ensure_xchg(h, batch));
+    if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 0);
+  }
+  MSCLIP_TRY(vision_tower(h, img_dev, dtype, batch, out_dev, normalize, fb, s));
+  h->last_img_batch = fb ? batch : -1;
+  if (!out_dev_ptr) {
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(batch) * c.embed_dim * 4, cudaMemcpyDeviceToHost, s));
+    MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  MSCLIP_REQUIRE(batch >= 0 && tokens != nullptr && out != nullptr, "encode_text: bad arguments");
+  if (batch == 0) return 0;
+  const msclip_config& c = h->cfg;
+  const int64_t* tok_dev = tokens;
+  if (!is_device_pointer(tokens)) {
+    WS(stage, int64_t, "tok_stage", static_cast<size_t>(batch) * c.context_length);
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(stage, tokens, static_cast<size_t>(batch) * c.context_length * 8, cudaMemcpyHostToDevice, s));
+    tok_dev = stage;
+  }
+  const bool out_dev_ptr = is_device_pointer(out);
+  float* out_dev = out;
+  if (!out_dev_ptr) {
+    WS(o, float, "txt_out", static_cast<size_t>(batch) * c.embed_dim);
+    out_dev = o;
+  }
+  bf16* fb = nullptr;
+  if (normalize) {
+    MSCLIP_TRY(ensure_xchg(h, batch));
+    if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 1);
+  }
+  MSCLIP_TRY(text_tower(h, tok_dev, batch, out_dev, normalize, fb, s));
+  h->last_txt_batch = fb ? batch : -1;
+  if (!out_dev_ptr) {
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(batch) * c.embed_dim * 4, cudaMemcpyDeviceToHost, s));
+    MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+    MSCLIP_TRY(check_token_error(s));
+  }
+  return 0;
+}
+
+// split-bf16 operands: [hi | hi | lo] . [hi | lo | hi]^T = hi.hi + hi.lo + lo.hi  (fp32-grade similarity
+// on the bf16 tensor cores; the lo.lo term is below fp32 rounding)
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long rows, int E, int role) {
+  const long long total = rows * E;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long r = i / E;
+    const int k = static_cast<int>(i % E);
+    const float v = x[i];
+    const bf16 hi = __float2bfloat16_rn(v);
+    const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    bf16* o = out + r * 3 * E;
+    o[k] = hi;
+    o[E + k] = role == 0 ? hi : lo;
+    o[2 * E + k] = role == 0 ? lo : hi;
+  }
+}
+
+int engine_similarity_logits(msclip_ctx* h, const float* img, int n_img, const float* txt, int n_txt, float scale,
+                             float* logits, cudaStream_t s) {
+  MSCLIP_REQUIRE(h != nullptr && img && txt && logits && n_img >= 0 && n_txt >= 0, "similarity_logits: bad arguments");
+  if (n_img == 0 || n_txt == 0) return 0;
+  const int E = h->cfg.embed_dim;
+  const float* a = img;
+  const float* b = txt;
+  if (!is_device_pointer(img)) {
+    WS(sa, float, "sim_a_in", static_cast<size_t>(n_img) * E);
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(sa, img, static_cast<size_t>(n_img) * E * 4, cudaMemcpyHostToDevice, s));
+    a = sa;
+  }
+  if (!is_device_pointer(txt)) {
+    WS(sb, float, "sim_b_in", static_cast<size_t>(n_txt) * E);
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(sb, txt, static_cast<size_t>(n_txt) * E * 4, cudaMemcpyHostToDevice, s));
+    b = sb;
+  }
+  WS(a3, bf16, "sim_a", static_cast<size_t>(n_img) * 3 * E);
+  WS(b3, bf16, "sim_b", static_cast<size_t>(n_txt) * 3 * E);
+  const bool out_dev_ptr = is_device_pointer(logits);
+  float* o = logits;
+  if (!out_dev_ptr) {
+    WS(lo, float, "sim_out", static_cast<size_t>(n_img) * n_txt);
+    o = lo;
+  }
+  auto grid_for = [](long long total) {
+    long long blocks = (total + 255) / 256;
+    return static_cast<int>(std::min<long long>(blocks, 148 * 32));
+  };
+  split_bf16_kernel<<<grid_for(static_cast<long long>(n_img) * E), 256, 0, s>>>(a, a3, n_img, E, 0);
+  split_bf16_kernel<<<grid_for(static_cast<long long>(n_txt) * E), 256, 0, s>>>(b, b3, n_txt, E, 1);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  MSCLIP_TRY(launch_gemm_scaled(a3, 3 * E, b3, 3 * E, n_img, n_txt, 3 * E, scale, nullptr, o, n_txt, nullptr, 0, EPI_F32, s));
+  count_launch(3);
+  if (!out_dev_ptr) {
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(logits, o, static_cast<size_t>(n_img) * n_txt * 4, cudaMemcpyDeviceToHost, s));
+    MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int batch, float* logits,
+                   cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  const int E = h->cfg.embed_dim;
+  WS(fi, float, "fwd_img", static_cast<size_t>(std::max(batch, 1)) * E);
+  WS(ft, float, "fwd_txt", static_cast<size_t>(std::max(batch, 1)) * E);
+  MSCLIP_TRY(engine_encode_text(h, tokens, batch, ft, 1, s));
+  MSCLIP_TRY(engine_encode_image(h, image, dtype, batch, fi, 1, s));
+  return engine_similarity_logits(h, fi, batch, ft, batch, std::exp(h->logit_scale), logits, s);
+}
+
+__global__ void publish_kernel(uint32_t* const* flag_tables, int world, int rank, uint32_t epoch) {
+  // embeddings were written by earlier kernels of this stream; make them visible system-wide, then raise
+  // this rank's flag in every peer's (and our own) flag array
+  const int r = threadIdx.x;
+  if (r < world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_tables[r] + rank), "r"(epoch) : "memory");
+  }
+}
+
+__global__ void finish_loss_kernel(const float* parts, float inv, float* loss) { loss[0] = (parts[0] + parts[1]) * inv; }
+
+int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* partial_out, float* loss_out,
+                            cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  MSCLIP_REQUIRE(b_local >= 1, "contrastive_loss: empty batch");
+  MSCLIP_REQUIRE(h->xchg != nullptr && h->last_img_batch == b_local && h->last_txt_batch == b_local,
+                 "contrastive_loss: encode_image and encode_text (normalize=1) of b_local rows must precede it");
+  MSCLIP_REQUIRE(h->world == 1 || h->shard_tables != nullptr, "contrastive_loss: msclip_comm_import has not been called");
+  const int W = h->world, E = h->cfg.embed_dim;
+  h->epoch += 1;
+  const int par = static_cast<int>(h->epoch & 1);
+  void** tables = static_cast<void**>(h->shard_tables);
+  const bf16* const* img_tab = reinterpret_cast<const bf16* const*>(tables + (par * 2 + 0) * W);
+  const bf16* const* txt_tab = reinterpret_cast<const bf16* const*>(tables + (par * 2 + 1) * W);
+  const uint32_t* flags = nullptr;
+  if (W > 1) {
+    publish_kernel<<<1, 32, 0, s>>>(h->peer_flag_tables, W, h->rank, h->epoch);
+    MSCLIP_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    flags = xchg_flags(h, h->xchg);
+  }
+  void* wsp = nullptr;
+  MSCLIP_TRY(ws_get(h, "loss_ws", contrastive_loss_workspace_bytes(W, b_local), &wsp));
+  WS(parts, float, "loss_parts", 4);
+  MSCLIP_TRY(launch_contrastive_loss_ex(xchg_slot(h, h->xchg, par, 0), xchg_slot(h, h->xchg, par, 1), img_tab, txt_tab,
+                                        flags, h->epoch, W, b_local, E, scale, wsp, parts, s));
+  count_launch(3);
+  if (loss_out && W == 1) {
+    finish_loss_kernel<<<1, 1, 0, s>>>(parts, 1.0f / (2.0f * b_local), parts + 2);
+    MSCLIP_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
+  bool need_sync = false;
+  if (partial_out) {
+    const bool dev = is_device_pointer(partial_out);
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(partial_out, parts, 8, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    need_sync |= !dev;
+  }
+  if (loss_out && W == 1) {
+    const bool dev = is_device_pointer(loss_out);
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(loss_out, parts + 2, 4, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    need_sync |= !dev;
+  }
+  if (need_sync) MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+  h->last_img_batch = h->last_txt_batch = -1;
+  return 0;
+}
+
+int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,
+                        float* partial_out, float* loss_out, cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  MSCLIP_REQUIRE(b_local >= 1 && image && tokens, "forward_loss: bad arguments");
+  MSCLIP_TRY(ensure_streams(h));
+  const msclip_config& c = h->cfg;
+  const int E = c.embed_dim;
+  WS(fi, float, "fwd_img", static_cast<size_t>(b_local) * E);
+  WS(ft, float, "fwd_txt", static_cast<size_t>(b_local) * E);
+  // host images: start the (large) transfer first, run the text tower while it is in flight
+  const void* img_dev = image;
+  if (!is_device_pointer(image)) {
+    const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
+    const size_t img_bytes = static_cast<size_t>(b_local) * 3 * c.image_resolution * c.image_resolution * esz;
+    WS(stage, uint8_t, "img_stage", img_bytes);
+    MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_main, s));
+    MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(stage, image, img_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_copy, h->copy_stream));
+    img_dev = stage;
+  }
+  MSCLIP_TRY(engine_encode_text(h, tokens, b_local, ft, 1, s));
+  if (img_dev != image) MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_copy, 0));
+  MSCLIP_TRY(engine_encode_image(h, img_dev, dtype, b_local, fi, 1, s));
+  return engine_contrastive_loss(h, b_local, std::exp(h->logit_scale), partial_out, loss_out, s);
+}
+
+}  // namespace msclip
+
+msclip_ctx::~msclip_ctx() {
+  cudaDeviceSynchronize();
+  for (auto& kv : raw) cudaFree(kv.second.dev);
+  for (void* p : weight_allocs) cudaFree(p);
+  for (auto& kv : ws) cudaFree(kv.second.p);
+  for (int r = 0; r < static_cast<int>(peer_base.size()); ++r)
+    if (r != rank && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
+  if (xchg) cudaFree(xchg);
+  if (shard_tables) cudaFree(shard_tables);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (ev_copy) cudaEventDestroy(ev_copy);
+  if (ev_main) cudaEventDestroy(ev_main);
+  cudaGetLastError();
+}

@@ -1,0 +1,113 @@
+// Engine: owns the packed weights and the workspace of one model instance and sequences the kernels of
+// the MS-CLIP-S forward (vision tower M.py:2621-2697 / 2357-2471, text tower M.py:3043-3079, contrast
+// M.py:3126-3155).  Host-only C++; all device work goes through the launchers in kernels.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/msclip_b200.h"
+#include "kernels.h"
+
+namespace msclip {
+
+struct RawTensor {
+  std::vector<int64_t> shape;
+  float* dev = nullptr;
+  size_t numel = 0;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct BlockWeights {
+  bf16 *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
+  float *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+};
+
+struct ConvWeights {
+  bf16* w = nullptr;   // [N, K] bf16, BN scale folded
+  float* b = nullptr;  // [N] BN shift (null = no bias)
+  int N = 0, K = 0;
+};
+
+struct AdapterWeights {
+  float *dw_w = nullptr, *dw_b = nullptr;    // top2bottom depth-wise k x k (+BN): [k*k][C], [C]
+  bf16* pw = nullptr;                        // top2bottom point-wise: [768, C]
+  float *bdw_w9 = nullptr, *bdw_b = nullptr; // bottom depth-wise 3x3 (+BN): [9][768], [768]
+  float *ln_w = nullptr, *ln_b = nullptr;
+  int C = 0, k = 0;
+};
+
+}  // namespace msclip
+
+struct msclip_ctx {
+  msclip_config cfg;
+  int grid = 0, l_img = 0, heads = 0;
+  std::map<std::string, std::vector<int64_t>> spec;  // expected state-dict keys -> shapes
+  std::map<std::string, msclip::RawTensor> raw;      // copies made by msclip_set_weight (freed by finalize)
+  bool finalized = false;
+  float logit_scale = 0.f;
+
+  // packed weights
+  std::vector<msclip::BlockWeights> vblocks, tblocks;  // index = block id (vblocks[0] unused: it is the stem)
+  msclip::ConvWeights first, stem[4], last_conv, br1[5], br2[5], br3[5];
+  msclip::AdapterWeights adapters[5];
+  float *cls = nullptr, *vpos = nullptr, *ln_pre_w = nullptr, *ln_pre_b = nullptr, *ln_post_w = nullptr,
+        *ln_post_b = nullptr;
+  float *tok_emb = nullptr, *tpos = nullptr, *ln_final_w = nullptr, *ln_final_b = nullptr;
+  msclip::bf16 *vproj = nullptr, *tproj = nullptr;  // [embed, width] (transposed projections)
+  std::vector<void*> weight_allocs;
+  size_t weight_bytes = 0;
+
+  // workspace (grown on demand)
+  std::map<std::string, msclip::DevBuf> ws;
+  size_t ws_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
+
+  // embedding exchange (data-parallel contrastive loss)
+  int rank = 0, world = 1, max_b_local = 0;
+  void* xchg = nullptr;  // [2 parity][2 modality][max_b_local, E] bf16, then uint32 flags[world]
+  size_t xchg_bytes = 0;
+  std::vector<void*> peer_base;    // imported peer bases (own base at [rank])
+  void* shard_tables = nullptr;    // device: [2 parity][2 modality][world] pointers
+  uint32_t** peer_flag_tables = nullptr;  // device: [world] pointers to each rank's flag array
+  uint32_t epoch = 0;
+  int last_img_batch = -1, last_txt_batch = -1;
+
+  ~msclip_ctx();
+};
+
+namespace msclip {
+
+void build_spec(msclip_ctx* h);
+int engine_finalize(msclip_ctx* h, cudaStream_t stream);
+int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, float* out, int normalize,
+                        cudaStream_t stream);
+int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize,
+                       cudaStream_t stream);
+int engine_similarity_logits(msclip_ctx* h, const float* img, int n_img, const float* txt, int n_txt, float scale,
+                             float* logits, cudaStream_t stream);
+int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int batch, float* logits,
+                   cudaStream_t stream);
+int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* partial_out, float* loss_out,
+                            cudaStream_t stream);
+int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,
+                        float* partial_out, float* loss_out, cudaStream_t stream);
+int comm_init(msclip_ctx* h, int rank, int world, int max_b_local);
+int comm_export(msclip_ctx* h, void* handle_out);
+int comm_import(msclip_ctx* h, const void* handles);
+
+int64_t launch_count();
+void count_launch(int n);
+bool is_device_pointer(const void* p);
+
+}  // namespace msclip

@@ -1,0 +1,337 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias).
+//
+// Replaces every F.linear of the shared block (QKV M.py:612, out-proj M.py:747, MLP M.py:794-798), the
+// projections (M.py:2690, 3074) and - through im2col - the convolutions of the stem / parallel branch
+// (M.py:1993-2000, 1842-1861).  Both operands are K-major bf16 (A = activations [M,K], W = nn.Linear
+// weight [N,K]), accumulation is fp32 in TMEM, and the epilogue (bias, QuickGELU / ReLU, residual add
+// on the fp32 stream) is fused so no GEMM output ever makes an extra HBM round trip.
+//
+// CTA layout (256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0   : TMA producer   (one lane)  global -> 128B-swizzled smem ring, kStages deep
+//   warp 1   : MMA issuer     (one lane)  tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM
+//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
+//   warps 4-7: epilogue       tcgen05.ld -> registers -> fused math -> global stores
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msclip {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 256;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_n, total_tiles;
+  const float* bias;
+  void* out;
+  const float* resid;
+  long long ldo, ldr;
+  float alpha;  // acc is scaled by alpha before the bias (similarity logits: exp(logit_scale))
+  int vec_ok;   // rows of out / resid keep 16-byte alignment -> vector stores
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageA = kBM * kBK * 2;
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStagesRaw = (192 * 1024) / kStage;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStage + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kChunk = (BN % 32 == 0) ? 32 : 16;                     // columns per tcgen05.ld
+  static_assert(kStageB % 1024 == 0, "B stage must keep 1024-byte alignment");
+  static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M = 128");
+};
+
+__device__ __forceinline__ float quick_gelu(float x) {
+  // x * sigmoid(1.702 x)   (M.py:224)
+  return x / (1.0f + __expf(-1.702f * x));
+}
+
+template <int EPI, int CH>
+__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const GemmParams& p, int row, int col0) {
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  if (!p.vec_ok || col0 + CH > p.N) {
+    // ragged edge (N not a multiple of the tile) or unaligned rows: scalar, bounds-checked
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int col = col0 + j;
+      if (col < p.N) {
+        float x = v[j] + (p.bias ? p.bias[col] : 0.f);
+        if (EPI == EPI_QGELU_BF16) x = quick_gelu(x);
+        if (EPI == EPI_RELU_BF16) x = fmaxf(x, 0.f);
+        if (EPI == EPI_RESID_F32) x += p.resid[static_cast<long long>(row) * p.ldr + col];
+        if (EPI == EPI_RESID_F32 || EPI == EPI_F32)
+          reinterpret_cast<float*>(p.out)[static_cast<long long>(row) * p.ldo + col] = x;
+        else
+          reinterpret_cast<bf16*>(p.out)[static_cast<long long>(row) * p.ldo + col] = __float2bfloat16_rn(x);
+      }
+    }
+    return;
+  }
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x;
+      v[4 * j + 1] += b.y;
+      v[4 * j + 2] += b.z;
+      v[4 * j + 3] += b.w;
+    }
+  }
+  if (EPI == EPI_QGELU_BF16) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = quick_gelu(v[j]);
+  } else if (EPI == EPI_RELU_BF16) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+    if (EPI == EPI_RESID_F32) {
+      const float4* x4 = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < CH / 4; ++j) {
+        const float4 x = x4[j];
+        v[4 * j + 0] += x.x;
+        v[4 * j + 1] += x.y;
+        v[4 * j + 2] += x.z;
+        v[4 * j + 3] += x.w;
+      }
+    }
+    float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int j = 0; j < CH / 8; ++j)
+      o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * kBM;
+        const int n0 = (tile % p.tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1, 1);
+          uint8_t* sa = smem + s * Cfg::kStage;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage);
+          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
+          tma_load_2d(sa + Cfg::kStageA, &tmap_b, &full_bar[s], kb * kBK, n0);
+          if (++s == Cfg::kStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::kStage);
+          const uint32_t b_addr = a_addr + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          if (++s == Cfg::kStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.tiles_n) * kBM;
+      const int n0 = (tile % p.tiles_n) * BN;
+      mbar_wait(&tfull_bar[as], aph, 4);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / Cfg::kChunk; ++c) {
+        uint32_t r[Cfg::kChunk];
+        if constexpr (Cfg::kChunk == 32) {
+          tmem_ld_32x32(taddr + c * 32, reinterpret_cast<uint32_t(&)[32]>(r));
+        } else {
+          tmem_ld_32x16(taddr + c * 16, reinterpret_cast<uint32_t(&)[16]>(r));
+        }
+        tmem_ld_wait();
+        if (row < p.M) epilogue_store<EPI, Cfg::kChunk>(r, p, row, n0 + c * Cfg::kChunk);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int BN, int EPI>
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_BF16: return launch_variant<BN, EPI_BF16>(ta, tb, p, stream);
+    case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16>(ta, tb, p, stream);
+    case EPI_RELU_BF16: return launch_variant<BN, EPI_RELU_BF16>(ta, tb, p, stream);
+    case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32>(ta, tb, p, stream);
+    case EPI_F32: return launch_variant<BN, EPI_F32>(ta, tb, p, stream);
+  }
+  set_last_error("launch_gemm: unknown epilogue " + std::to_string(epi));
+  return 2;
+}
+
+}  // namespace
+
+int gemm_pick_bn(int N) {
+  const int cands[6] = {256, 192, 128, 96, 64, 48};
+  for (int i = 0; i < 6; ++i)
+    if (N % cands[i] == 0) return cands[i];
+  if (N >= 256) return 256;  // ragged N: last tile is masked in the epilogue
+  for (int i = 5; i >= 0; --i)
+    if (cands[i] >= N) return cands[i];
+  return 256;
+}
+
+int launch_gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, const float* bias,
+                void* out, int64_t ldo, const float* resid, int64_t ldr, int epi, cudaStream_t stream) {
+  return launch_gemm_scaled(A, lda, W, ldw, M, N, K, 1.0f, bias, out, ldo, resid, ldr, epi, stream);
+}
+
+int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, float alpha,
+                       const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
+                       cudaStream_t stream) {
+  MSCLIP_REQUIRE(M > 0 && N > 0 && K > 0, "launch_gemm: empty problem");
+  MSCLIP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "launch_gemm: K and operand pitches must be multiples of 8");
+  const int bn = gemm_pick_bn(N);
+  const bool f32_out = (epi == EPI_RESID_F32 || epi == EPI_F32);
+  if (epi == EPI_RESID_F32) MSCLIP_REQUIRE(resid != nullptr, "launch_gemm: residual operand missing");
+  bool vec_ok = ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  if (epi == EPI_RESID_F32) vec_ok = vec_ok && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;
+  CUtensorMap ta, tb;
+  MSCLIP_TRY(make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
+                               kBM));
+  MSCLIP_TRY(make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+                               static_cast<uint32_t>(bn)));
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.tiles_n = (N + bn - 1) / bn;
+  p.alpha = alpha;
+  p.vec_ok = vec_ok ? 1 : 0;
+  p.total_tiles = ((M + kBM - 1) / kBM) * p.tiles_n;
+  p.bias = bias;
+  p.out = out;
+  p.resid = resid;
+  p.ldo = ldo;
+  p.ldr = ldr;
+  switch (bn) {
+    case 256: return launch_bn<256>(ta, tb, p, epi, stream);
+    case 192: return launch_bn<192>(ta, tb, p, epi, stream);
+    case 128: return launch_bn<128>(ta, tb, p, epi, stream);
+    case 96: return launch_bn<96>(ta, tb, p, epi, stream);
+    case 64: return launch_bn<64>(ta, tb, p, epi, stream);
+    case 48: return launch_bn<48>(ta, tb, p, epi, stream);
+  }
+  return 2;
+}
+
+}  // namespace msclip

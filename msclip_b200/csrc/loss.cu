@@ -1,0 +1,311 @@
+// Global-batch contrastive loss without materialising the G x G logits (reference: CLIP.forward builds
+// logits = exp(logit_scale) * I_all @ T_all^T on every rank after two NCCL all-gathers, M.py:3136-3141,
+// lib/utils/comm.py:140-154; the symmetric cross-entropy itself is the north star's).
+//
+// Formulation: rank r owns rows [r*B, (r+1)*B).  For both directions (image rows vs all text columns,
+// text rows vs all image columns) it needs  lse_i = log sum_j exp(s_ij)  over all G columns and the
+// diagonal s_ii.  One CTA owns one 128-column tile of the *gathered* matrix: it pulls that tile straight
+// from the owning rank's shard (a local or an NVLink peer-mapped pointer - this is the all-gather, issued
+// as plain loads from inside the kernel, each peer byte crossing NVLink exactly once), keeps it resident
+// in 128B-swizzled shared memory as the UMMA B operand, and streams the local rows past it with TMA
+// (L2-resident) through tcgen05.mma into double-buffered TMEM accumulators.  The epilogue warps turn
+// each 128x128 score tile into per-row (max, sum-exp) partials in registers; a second tiny kernel merges
+// the partials across column tiles, subtracts the diagonal and reduces deterministically.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace msclip {
+
+namespace {
+
+constexpr int kLossE = 512;            // embedding width (K of the similarity GEMM)
+constexpr int kLossKB = kLossE / 64;   // 8 k-blocks
+constexpr int kLossBN = 128;           // columns per CTA
+constexpr int kLossStages = 4;
+constexpr int kLossStageBytes = 128 * 64 * 2;  // one A k-block: 16 KB
+constexpr int kLossBBytes = kLossKB * kLossBN * 64 * 2;  // 128 KB resident column tile
+constexpr int kLossSmem = kLossBBytes + kLossStages * kLossStageBytes + 256 + 1024;
+constexpr int kLossThreads = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct LossParams {
+  const bf16* const* col_shards[2];  // [dir] -> device table of `world` shard pointers (columns of that direction)
+  const uint32_t* flags;             // optional: this rank's flag array [world], raised by the owners; null for world == 1
+  uint32_t epoch;
+  int world, b_local, tiles_per_shard, n_col_tiles, n_row_blocks, b_pad;
+  float scale_log2;                  // exp(logit_scale) * log2(e): scores are kept in the log2 domain
+  float2* ws;                        // [2][n_col_tiles][b_pad] (max, sum) partials, log2 domain
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kLossThreads, 1)
+contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const __grid_constant__ CUtensorMap tmap_rows_txt,
+                       const LossParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + kLossBBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + kLossStages * kLossStageBytes);
+  uint64_t* empty_bar = full_bar + kLossStages;
+  uint64_t* tfull_bar = empty_bar + kLossStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ct = blockIdx.x;   // column tile of the gathered matrix
+  const int dir = blockIdx.y;  // 0: image rows x text columns, 1: text rows x image columns
+  const CUtensorMap* tmap_rows = dir == 0 ? &tmap_rows_img : &tmap_rows_txt;
+  const int owner = ct / p.tiles_per_shard;
+  const int c0 = (ct % p.tiles_per_shard) * kLossBN;
+  const int valid_cols = min(kLossBN, p.b_local - c0);
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(tmap_rows);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kLossStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+
+  // ---- in-kernel gather of this column tile from its owner (local or NVLink peer) -------------------
+  if (p.flags != nullptr) {
+    // the owner publishes `epoch` with a system-scope release once its embeddings are written
+    if (threadIdx.x == 0) {
+      const uint32_t* f = p.flags + owner;
+      const uint64_t t0 = global_timer_ns();
+      while (static_cast<int32_t>(ld_acquire_sys(f) - p.epoch) < 0) {
+        if (global_timer_ns() - t0 > 20000000000ull) {  // bounded wait: a dead peer must not hang the GPU
+          printf("msclip: peer %d never published epoch %u\n", owner, p.epoch);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+  }
+  {
+    const bf16* src = p.col_shards[dir][owner] + static_cast<long long>(c0) * kLossE;
+    // 128 rows x 64 chunks of 16 B; adjacent threads read adjacent chunks of one row (coalesced)
+    for (int i = threadIdx.x; i < kLossBN * (kLossE / 8); i += kLossThreads) {
+      const int r = i >> 6;
+      const int cc = i & 63;
+      const int kb = cc >> 3, c = cc & 7;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < valid_cols) v = __ldcg(reinterpret_cast<const uint4*>(src + static_cast<long long>(r) * kLossE + cc * 8));
+      *reinterpret_cast<uint4*>(sB + kb * (kLossBN * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int rb = 0; rb < p.n_row_blocks; ++rb) {
+        for (int kb = 0; kb < kLossKB; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1, 11);
+          mbar_arrive_expect_tx(&full_bar[s], kLossStageBytes);
+          tma_load_2d(sA + s * kLossStageBytes, tmap_rows, &full_bar[s], kb * 64, rb * 128);
+          if (++s == kLossStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kLossBN);
+      const uint32_t b_base = smem_u32(sB);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int rb = 0; rb < p.n_row_blocks; ++rb) {
+        const int as = rb & 1;
+        const uint32_t aph = (rb >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1, 12);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kLossBN;
+        for (int kb = 0; kb < kLossKB; ++kb) {
+          mbar_wait(&full_bar[s], ph, 13);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * kLossStageBytes);
+          const uint32_t b_addr = b_base + kb * (kLossBN * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (++s == kLossStages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    float2* ws = p.ws + (static_cast<long long>(dir) * p.n_col_tiles + ct) * p.b_pad;
+    for (int rb = 0; rb < p.n_row_blocks; ++rb) {
+      const int as = rb & 1;
+      const uint32_t aph = (rb >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aph, 14);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kLossBN;
+      float m = -INFINITY, l = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kLossBN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = (c * 32 + j < valid_cols) ? __uint_as_float(r[j]) * p.scale_log2 : -INFINITY;
+          cm = fmaxf(cm, v[j]);
+        }
+        const float mn = fmaxf(m, cm);
+        if (mn != -INFINITY) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += exp2f(v[j] - mn);
+          l = l * exp2f(m - mn) + acc;
+          m = mn;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      const int row = rb * 128 + q * 32 + lane;
+      if (row < p.b_local) ws[row] = make_float2(m, l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// per local row and direction: merge the column-tile partials, subtract the diagonal logit
+__global__ void __launch_bounds__(256)
+lse_combine_kernel(const float2* __restrict__ ws, const bf16* __restrict__ img_local, const bf16* __restrict__ txt_local,
+                   int b_local, int b_pad, int n_col_tiles, float scale_log2, float* __restrict__ row_loss) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= 2 * b_local) return;
+  const int dir = idx / b_local, row = idx % b_local;
+  const float2* w = ws + static_cast<long long>(dir) * n_col_tiles * b_pad + row;
+  float m = -INFINITY;
+  for (int t = 0; t < n_col_tiles; ++t) m = fmaxf(m, w[static_cast<long long>(t) * b_pad].x);
+  float l = 0.f;
+  for (int t = 0; t < n_col_tiles; ++t) {
+    const float2 e = w[static_cast<long long>(t) * b_pad];
+    l += e.y * exp2f(e.x - m);
+  }
+  // diagonal: same bf16 operands as the tensor-core product, fp32 accumulation
+  const uint4* a4 = reinterpret_cast<const uint4*>(img_local + static_cast<long long>(row) * kLossE);
+  const uint4* b4 = reinterpret_cast<const uint4*>(txt_local + static_cast<long long>(row) * kLossE);
+  float dot = 0.f;
+  for (int i = 0; i < kLossE / 8; ++i) {
+    const uint4 a = a4[i], b = b4[i];
+    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = __bfloat1622float2(ah[j]), y = __bfloat1622float2(bh[j]);
+      dot = fmaf(x.x, y.x, dot);
+      dot = fmaf(x.y, y.y, dot);
+    }
+  }
+  // natural-log units: lse = ln2 * (m + log2 l); diag = scale * dot = ln2 * scale_log2 * dot
+  row_loss[idx] = kLn2 * (m + log2f(l) - scale_log2 * dot);
+}
+
+// deterministic reduction: out[dir] = sum_row row_loss[dir][row]
+__global__ void __launch_bounds__(1024)
+loss_reduce_kernel(const float* __restrict__ row_loss, int b_local, float* __restrict__ out) {
+  __shared__ double sh[1024];
+  const int dir = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < b_local; i += 1024) acc += static_cast<double>(row_loss[dir * b_local + i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[dir] = static_cast<float>(sh[0]);
+}
+
+inline int pad128(int x) { return (x + 127) / 128 * 128; }
+
+}  // namespace
+
+size_t contrastive_loss_workspace_bytes(int world, int b_local) {
+  const size_t tiles = static_cast<size_t>(world) * ((b_local + kLossBN - 1) / kLossBN);
+  return 2 * tiles * pad128(b_local) * sizeof(float2) + 2 * static_cast<size_t>(b_local) * sizeof(float);
+}
+
+int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, const bf16* const* img_shards,
+                               const bf16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
+                               int b_local, int E, float scale, void* workspace, float* loss_parts,
+                               cudaStream_t stream) {
+  MSCLIP_REQUIRE(E == kLossE, "contrastive loss: embedding width must be 512");
+  MSCLIP_REQUIRE(world >= 1 && b_local >= 1, "contrastive loss: empty problem");
+  static bool configured = false;
+  if (!configured) {
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(contrastive_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kLossSmem));
+    configured = true;
+  }
+  LossParams p;
+  p.col_shards[0] = txt_shards;  // image rows see text columns
+  p.col_shards[1] = img_shards;  // text rows see image columns
+  p.flags = world > 1 ? flags : nullptr;
+  p.epoch = epoch;
+  p.world = world;
+  p.b_local = b_local;
+  p.tiles_per_shard = (b_local + kLossBN - 1) / kLossBN;
+  p.n_col_tiles = world * p.tiles_per_shard;
+  p.n_row_blocks = (b_local + 127) / 128;
+  p.b_pad = pad128(b_local);
+  p.scale_log2 = scale * kLog2e;
+  p.ws = reinterpret_cast<float2*>(workspace);
+  float* row_loss = reinterpret_cast<float*>(p.ws + 2ll * p.n_col_tiles * p.b_pad);
+  CUtensorMap ti, tt;
+  MSCLIP_TRY(make_tmap_bf16_2d(&ti, img_local, b_local, kLossE, kLossE, 128));
+  MSCLIP_TRY(make_tmap_bf16_2d(&tt, txt_local, b_local, kLossE, kLossE, 128));
+  contrastive_lse_kernel<<<dim3(p.n_col_tiles, 2), kLossThreads, kLossSmem, stream>>>(ti, tt, p);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  lse_combine_kernel<<<(2 * b_local + 255) / 256, 256, 0, stream>>>(p.ws, img_local, txt_local, b_local, p.b_pad,
+                                                                    p.n_col_tiles, p.scale_log2, row_loss);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  loss_reduce_kernel<<<2, 1024, 0, stream>>>(row_loss, b_local, loss_parts);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_similarity_logits(const bf16* a, const bf16* b, int Ma, int Mb, int E, float scale, float* out,
+                             cudaStream_t stream) {
+  return launch_gemm_scaled(a, E, b, E, Ma, Mb, E, scale, nullptr, out, Mb, nullptr, 0, EPI_F32, stream);
+}
+
+}  // namespace msclip

@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference model API, backed by the sm_100a library.
+
+Mirrors lib/models/clip_openai_pe_res_v1.py ("M.py") of Hxyou/MSCLIP for the MS-CLIP-S path:
+
+* ``get_clip_model(config, vocab_size=None, eot_token=None)``           M.py:3182-3227
+* ``CLIP.encode_image(image, norm=True, action=None)``                 M.py:2979-2985
+* ``CLIP.encode_text(text, norm=True, action=None)``                   M.py:3043-3079
+* ``CLIP.forward(image, text) -> logits``                              M.py:3126-3155
+* ``CLIP.state_dict() / load_state_dict()`` with the reference's key names, including the text-tower
+  keys that alias the vision tower's shared attention / MLP parameters (M.py:2786-2830)
+* ``CLIP.logit_scale``, ``CLIP.dtype``                                 M.py:2850, 2973-2975
+
+plus the call the reference lacks: ``contrastive_loss(image, text)`` — the symmetric cross-entropy over
+the global batch, computed by one fused kernel that never materialises the logits.
+
+PyTorch is plumbing here (parameter storage, device memory, streams); all arithmetic happens in
+libmsclip_b200.so through ctypes.  There is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import MSCLIPConfig, from_reference_config
+from .synth import alias_of, state_dict_spec
+
+_IMAGE_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+class _Node(nn.Module):
+    """Anonymous container: only there so parameters get the reference's dotted names."""
+
+
+def _descend(root: nn.Module, path):
+    node = root
+    for name in path:
+        child = node._modules.get(name)
+        if child is None:
+            child = _Node()
+            node.add_module(name, child)
+        node = child
+    return node
+
+
+def _init_tensor(key: str, shape) -> torch.Tensor:
+    """Reference-style initialisation (trunc-normal 0.02 weights, zero biases, identity norms,
+    M.py:2344-2355, 2937-2948); real use loads a checkpoint over it."""
+    if key == "logit_scale":
+        return torch.ones(())                                       # M.py:2850
+    if key.endswith("num_batches_tracked"):
+        return torch.zeros((), dtype=torch.long)
+    if key.endswith("running_mean"):
+        return torch.zeros(shape)
+    if key.endswith("running_var"):
+        return torch.ones(shape)
+    is_norm = any(s in key for s in (".bn", "downsample.1", "residual_bn", ".ln_", "ln_final", "ln_pre", "ln_post",
+                                     "ln_adapt"))
+    if is_norm:
+        return torch.ones(shape) if key.endswith(".weight") else torch.zeros(shape)
+    if key.endswith("bias"):
+        return torch.zeros(shape)
+    t = torch.empty(shape)
+    nn.init.trunc_normal_(t, std=0.02)
+    return t
+
+
+class CLIP(nn.Module):
+    def __init__(self, cfg: MSCLIPConfig):
+        super().__init__()
+        self.cfg = cfg
+        self._spec = state_dict_spec(cfg)
+        made = {}
+        for key, shape in self._spec.items():
+            *path, leaf = key.split(".")
+            node = _descend(self, path)
+            src = alias_of(cfg, key)
+            if leaf in ("running_mean", "running_var", "num_batches_tracked"):
+                node.register_buffer(leaf, _init_tensor(key, shape))
+            else:
+                p = made[src] if src is not None else nn.Parameter(_init_tensor(key, shape), requires_grad=False)
+                made[key] = p
+                node.register_parameter(leaf, p)
+        self._handle = C.c_void_p()
+        self._synced = None         # fingerprint of the tensors last handed to the library
+        self._comm = None           # (rank, world, max_b_local) once the peer exchange is set up
+
+    # ---- reference attributes -----------------------------------------------------------------------
+    @property
+    def dtype(self):                                                # M.py:2973-2975
+        return self.visual.proj.dtype
+
+    @property
+    def device(self):
+        return self.visual.proj.device
+
+    # ---- library handle ------------------------------------------------------------------------------
+    def _ensure_handle(self):
+        if not self._handle:
+            c = self.cfg
+            cc = _lib.Config(c.patch_size, c.layers, c.width, c.embed_dim, c.image_resolution, c.context_length,
+                             c.vocab_size, (C.c_int32 * 4)(*c.early_strides), (C.c_int32 * 5)(*c.parallel_strides),
+                             (C.c_int32 * 5)(*c.t2b_kernels))
+            _lib.check(_lib.lib().msclip_create(C.byref(cc), C.byref(self._handle)), "msclip_create")
+        return self._handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                _lib.lib().msclip_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _sync_weights(self):
+        """Hand the current state_dict to the library if any tensor changed since the last call."""
+        sd = self.state_dict(keep_vars=True)
+        finger = tuple((t.data_ptr(), t._version) for t in sd.values())
+        if finger == self._synced:
+            return
+        if not torch.cuda.is_available():
+            raise _lib.MsclipError("msclip_b200 needs an sm_100 GPU: there is no CPU fallback")
+        h = self._ensure_handle()
+        L = _lib.lib()
+        for key, t in sd.items():
+            if t.dtype == torch.long:
+                dt, tt = _lib.I64, t
+            else:
+                dt, tt = _lib.F32, t.detach().to(torch.float32).contiguous()
+            shape = (C.c_int64 * max(tt.dim(), 1))(*tt.shape)
+            _lib.check(L.msclip_set_weight(h, key.encode(), C.c_void_p(tt.data_ptr()), dt, tt.dim(), shape),
+                       f"msclip_set_weight({key})")
+        _lib.check(L.msclip_finalize_weights(h, self._stream()), "msclip_finalize_weights")
+        self._synced = finger
+
+    # ---- reference methods ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_image(self, image: torch.Tensor, norm: bool = True, action=None) -> torch.Tensor:
+        if action is not None:
+            raise AssertionError("action must be None (Gumbel search is outside the MS-CLIP-S envelope, M.py:942)")
+        c = self.cfg
+        if image.dim() != 4 or tuple(image.shape[1:]) != (3, c.image_resolution, c.image_resolution):
+            raise ValueError(f"expected [B, 3, {c.image_resolution}, {c.image_resolution}], got {tuple(image.shape)}")
+        if image.dtype not in _IMAGE_DTYPES:
+            image = image.float()
+        image = image.contiguous()
+        self._sync_weights()
+        out = torch.empty((image.shape[0], c.embed_dim), dtype=torch.float32, device=image.device)
+        _lib.check(_lib.lib().msclip_encode_image(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+                                                  image.shape[0], C.c_void_p(out.data_ptr()), int(bool(norm)),
+                                                  self._stream()), "msclip_encode_image")
+        return out
+
+    @torch.no_grad()
+    def encode_text(self, text: torch.Tensor, norm: bool = True, action=None) -> torch.Tensor:
+        if action is not None:
+            raise AssertionError("action must be None (Gumbel search is outside the MS-CLIP-S envelope, M.py:942)")
+        c = self.cfg
+        if text.dim() != 2 or text.shape[1] != c.context_length:
+            raise ValueError(f"expected [B, {c.context_length}] token ids, got {tuple(text.shape)}")
+        text = text.to(torch.long).contiguous()
+        self._sync_weights()
+        out = torch.empty((text.shape[0], c.embed_dim), dtype=torch.float32, device=text.device)
+        _lib.check(_lib.lib().msclip_encode_text(self._handle, C.c_void_p(text.data_ptr()), text.shape[0],
+                                                 C.c_void_p(out.data_ptr()), int(bool(norm)), self._stream()),
+                   "msclip_encode_text")
+        return out
+
+    @torch.no_grad()
+    def similarity_logits(self, image_features: torch.Tensor, text_features: torch.Tensor, scale: float) -> torch.Tensor:
+        """scale * I @ T^T (M.py:3141/3146; tools/zero_shot.py:266 with scale = 100)."""
+        fi = image_features.float().contiguous()
+        ft = text_features.float().contiguous()
+        self._ensure_handle()
+        out = torch.empty((fi.shape[0], ft.shape[0]), dtype=torch.float32, device=fi.device)
+        _lib.check(_lib.lib().msclip_similarity_logits(self._handle, C.c_void_p(fi.data_ptr()), fi.shape[0],
+                                                       C.c_void_p(ft.data_ptr()), ft.shape[0], float(scale),
+                                                       C.c_void_p(out.data_ptr()), self._stream()),
+                   "msclip_similarity_logits")
+        return out
+
+    @torch.no_grad()
+    def forward(self, image: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+        """CLIP.forward (M.py:3126-3155): logits over the (gathered) batch.  With gather_tensors and an
+        initialised process group the features are all-gathered in rank order exactly like
+        lib/utils/comm.py:140-154 (this materialising path is the reference-compatible one; the
+        B200-native training-step path is ``contrastive_loss``)."""
+        fi = self.encode_image(image)
+        ft = self.encode_text(text)
+        scale = float(self.logit_scale.detach().float().exp())
+        if self.cfg.gather_tensors and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            from .comm import gather_tensors
+            fi, ft = gather_tensors(fi), gather_tensors(ft)
+        return self.similarity_logits(fi, ft, scale)
+
+    # ---- the fused training-step path ------------------------------------------------------------------
+    def setup_data_parallel(self, max_b_local: int, group=None):
+        """Register the peer-visible embedding buffers of all ranks (one process per GPU)."""
+        from .comm import setup_peer_exchange
+        self._sync_weights()
+        self._comm = setup_peer_exchange(self._handle, max_b_local, group)
+        return self._comm
+
+    @torch.no_grad()
+    def contrastive_loss(self, image: torch.Tensor, text: torch.Tensor, reduce: bool = True):
+        """Symmetric cross-entropy of exp(logit_scale) * I_all @ T_all^T over the global batch
+        (SURVEY.md section 8a rows G, C, L).  Returns a 0-dim tensor; with world > 1 and ``reduce`` the
+        per-rank partial sums are summed with one 2-float all-reduce."""
+        if image.shape[0] != text.shape[0]:
+            raise ValueError("image and text batch sizes differ")
+        if image.dtype not in _IMAGE_DTYPES:
+            image = image.float()
+        image, text = image.contiguous(), text.to(torch.long).contiguous()
+        self._sync_weights()
+        b = image.shape[0]
+        world = self._comm[1] if self._comm else 1
+        dev = self.device
+        parts = torch.empty(2, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().msclip_forward_loss(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+                                                  C.c_void_p(text.data_ptr()), b, C.c_void_p(parts.data_ptr()),
+                                                  C.c_void_p(loss.data_ptr()) if world == 1 else None, self._stream()),
+                   "msclip_forward_loss")
+        if world == 1:
+            return loss
+        if reduce:
+            torch.distributed.all_reduce(parts)
+        return parts.sum() / (2.0 * world * b)
+
+    def launch_count(self) -> int:
+        return int(_lib.lib().msclip_launch_count(self._handle)) if self._handle else 0
+
+
+def get_clip_model(config: Any, vocab_size: Optional[int] = None, eot_token: Optional[int] = None, **kwargs) -> CLIP:
+    """Drop-in for ``clip_openai_pe_res_v1.get_clip_model`` (M.py:3182-3227): accepts the reference's
+    yacs config (or any duck-typed equivalent) and refuses flag combinations outside MS-CLIP-S."""
+    cfg = config if isinstance(config, MSCLIPConfig) else from_reference_config(config)
+    if vocab_size is not None and int(vocab_size) != cfg.vocab_size:
+        cfg = MSCLIPConfig(**{**cfg.to_dict(), "vocab_size": int(vocab_size)})
+    return CLIP(cfg)

@@ -81,6 +81,13 @@ def run_case(name):
         logits = model(timg, ttok)
         tgt = torch.arange(logits.shape[0])
         loss = 0.5 * (F.cross_entropy(logits, tgt) + F.cross_entropy(logits.t(), tgt))
+        # the reference's own bf16 mode (torch.autocast; model.bfloat16() is unusable, M.py:689-691): the
+        # yardstick for "how far may a bf16-operand pipeline be from the fp32 forward" 
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            fi_ac = model.encode_image(timg).float()
+            ft_ac = model.encode_text(ttok).float()
+            logits_ac = model(timg, ttok).float()
+        loss_ac = 0.5 * (F.cross_entropy(logits_ac, tgt) + F.cross_entropy(logits_ac.t(), tgt))
     keys = {k: list(v.shape) for k, v in model.state_dict().items()}
     out = dict(
         meta=json.dumps(dict(case=name, cfg=cfg.to_dict(), batch=CASES[name][1], weight_seed=CASES[name][2],
@@ -88,6 +95,8 @@ def run_case(name):
                              correlated=CASES[name][6], tap_stride=TAP_STRIDE, torch=torch.__version__)),
         image_features=fi.numpy(), text_features=ft.numpy(), image_features_unnormalised=fi_raw.numpy(),
         logits=logits.numpy(), loss=np.float64(loss.item()),
+        image_features_autocast=fi_ac.numpy(), text_features_autocast=ft_ac.numpy(),
+        logits_autocast=logits_ac.numpy(), loss_autocast=np.float64(loss_ac.item()),
     )
     out.update({"tap_" + k: v for k, v in taps.items()})
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)

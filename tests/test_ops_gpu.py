@@ -1,0 +1,265 @@
+"""Per-kernel parity on the B200, through the C ABI (include/msclip_b200_ops.h).
+
+Each sm_100a kernel is compared with the operation of the reference it replaces, restated by the oracle
+(oracle/msclip_oracle.py) or, for pure contractions, by a torch fp32 product of the *same* bf16-rounded
+operands.  Tolerances (Frobenius-relative unless stated):
+  * fp32-out GEMM / similarity:     2e-5   (fp32 accumulation, different summation order only)
+  * bf16-out GEMM, attention, LN:   3e-3   (one bf16 rounding of the result = 2^-9 per element)
+  * data movement (im2col):         bit-exact
+"""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from msclip_b200 import _lib
+from oracle import msclip_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+_results = {}
+
+
+def _record(name, value):
+    _results[name] = value
+    try:
+        os.makedirs(OUT_DIR, exist_ok=True)
+        with open(os.path.join(OUT_DIR, "parity_ops.json"), "w") as f:
+            json.dump(_results, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    assert _lib.device_count() >= 1, "no sm_100 device visible to libmsclip_b200"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    yield
+
+
+def run_gemm(M, N, K, epi, alpha=1.0, bias=True, lda=None, a_off=0, ldo=None, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    lda = lda or K
+    ldo = ldo or N
+    a_full = (torch.randn(M, lda, device="cuda", generator=g)).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    a = a_full[:, a_off:a_off + K]
+    f32_out = epi in (_lib.EPI_RESID_F32, _lib.EPI_F32)
+    out = torch.full((M, ldo), 7.0, device="cuda", dtype=torch.float32 if f32_out else torch.bfloat16)
+    resid = torch.randn(M, ldo, device="cuda", generator=g) if epi == _lib.EPI_RESID_F32 else None
+    if resid is not None:
+        out.copy_(resid)
+    ref = alpha * (a.float() @ w.float().t())
+    if b is not None:
+        ref = ref + b
+    if epi == _lib.EPI_QGELU_BF16:
+        ref = O.quick_gelu(ref)
+    elif epi == _lib.EPI_RELU_BF16:
+        ref = torch.relu(ref)
+    elif epi == _lib.EPI_RESID_F32:
+        ref = ref + resid[:, :N]
+    a_ptr = C.c_void_p(a_full.data_ptr() + 2 * a_off)
+    rc = _lib.lib().msclip_op_gemm(a_ptr, lda, ptr(w), K, M, N, K, alpha, ptr(b), ptr(out), ldo,
+                                   ptr(out) if resid is not None else None, ldo, epi, stream())
+    _lib.check(rc, "msclip_op_gemm")
+    torch.cuda.synchronize()
+    got = out[:, :N].float()
+    if ldo > N:     # columns beyond N must be untouched
+        assert torch.all(out[:, N:].float() == (resid[:, N:] if resid is not None else 7.0))
+    return rel(got, ref), float((got - ref).abs().max())
+
+
+GEMM_CASES = [
+    # name,            M,     N,    K,    epilogue,             kwargs
+    ("qkv",            1000,  2304, 768,  _lib.EPI_BF16,        {}),
+    ("out_proj",       300,   768,  768,  _lib.EPI_RESID_F32,   {}),
+    ("fc1",            128,   3072, 768,  _lib.EPI_QGELU_BF16,  {}),
+    ("fc2",            4173,  768,  3072, _lib.EPI_RESID_F32,   {}),
+    ("many_tiles",     40000, 768,  768,  _lib.EPI_BF16,        {}),
+    ("conv_first",     5000,  96,   32,   _lib.EPI_RELU_BF16,   {}),
+    ("conv_stem0",     3136,  96,   432,  _lib.EPI_RELU_BF16,   {}),
+    ("conv_stem1",     784,   192,  864,  _lib.EPI_RELU_BF16,   {}),
+    ("conv_stem3",     49,    768,  3456, _lib.EPI_RELU_BF16,   {}),
+    ("branch_1x1",     2000,  48,   48,   _lib.EPI_RELU_BF16,   dict(lda=96, a_off=48)),
+    ("branch_cat_out", 777,   48,   432,  _lib.EPI_RELU_BF16,   dict(ldo=96)),
+    ("branch_384",     196,   384,  384,  _lib.EPI_RELU_BF16,   {}),
+    ("adapter_pw",     392,   768,  48,   _lib.EPI_F32,         dict(bias=False)),
+    ("proj",           77,    512,  768,  _lib.EPI_F32,         dict(bias=False)),
+    ("logits_small",   8,     8,    1536, _lib.EPI_F32,         dict(bias=False, alpha=14.2857)),
+    ("logits_ragged",  1024,  1000, 1536, _lib.EPI_F32,         dict(bias=False, alpha=100.0)),
+    ("ragged_bf16",    130,   200,  72,   _lib.EPI_BF16,        {}),
+    ("one_row",        1,     64,   8,    _lib.EPI_F32,         {}),
+]
+
+
+@pytest.mark.parametrize("name,M,N,K,epi,kw", GEMM_CASES, ids=[c[0] for c in GEMM_CASES])
+def test_gemm(name, M, N, K, epi, kw):
+    r, mx = run_gemm(M, N, K, epi, **kw)
+    _record(f"gemm/{name}", {"rel": r, "max_abs": mx})
+    tol = 2e-5 if epi in (_lib.EPI_RESID_F32, _lib.EPI_F32) else 3e-3
+    assert r < tol, (name, r, mx)
+
+
+def test_gemm_rejects_bad_arguments():
+    a = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(8, 8, device="cuda")
+    rc = _lib.lib().msclip_op_gemm(ptr(a), 12, ptr(a), 12, 8, 8, 12, 1.0, None, ptr(out), 8, None, 0, _lib.EPI_F32, stream())
+    assert rc != 0 and "multiples of 8" in _lib.last_error()
+
+
+@pytest.mark.parametrize("rows,stride", [(1, 1), (77, 1), (5000, 1), (64, 50)])
+def test_layernorm(rows, stride):
+    x = torch.randn(rows * stride, 768, device="cuda") * 3 + 0.5
+    w, b = torch.randn(768, device="cuda"), torch.randn(768, device="cuda")
+    y = torch.empty(rows, 768, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_layernorm(ptr(x), stride, ptr(w), ptr(b), ptr(y), rows, stream()))
+    ref = O.layer_norm(x[::stride], w, b)
+    r = rel(y.float(), ref)
+    # compare against the bf16 rounding of the oracle too: must agree to the last bit almost everywhere
+    exact = float((y == ref.to(torch.bfloat16)).float().mean())
+    _record(f"layernorm/{rows}x{stride}", {"rel": r, "bf16_exact_fraction": exact})
+    assert r < 3e-3 and exact > 0.99
+
+
+def attention_reference(qkv, B, L, H, causal):
+    q, k, v = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)      # [B,H,L,64]
+    s = q @ k.transpose(-1, -2)
+    if causal:
+        s = s + O.causal_mask(L, s.device)
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * L, H * 64)
+
+
+@pytest.mark.parametrize("B,L,causal", [(3, 50, 0), (2, 77, 1), (2, 197, 0), (1, 197, 1), (2, 1, 0), (2, 64, 1),
+                                        (1, 80, 0), (5, 17, 1), (300, 50, 0)])
+def test_attention(B, L, causal):
+    H = 12
+    qkv = (torch.randn(B * L, 3 * H * 64, device="cuda") * 0.7).to(torch.bfloat16)
+    out = torch.zeros(B * L, H * 64, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_attention(ptr(qkv), ptr(out), B, L, H, causal, stream()))
+    ref = attention_reference(qkv, B, L, H, causal)
+    r = rel(out.float(), ref)
+    _record(f"attention/B{B}_L{L}_c{causal}", {"rel": r})
+    assert r < 6e-3, r            # P is rounded to bf16 before P.V, the result once more
+
+
+def test_im2col_first_bit_exact():
+    B, R = 3, 224
+    img = torch.randn(B, 3, R, R, device="cuda")
+    out = torch.empty(B * 112 * 112, 32, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_im2col_first(ptr(img), _lib.F32, ptr(out), B, R, R, stream()))
+    cols = F.unfold(img, 3, padding=1, stride=2)                  # [B, 27, 112*112], k = c*9 + ky*3 + kx
+    ref = cols.transpose(1, 2).reshape(-1, 27).to(torch.bfloat16)
+    assert torch.equal(out[:, :27], ref)
+    assert torch.all(out[:, 27:] == 0)
+    img16 = img.to(torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_im2col_first(ptr(img16), _lib.BF16, ptr(out), B, R, R, stream()))
+    assert torch.equal(out[:, :27], F.unfold(img16.float(), 3, padding=1, stride=2).transpose(1, 2).reshape(-1, 27).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("H,cpix,coff,Cc,k,s,p", [(112, 96, 0, 48, 3, 2, 1), (112, 96, 48, 48, 1, 2, 0), (28, 192, 0, 192, 3, 2, 1),
+                                                (14, 384, 0, 384, 3, 1, 1), (14, 384, 0, 384, 1, 1, 0)])
+def test_im2col_nhwc_bit_exact(H, cpix, coff, Cc, k, s, p):
+    B = 2
+    x = torch.randn(B, H, H, cpix, device="cuda").to(torch.bfloat16)
+    Ho = (H + 2 * p - k) // s + 1
+    ld, off = k * k * Cc + 16, 8
+    out = torch.full((B * Ho * Ho, ld), 5.0, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_im2col_nhwc(ptr(x), B, H, H, cpix, coff, Cc, k, s, p, ptr(out), ld, off, stream()))
+    nchw = x[..., coff:coff + Cc].permute(0, 3, 1, 2).float()
+    cols = F.unfold(nchw, k, padding=p, stride=s)                 # [B, C*k*k, Ho*Ho], index c*k*k + tap
+    ref = cols.view(B, Cc, k * k, Ho * Ho).permute(0, 3, 2, 1).reshape(B * Ho * Ho, k * k * Cc).to(torch.bfloat16)
+    assert torch.equal(out[:, off:off + k * k * Cc], ref)
+    assert torch.all(out[:, :off] == 5.0) and torch.all(out[:, off + k * k * Cc:] == 5.0)
+
+
+@pytest.mark.parametrize("H,cpix,coff,Cc,k", [(112, 96, 48, 48, 16), (56, 96, 0, 96, 8), (14, 384, 0, 384, 1), (7, 768, 0, 768, 1)])
+def test_patch_pool(H, cpix, coff, Cc, k):
+    B = 2
+    x = torch.randn(B, H, H, cpix, device="cuda").to(torch.bfloat16)
+    wt = torch.randn(Cc, 1, k, k, device="cuda") / k
+    bias = torch.randn(Cc, device="cuda")
+    w_packed = wt.view(Cc, k * k).t().contiguous()                # [k*k][C]
+    g = H // k
+    out = torch.empty(B * g * g, Cc, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_patch_pool(ptr(x), B, H, H, cpix, coff, Cc, k, ptr(w_packed), ptr(bias), ptr(out), stream()))
+    nchw = x[..., coff:coff + Cc].permute(0, 3, 1, 2).float()
+    ref = F.conv2d(nchw, wt, stride=k, groups=Cc) + bias[None, :, None, None]
+    ref = ref.flatten(2).transpose(1, 2).reshape(B * g * g, Cc)
+    r = rel(out.float(), ref)
+    _record(f"patch_pool/H{H}_k{k}", {"rel": r})
+    assert r < 3e-3
+
+
+@pytest.mark.parametrize("g", [7, 14])
+def test_adapter_tail_matches_oracle(g):
+    """Lateral adapter (M.py:1752-1778) through the oracle: BN folded by hand here, exactly as the engine does."""
+    B, D, L = 3, 768, g * g + 1
+    x = torch.randn(B, L, D, device="cuda")
+    t = torch.randn(B * g * g, D, device="cuda")
+    dw = torch.randn(D, 1, 3, 3, device="cuda") / 3
+    gamma, beta = torch.rand(D, device="cuda") + 0.5, torch.randn(D, device="cuda") * 0.1
+    mean, var = torch.randn(D, device="cuda") * 0.1, torch.rand(D, device="cuda") + 0.5
+    lw, lb = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    scale = gamma / torch.sqrt(var + 1e-5)
+    w9 = (dw.view(D, 9) * scale[:, None]).t().contiguous()
+    bias = beta - mean * scale
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().msclip_op_adapter_fuse_ln(ptr(x), ptr(t), ptr(w9), ptr(bias), ptr(lw), ptr(lb), ptr(out), B, g, stream()))
+    # oracle pieces
+    cls, tok = x[:, :1], x[:, 1:]
+    gmap = tok.transpose(1, 2).reshape(B, D, g, g)
+    bconv = F.conv2d(gmap, dw, padding=1, groups=D)
+    bconv = (bconv - mean[None, :, None, None]) / torch.sqrt(var + 1e-5)[None, :, None, None] * gamma[None, :, None, None] \
+        + beta[None, :, None, None]
+    y = torch.cat([cls + cls, bconv.flatten(2).transpose(1, 2) + t.view(B, g * g, D)], dim=1)
+    ref = O.layer_norm(y, lw, lb)
+    r = rel(out, ref)
+    _record(f"adapter_tail/g{g}", {"rel": r})
+    assert r < 1e-5
+
+
+@pytest.mark.parametrize("b,scale", [(8, math.e), (128, 14.2857), (300, 100.0), (1000, 14.2857), (4096, 100.0)])
+def test_contrastive_lse(b, scale):
+    g = torch.Generator(device="cuda").manual_seed(b)
+    fi = F.normalize(torch.randn(b, 512, device="cuda", generator=g), dim=-1)
+    ft = F.normalize(fi * 0.5 + torch.randn(b, 512, device="cuda", generator=g) * 0.05, dim=-1)   # correlated pairs
+    fi16, ft16 = fi.to(torch.bfloat16).contiguous(), ft.to(torch.bfloat16).contiguous()
+    ws = torch.empty(_lib.lib().msclip_op_contrastive_lse_workspace(b), device="cuda", dtype=torch.uint8)
+    parts = torch.zeros(2, device="cuda")
+    _lib.check(_lib.lib().msclip_op_contrastive_lse(ptr(fi16), ptr(ft16), b, scale, ptr(ws), ptr(parts), stream()))
+    logits = scale * fi16.double() @ ft16.double().t()
+    d = logits.diag()
+    ref0 = float((torch.logsumexp(logits, 1) - d).sum())
+    ref1 = float((torch.logsumexp(logits, 0) - d).sum())
+    got = parts.double().cpu()
+    loss = float(got.sum()) / (2 * b)
+    loss_ref = (ref0 + ref1) / (2 * b)
+    loss_fp32_feats = float(O.contrastive_loss(scale * fi @ ft.t()))
+    _record(f"contrastive_lse/b{b}", {"parts": got.tolist(), "ref": [ref0, ref1], "loss": loss, "loss_ref": loss_ref,
+                                      "loss_fp32_features": loss_fp32_feats})
+    assert abs(got[0] - ref0) <= 2e-5 * abs(ref0) + 1e-4 * b * 1e-2
+    assert abs(got[1] - ref1) <= 2e-5 * abs(ref1) + 1e-4 * b * 1e-2
+    assert abs(loss - loss_fp32_feats) <= 1e-3 * abs(loss_fp32_feats) + 1e-4
