@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the MS-CLIP-S encode-and-contrast hot path (BASELINE.json metric: image-text pairs/sec,
+MS-CLIP-S ViT-B/32, forward + global-batch contrastive loss).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over one batch of synthetic pairs: encode_image + encode_text +
+similarity + symmetric cross-entropy.  Weak scaling: every rank owns `--batch` (4096) pairs, the global
+batch is N x 4096 (32 768 at N = 8, BASELINE.json configs[3]); at N = 1 the workload is configs[1].
+Under torchrun one process drives one GPU; the only cross-rank traffic on the data path is the in-kernel
+NVLink read of the peers' embeddings inside the fused loss kernel.
+
+JSON keys: see the contract in the task statement; `value` is device-resident throughput, `e2e` goes
+through the public API with pinned HOST buffers (H2D of images/tokens and D2H of the loss inside the
+timed region), `roofline` times the dominant kernel (the shared-block fc1 GEMM) alone with CUDA events,
+`cpu_baseline` times the CPU oracle (a port of the reference forward) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from msclip_b200 import synth
+from msclip_b200.config import MSCLIPConfig
+
+METRIC = "image-text pairs/sec (forward + contrastive loss), MS-CLIP-S ViT-B/32"
+UNIT = "pairs/s"
+GF_PER_PAIR = {32: 23.549e9, 16: 49.617e9}        # BASELINE.md section 3 (2*m*n*k of every GEMM/bmm/conv)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_oracle_throughput(cfg, sd_np, sample: int, steps: int, warmup: int, seed: int = 1234):
+    """pairs/s of the CPU oracle (fp32 torch port of the reference forward + loss) with all host threads."""
+    from oracle import msclip_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.to_torch(sd_np)
+    img = torch.from_numpy(synth.synth_images(sample, seed, cfg.image_resolution))
+    tok = torch.from_numpy(synth.synth_tokens(sample, seed, cfg.context_length, cfg.vocab_size))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            logits = O.forward(img, tok, sd, cfg)
+            loss = float(O.contrastive_loss(logits))
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert math.isfinite(loss)
+    total = sum(times)
+    return sample * len(times) / total, total / len(times), torch.get_num_threads()
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    sd_np = synth.synth_state_dict(cfg, seed=0)
+    sample = args.cpu_sample
+    value, sec_per_step, cores = cpu_oracle_throughput(cfg, sd_np, sample, args.steps, args.warmup)
+    desc = f"{sample} pairs per step of the same synthetic workload, fp32, {cores} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, world):
+    name = (f"MS-CLIP-S ViT-B/{cfg.patch_size} full {cfg.layers}-layer shared encoder, batch {args.batch} synthetic "
+            f"224^2 + 77-token pairs per GPU")
+    return {"workload": name, "per_gpu_batch": args.batch, "global_batch": args.batch * world, "image": "3x224x224 f32",
+            "tokens": cfg.context_length, "parallelism": f"dp{world}", "l2": "inputs (2.5 GB/step) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args, cfg, rank, world, local):
+    from msclip_b200 import _lib
+    from msclip_b200.model import CLIP
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the MS-CLIP-S path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    sd_np = synth.synth_state_dict(cfg, seed=0)
+    model = CLIP(cfg)
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in sd_np.items()})
+    model = model.to(dev).eval()
+    model._sync_weights()
+    if world > 1:
+        model.setup_data_parallel(B)
+
+    # synthetic shard of this rank (rows rank*B .. rank*B+B of the global batch)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    img_dev = torch.randn(B, 3, cfg.image_resolution, cfg.image_resolution, device=dev, generator=g)
+    tok_np = synth.synth_tokens(B, 1234, cfg.context_length, cfg.vocab_size, offset=rank * B)
+    tok_dev = torch.from_numpy(tok_np).to(dev)
+    parts = torch.zeros(2, device=dev)
+    loss_dev = torch.zeros((), device=dev)
+    L = _lib.lib()
+    h = model._handle
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step_device():
+        _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_dev.data_ptr()), _lib.F32, C.c_void_p(tok_dev.data_ptr()), B,
+                                         C.c_void_p(parts.data_ptr()), C.c_void_p(loss_dev.data_ptr()) if world == 1 else None,
+                                         sp), "msclip_forward_loss")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.msclip_launch_count(h)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms) / 1e3, int(L.msclip_launch_count(h) - n0)
+
+    warmup = max(args.warmup, args.min_warmup)
+    for _ in range(warmup):
+        step_device()
+    with ClockSampler(local) as clocks:
+        sec, launches = timed(step_device, args.steps)
+    clock_summary = clocks.summary()
+    pairs = B * world * args.steps
+    value = pairs / sec
+    if world > 1:
+        p = parts.clone()
+        torch.distributed.all_reduce(p)
+        loss_value = float(p.sum() / (2.0 * world * B))
+    else:
+        loss_value = float(loss_dev)
+
+    # ---- end to end through the public C ABI with pinned HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        img_host = torch.empty(img_dev.shape, dtype=torch.float32).pin_memory()
+        img_host.copy_(img_dev)
+        tok_host = torch.from_numpy(tok_np).pin_memory()
+        out_host = torch.zeros(3).pin_memory()
+
+        def step_host():
+            _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_host.data_ptr()), _lib.F32, C.c_void_p(tok_host.data_ptr()), B,
+                                             C.c_void_p(out_host.data_ptr()),
+                                             C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
+                       "msclip_forward_loss(host)")
+
+        for _ in range(3):
+            step_host()
+        e2e_steps = max(3, min(args.steps, 10))
+        sec_h, _ = timed(step_host, e2e_steps)
+        e2e = {"value": B * world * e2e_steps / sec_h, "unit": UNIT, "ms_per_step": sec_h / e2e_steps * 1e3,
+               "h2d_bytes_per_step": int(img_host.numel() * 4 + tok_host.numel() * 8), "d2h_bytes_per_step": 12 if world == 1 else 8,
+               "steps": e2e_steps, "api": "msclip_forward_loss(host pointers)"}
+        del img_host
+
+    # ---- roofline of the dominant kernel: the shared-block fc1 GEMM (+bias+QuickGELU) at the text-tower M
+    pk = peaks()
+    M, N, K = B * cfg.context_length, 4 * cfg.width, cfg.width
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+
+    def gemm():
+        _lib.check(L.msclip_op_gemm(C.c_void_p(a.data_ptr()), K, C.c_void_p(w.data_ptr()), K, M, N, K, 1.0,
+                                    C.c_void_p(bias.data_ptr()), C.c_void_p(o.data_ptr()), N, None, 0, _lib.EPI_QGELU_BF16, sp))
+    for _ in range(3):
+        gemm()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record(stream)
+    for _ in range(reps):
+        gemm()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    gemm_s = e0.elapsed_time(e1) / 1e3 / reps
+    gemm_tf = 2.0 * M * N * K / gemm_s / 1e12
+    step_tf = value / world * GF_PER_PAIR[cfg.patch_size] / 1e12
+    roofline = {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel<256, QGELU> fc1 M={M} N={N} K={K}",
+                "achieved": gemm_tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": gemm_tf / pk["burst"],
+                "traffic": None, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+                "us_per_launch": gemm_s * 1e6,
+                "whole_step": {"achieved": step_tf, "peak": pk["sustained"], "frac": step_tf / pk["sustained"],
+                               "note": "per-GPU pairs/s x 23.549 GFLOP/pair against the sustained cuBLAS peak"}}
+    del a, w, o
+
+    if rank != 0:
+        return
+    cpu = None
+    if not args.no_cpu:
+        v, sec_step, cores = cpu_oracle_throughput(cfg, sd_np, args.cpu_sample, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"CPU oracle (torch fp32 port of the reference forward + loss), {args.cpu_sample} pairs x 2 timed steps"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world), "impl": "ours",
+        "loss": loss_value, "loss_expected_ln_G": math.log(B * world),
+        "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary, "roofline": roofline, "cpu_baseline": cpu,
+        "device_bytes": int(L.msclip_device_bytes(h)),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="pairs per GPU per step")
+    ap.add_argument("--patch", type=int, default=32, choices=[16, 32])
+    ap.add_argument("--layers", type=int, default=12)
+    ap.add_argument("--cpu-sample", type=int, default=32, help="pairs per CPU-oracle step")
+    ap.add_argument("--min-warmup", type=int, default=3, help="timing rule: at least 3 warm-up steps (lower only for profiling)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    cfg = MSCLIPConfig(patch_size=args.patch, layers=args.layers)
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+    else:
+        run_ours(args, cfg, rank, world, local)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -213,7 +213,7 @@ int msclip_op_contrastive_lse(const void* img_bf16, const void* txt_bf16, int b,
   MSCLIP_CHECK_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice, as_stream(stream)));
   return launch_contrastive_loss_ex(static_cast<const bf16*>(img_bf16), static_cast<const bf16*>(txt_bf16),
                                     reinterpret_cast<const bf16* const*>(tab), reinterpret_cast<const bf16* const*>(tab + 1),
-                                    nullptr, 0, 1, b, 512, scale, workspace, parts2, as_stream(stream));
+                                    nullptr, 0, 1, 0, b, 512, scale, workspace, parts2, as_stream(stream));
 }
 size_t msclip_op_contrastive_lse_workspace(int b) { return ((contrastive_loss_workspace_bytes(1, b) + 15) & ~size_t(15)) + 64; }
 

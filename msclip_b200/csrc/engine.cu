@@ -723,9 +723,9 @@ static int next_parity(const msclip_ctx* h) { return static_cast<int>((h->epoch 
 int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, float* out, int normalize,
                         cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));
-  MSCLIP_REQUIRE(batch >= 0 && image != nullptr && out != nullptr, "encode_image: bad arguments");
-  MSCLIP_REQUIRE(dtype == MSCLIP_F32 || dtype == MSCLIP_BF16 || dtype == MSCLIP_F16, "encode_image: unsupported image dtype");
   if (batch == 0) return 0;
+  MSCLIP_REQUIRE(batch > 0 && image != nullptr && out != nullptr, "encode_image: bad arguments");
+  MSCLIP_REQUIRE(dtype == MSCLIP_F32 || dtype == MSCLIP_BF16 || dtype == MSCLIP_F16, "encode_image: unsupported image dtype");
   MSCLIP_TRY(ensure_streams(h));
   const msclip_config& c = h->cfg;
   const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
@@ -763,8 +763,8 @@ int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, 
 
 int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));
-  MSCLIP_REQUIRE(batch >= 0 && tokens != nullptr && out != nullptr, "encode_text: bad arguments");
   if (batch == 0) return 0;
+  MSCLIP_REQUIRE(batch > 0 && tokens != nullptr && out != nullptr, "encode_text: bad arguments");
   const msclip_config& c = h->cfg;
   const int64_t* tok_dev = tokens;
   if (!is_device_pointer(tokens)) {
@@ -899,7 +899,7 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
   MSCLIP_TRY(ws_get(h, "loss_ws", contrastive_loss_workspace_bytes(W, b_local), &wsp));
   WS(parts, float, "loss_parts", 4);
   MSCLIP_TRY(launch_contrastive_loss_ex(xchg_slot(h, h->xchg, par, 0), xchg_slot(h, h->xchg, par, 1), img_tab, txt_tab,
-                                        flags, h->epoch, W, b_local, E, scale, wsp, parts, s));
+                                        flags, h->epoch, W, h->rank, b_local, E, scale, wsp, parts, s));
   count_launch(3);
   if (loss_out && W == 1) {
     finish_loss_kernel<<<1, 1, 0, s>>>(parts, 1.0f / (2.0f * b_local), parts + 2);

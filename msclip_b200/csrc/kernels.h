@@ -71,7 +71,7 @@ int launch_attention(const bf16* qkv, bf16* out, int batch, int L, int heads, in
 // `world` rank-ordered shard pointers; flags: this rank's device array of `world` publish flags or null.
 int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, const bf16* const* img_shards,
                                const bf16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
-                               int b_local, int E, float scale, void* workspace, float* loss_parts,
+                               int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
                                cudaStream_t stream);
 size_t contrastive_loss_workspace_bytes(int world, int b_local);
 // plain logits (eval path / parity): out[i,j] = scale * <a_i, b_j>, f32 [Ma, Mb]

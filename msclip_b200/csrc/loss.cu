@@ -33,9 +33,10 @@ struct LossParams {
   const bf16* const* col_shards[2];  // [dir] -> device table of `world` shard pointers (columns of that direction)
   const uint32_t* flags;             // optional: this rank's flag array [world], raised by the owners; null for world == 1
   uint32_t epoch;
-  int world, b_local, tiles_per_shard, n_col_tiles, n_row_blocks, b_pad;
+  int world, rank, b_local, tiles_per_shard, n_col_tiles, n_row_blocks, b_pad;
   float scale_log2;                  // exp(logit_scale) * log2(e): scores are kept in the log2 domain
   float2* ws;                        // [2][n_col_tiles][b_pad] (max, sum) partials, log2 domain
+  float* diag;                       // [2][b_pad] the diagonal scores s_ii taken from the same accumulators
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -172,6 +173,11 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kLossBN;
       float m = -INFINITY, l = 0.f;
+      // the tile that holds the positives of these rows: row i of the block meets column i of the tile.
+      // Taking s_ii from the very accumulator that also enters the log-sum-exp keeps lse_i - s_ii free of
+      // cancellation error (it is >= 0 by construction), which matters at large logit scales.
+      const bool diag_tile = (owner == p.rank) && (rb * 128 == c0);
+      float diag = 0.f;
 #pragma unroll 1
       for (int c = 0; c < kLossBN / 32; ++c) {
         uint32_t r[32];
@@ -183,6 +189,12 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
         for (int j = 0; j < 32; ++j) {
           v[j] = (c * 32 + j < valid_cols) ? __uint_as_float(r[j]) * p.scale_log2 : -INFINITY;
           cm = fmaxf(cm, v[j]);
+        }
+        if (diag_tile && c == q) {
+          float d = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) d = (lane == j) ? v[j] : d;
+          diag = d;
         }
         const float mn = fmaxf(m, cm);
         if (mn != -INFINITY) {
@@ -197,7 +209,10 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       const int row = rb * 128 + q * 32 + lane;
-      if (row < p.b_local) ws[row] = make_float2(m, l);
+      if (row < p.b_local) {
+        ws[row] = make_float2(m, l);
+        if (diag_tile) p.diag[dir * p.b_pad + row] = diag;
+      }
     }
   }
   tc_fence_before();
@@ -205,10 +220,10 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
-// per local row and direction: merge the column-tile partials, subtract the diagonal logit
+// per local row and direction: merge the column-tile partials, subtract the diagonal score
 __global__ void __launch_bounds__(256)
-lse_combine_kernel(const float2* __restrict__ ws, const bf16* __restrict__ img_local, const bf16* __restrict__ txt_local,
-                   int b_local, int b_pad, int n_col_tiles, float scale_log2, float* __restrict__ row_loss) {
+lse_combine_kernel(const float2* __restrict__ ws, const float* __restrict__ diag, int b_local, int b_pad,
+                   int n_col_tiles, float* __restrict__ row_loss) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= 2 * b_local) return;
   const int dir = idx / b_local, row = idx % b_local;
@@ -220,23 +235,8 @@ lse_combine_kernel(const float2* __restrict__ ws, const bf16* __restrict__ img_l
     const float2 e = w[static_cast<long long>(t) * b_pad];
     l += e.y * exp2f(e.x - m);
   }
-  // diagonal: same bf16 operands as the tensor-core product, fp32 accumulation
-  const uint4* a4 = reinterpret_cast<const uint4*>(img_local + static_cast<long long>(row) * kLossE);
-  const uint4* b4 = reinterpret_cast<const uint4*>(txt_local + static_cast<long long>(row) * kLossE);
-  float dot = 0.f;
-  for (int i = 0; i < kLossE / 8; ++i) {
-    const uint4 a = a4[i], b = b4[i];
-    const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-    const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&b);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 x = __bfloat1622float2(ah[j]), y = __bfloat1622float2(bh[j]);
-      dot = fmaf(x.x, y.x, dot);
-      dot = fmaf(x.y, y.y, dot);
-    }
-  }
-  // natural-log units: lse = ln2 * (m + log2 l); diag = scale * dot = ln2 * scale_log2 * dot
-  row_loss[idx] = kLn2 * (m + log2f(l) - scale_log2 * dot);
+  // scores are in log2 units (scale * log2 e folded in): lse_i - s_ii = ln2 * ((m - d) + log2 l)
+  row_loss[idx] = kLn2 * ((m - diag[dir * b_pad + row]) + log2f(l));
 }
 
 // deterministic reduction: out[dir] = sum_row row_loss[dir][row]
@@ -261,12 +261,13 @@ inline int pad128(int x) { return (x + 127) / 128 * 128; }
 
 size_t contrastive_loss_workspace_bytes(int world, int b_local) {
   const size_t tiles = static_cast<size_t>(world) * ((b_local + kLossBN - 1) / kLossBN);
-  return 2 * tiles * pad128(b_local) * sizeof(float2) + 2 * static_cast<size_t>(b_local) * sizeof(float);
+  return 2 * tiles * pad128(b_local) * sizeof(float2) + 2 * static_cast<size_t>(pad128(b_local)) * sizeof(float) +
+         2 * static_cast<size_t>(b_local) * sizeof(float);
 }
 
 int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, const bf16* const* img_shards,
                                const bf16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
-                               int b_local, int E, float scale, void* workspace, float* loss_parts,
+                               int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
                                cudaStream_t stream) {
   MSCLIP_REQUIRE(E == kLossE, "contrastive loss: embedding width must be 512");
   MSCLIP_REQUIRE(world >= 1 && b_local >= 1, "contrastive loss: empty problem");
@@ -282,6 +283,7 @@ int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, con
   p.flags = world > 1 ? flags : nullptr;
   p.epoch = epoch;
   p.world = world;
+  p.rank = rank;
   p.b_local = b_local;
   p.tiles_per_shard = (b_local + kLossBN - 1) / kLossBN;
   p.n_col_tiles = world * p.tiles_per_shard;
@@ -289,14 +291,15 @@ int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, con
   p.b_pad = pad128(b_local);
   p.scale_log2 = scale * kLog2e;
   p.ws = reinterpret_cast<float2*>(workspace);
-  float* row_loss = reinterpret_cast<float*>(p.ws + 2ll * p.n_col_tiles * p.b_pad);
+  p.diag = reinterpret_cast<float*>(p.ws + 2ll * p.n_col_tiles * p.b_pad);
+  float* row_loss = p.diag + 2 * p.b_pad;
   CUtensorMap ti, tt;
   MSCLIP_TRY(make_tmap_bf16_2d(&ti, img_local, b_local, kLossE, kLossE, 128));
   MSCLIP_TRY(make_tmap_bf16_2d(&tt, txt_local, b_local, kLossE, kLossE, 128));
   contrastive_lse_kernel<<<dim3(p.n_col_tiles, 2), kLossThreads, kLossSmem, stream>>>(ti, tt, p);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
-  lse_combine_kernel<<<(2 * b_local + 255) / 256, 256, 0, stream>>>(p.ws, img_local, txt_local, b_local, p.b_pad,
-                                                                    p.n_col_tiles, p.scale_log2, row_loss);
+  lse_combine_kernel<<<(2 * b_local + 255) / 256, 256, 0, stream>>>(p.ws, p.diag, b_local, p.b_pad, p.n_col_tiles,
+                                                                    row_loss);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   loss_reduce_kernel<<<2, 1024, 0, stream>>>(row_loss, b_local, loss_parts);
   MSCLIP_CHECK_CUDA(cudaGetLastError());

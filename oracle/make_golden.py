@@ -63,7 +63,8 @@ def run_case(name):
     def hook(tag, lnd=True):
         def fn(_m, _inp, out):
             o = out[1] if isinstance(out, tuple) else out       # Lateral_Adapter returns (top, bottom)
-            taps[tag] = sample(o.detach().permute(1, 0, 2) if lnd else o.detach())
+            if tag not in taps:      # first (fp32) forward only; later forwards (norm=False, autocast) must not overwrite
+                taps[tag] = sample(o.detach().permute(1, 0, 2) if lnd else o.detach())
         return fn
 
     vt = model.visual.transformer

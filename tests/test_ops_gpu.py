@@ -260,6 +260,8 @@ def test_contrastive_lse(b, scale):
     loss_fp32_feats = float(O.contrastive_loss(scale * fi @ ft.t()))
     _record(f"contrastive_lse/b{b}", {"parts": got.tolist(), "ref": [ref0, ref1], "loss": loss, "loss_ref": loss_ref,
                                       "loss_fp32_features": loss_fp32_feats})
-    assert abs(got[0] - ref0) <= 2e-5 * abs(ref0) + 1e-4 * b * 1e-2
-    assert abs(got[1] - ref1) <= 2e-5 * abs(ref1) + 1e-4 * b * 1e-2
+    # per row the kernel's fp32 (lse_i - s_ii) may differ from the float64 value by a few ulp of the score
+    assert abs(got[0] - ref0) <= 2e-5 * abs(ref0) + 3e-6 * b
+    assert abs(got[1] - ref1) <= 2e-5 * abs(ref1) + 3e-6 * b
+    assert float(got.min()) >= 0.0        # lse_i >= s_ii exactly: both come from the same accumulator
     assert abs(loss - loss_fp32_feats) <= 1e-3 * abs(loss_fp32_feats) + 1e-4
