@@ -36,6 +36,8 @@ enum {
 int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, float alpha,
                    const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epilogue,
                    void* stream);
+/* 1 (default): large GEMMs (N % 256 == 0, M >= 256) run on CTA pairs (cta_group::2); 0: always one CTA per tile. */
+void msclip_op_set_gemm_pair_mode(int enable);
 /* y[r,:] (bf16) = LN(x[r*row_stride,:]) over 768 columns, eps 1e-12 inside the sqrt. */
 int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
                         void* stream);

@@ -178,6 +178,7 @@ int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m
   return launch_gemm_scaled(static_cast<const bf16*>(a), lda, static_cast<const bf16*>(w), ldw, m, n, k, alpha, bias,
                             out, ldo, resid, ldr, epilogue, as_stream(stream));
 }
+void msclip_op_set_gemm_pair_mode(int enable) { gemm_set_pair_mode(enable); }
 int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
                         void* stream) {
   return launch_layernorm_bf16(x, row_stride, w, b, static_cast<bf16*>(y_bf16), rows, as_stream(stream));

@@ -6,11 +6,12 @@
 // weight [N,K]), accumulation is fp32 in TMEM, and the epilogue (bias, QuickGELU / ReLU, residual add
 // on the fp32 stream) is fused so no GEMM output ever makes an extra HBM round trip.
 //
-// CTA layout (256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
-//   warp 0   : TMA producer   (one lane)  global -> 128B-swizzled smem ring, kStages deep
-//   warp 1   : MMA issuer     (one lane)  tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM
-//   warp 2   : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
-//   warps 4-7: epilogue       tcgen05.ld -> registers -> fused math -> global stores
+// CTA layout (384 threads, 1 CTA / SM, persistent, static round-robin tile schedule):
+//   warp 0    : TMA producer   (one lane)  global -> 128B-swizzled smem ring, 4-8 stages deep
+//   warp 1    : MMA issuer     (one lane)  tcgen05.mma (128|256) x BN x 16, accumulators double-buffered in TMEM
+//   warp 2    : TMEM allocator (512 columns = 2 accumulator stages of up to 256 columns)
+//   warps 4-11: epilogue       tcgen05.ld -> registers -> fused math -> global stores (two warps per TMEM
+//                              lane quarter, each draining half of the tile's columns)
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
@@ -22,7 +23,8 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 256;
+constexpr int kNumEpilogueWarps = 8;
+constexpr int kGemmThreads = 128 + 32 * kNumEpilogueWarps;  // TMA, MMA, TMEM-alloc, spare + epilogue warps
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 
 struct GemmParams {
@@ -36,23 +38,27 @@ struct GemmParams {
   int vec_ok;   // rows of out / resid keep 16-byte alignment -> vector stores
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
+  static constexpr int kBRows = BN / CG;               // rows of W this CTA stages per k-block
   static constexpr int kStageA = kBM * kBK * 2;
-  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStageB = kBRows * kBK * 2;
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStagesRaw = (192 * 1024) / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kSmemBytes = kStages * kStage + kBarrierBytes + 1024;  // + alignment slack
   static constexpr int kChunk = (BN % 32 == 0) ? 32 : 16;                     // columns per tcgen05.ld
+  static constexpr int kNumChunks = BN / kChunk;
   static_assert(kStageB % 1024 == 0, "B stage must keep 1024-byte alignment");
-  static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint for M = 128");
+  static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint");
+  static_assert(CG == 1 || BN % 32 == 0, "pair tiles split N in two halves");
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x)   (M.py:224)
-  return x / (1.0f + __expf(-1.702f * x));
+  // 1 / (1 + 2^(-1.702 log2(e) x)) with MUFU.EX2 + MUFU.RCP (2^-22 relative error each)
+  return x * fast_rcp(1.0f + fast_ex2(-2.4554669595930157f * x));
 }
 
 template <int EPI, int CH>
@@ -122,11 +128,15 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ge
   }
 }
 
-template <int BN, int EPI>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile -
+// each CTA stages its own 128 rows of A and one half of the W rows, the leader issues M = 256 MMAs that read
+// both CTAs' shared memory, and each CTA's TMEM holds its 128 rows of the accumulator.  Halving the W bytes
+// per CTA cuts the L2 -> SM operand traffic per flop by a third and deepens the smem ring from 4 to 6 stages.
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
@@ -137,6 +147,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int first_tile = (CG == 2) ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
+  const int tile_step = (CG == 2) ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -149,16 +163,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kNumEpilogueWarps * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_kb = (p.K + kBK - 1) / kBK;
@@ -167,15 +186,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * kBM;
-        const int n0 = (tile % p.tiles_n) * BN;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const int m0 = (tile / p.tiles_n) * (kBM * CG) + static_cast<int>(cta_rank) * kBM;
+        const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1, 1);
           uint8_t* sa = smem + s * Cfg::kStage;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage);
-          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
-          tma_load_2d(sa + Cfg::kStageA, &tmap_b, &full_bar[s], kb * kBK, n0);
+          if (CG == 2) {
+            // both CTAs' bytes are counted on the leader's barrier, which the leader arms for the pair
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage * 2);
+            tma_load_2d_pair(sa, &tmap_a, bar, kb * kBK, m0);
+            tma_load_2d_pair(sa + Cfg::kStageA, &tmap_b, bar, kb * kBK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage);
+            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
+            tma_load_2d(sa + Cfg::kStageA, &tmap_b, &full_bar[s], kb * kBK, n0);
+          }
           if (++s == Cfg::kStages) {
             s = 0;
             ph ^= 1;
@@ -184,13 +211,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM * CG, BN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[as], aph ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
@@ -201,33 +228,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t b_addr = a_addr + Cfg::kStageA;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            const uint64_t da = umma_desc_sw128(a_addr + k * 32), db = umma_desc_sw128(b_addr + k * 32);
+            if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs) once these MMAs have read it
+          if (CG == 2) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
           if (++s == Cfg::kStages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
         as ^= 1;
         if (as == 0) aph ^= 1;
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;    // which half of the tile's column chunks this warp drains
+    constexpr int kPerHalf = (Cfg::kNumChunks + 1) / 2;
+    const int c_begin = half * kPerHalf;
+    const int c_end = (c_begin + kPerHalf < Cfg::kNumChunks) ? c_begin + kPerHalf : Cfg::kNumChunks;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * kBM;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      const int m0 = (tile / p.tiles_n) * (kBM * CG) + static_cast<int>(cta_rank) * kBM;
       const int n0 = (tile % p.tiles_n) * BN;
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN / Cfg::kChunk; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[Cfg::kChunk];
         if constexpr (Cfg::kChunk == 32) {
           tmem_ld_32x32(taddr + c * 32, reinterpret_cast<uint32_t(&)[32]>(r));
@@ -239,45 +273,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+        else mbar_arrive(&tempty_bar[as]);
+      }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (CG == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::kSmemBytes));
     configured = true;
   }
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  const int units = num_sms() / CG;  // CTAs or CTA pairs that can be resident
+  const int n = p.total_tiles < units ? p.total_tiles : units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MSCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, ta, tb, p));
   return 0;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t stream) {
   switch (epi) {
-    case EPI_BF16: return launch_variant<BN, EPI_BF16>(ta, tb, p, stream);
-    case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16>(ta, tb, p, stream);
-    case EPI_RELU_BF16: return launch_variant<BN, EPI_RELU_BF16>(ta, tb, p, stream);
-    case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32>(ta, tb, p, stream);
-    case EPI_F32: return launch_variant<BN, EPI_F32>(ta, tb, p, stream);
+    case EPI_BF16: return launch_variant<BN, EPI_BF16, CG>(ta, tb, p, stream);
+    case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16, CG>(ta, tb, p, stream);
+    case EPI_RELU_BF16: return launch_variant<BN, EPI_RELU_BF16, CG>(ta, tb, p, stream);
+    case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32, CG>(ta, tb, p, stream);
+    case EPI_F32: return launch_variant<BN, EPI_F32, CG>(ta, tb, p, stream);
   }
   set_last_error("launch_gemm: unknown epilogue " + std::to_string(epi));
   return 2;
 }
 
 }  // namespace
+
+static bool g_allow_pairs = true;
+void gemm_set_pair_mode(int enable) { g_allow_pairs = enable != 0; }
 
 int gemm_pick_bn(int N) {
   const int cands[6] = {256, 192, 128, 96, 64, 48};
@@ -305,11 +359,13 @@ int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, i
   bool vec_ok = ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                 (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   if (epi == EPI_RESID_F32) vec_ok = vec_ok && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;
+  // CTA pairs for the large transformer GEMMs (N a multiple of 256, at least one full pair tile of rows)
+  const int cg = (g_allow_pairs && bn == 256 && N % 256 == 0 && M >= 256) ? 2 : 1;
   CUtensorMap ta, tb;
   MSCLIP_TRY(make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
                                kBM));
   MSCLIP_TRY(make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
-                               static_cast<uint32_t>(bn)));
+                               static_cast<uint32_t>(bn / cg)));
   GemmParams p;
   p.M = M;
   p.N = N;
@@ -317,19 +373,20 @@ int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, i
   p.tiles_n = (N + bn - 1) / bn;
   p.alpha = alpha;
   p.vec_ok = vec_ok ? 1 : 0;
-  p.total_tiles = ((M + kBM - 1) / kBM) * p.tiles_n;
+  p.total_tiles = ((M + kBM * cg - 1) / (kBM * cg)) * p.tiles_n;
   p.bias = bias;
   p.out = out;
   p.resid = resid;
   p.ldo = ldo;
   p.ldr = ldr;
+  if (cg == 2) return launch_bn<256, 2>(ta, tb, p, epi, stream);
   switch (bn) {
-    case 256: return launch_bn<256>(ta, tb, p, epi, stream);
-    case 192: return launch_bn<192>(ta, tb, p, epi, stream);
-    case 128: return launch_bn<128>(ta, tb, p, epi, stream);
-    case 96: return launch_bn<96>(ta, tb, p, epi, stream);
-    case 64: return launch_bn<64>(ta, tb, p, epi, stream);
-    case 48: return launch_bn<48>(ta, tb, p, epi, stream);
+    case 256: return launch_bn<256, 1>(ta, tb, p, epi, stream);
+    case 192: return launch_bn<192, 1>(ta, tb, p, epi, stream);
+    case 128: return launch_bn<128, 1>(ta, tb, p, epi, stream);
+    case 96: return launch_bn<96, 1>(ta, tb, p, epi, stream);
+    case 64: return launch_bn<64, 1>(ta, tb, p, epi, stream);
+    case 48: return launch_bn<48, 1>(ta, tb, p, epi, stream);
   }
   return 2;
 }

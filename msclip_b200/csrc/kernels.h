@@ -24,6 +24,7 @@ enum GemmEpilogue {
 int launch_gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, const float* bias,
                 void* out, int64_t ldo, const float* resid, int64_t ldr, int epi, cudaStream_t stream);
 
+void gemm_set_pair_mode(int enable);  // 0 forces the single-CTA kernel (tests / A-B timing)
 int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
                        cudaStream_t stream);

@@ -1,0 +1,71 @@
+"""Worker for tests/test_multigpu.py (launched by torch.distributed.run, one rank per GPU).
+
+Checks the sharded contrastive step: every rank encodes its own shard, the fused loss kernel reads the
+peers' embeddings over NVLink (no collective on the data path), and the result must equal
+  (a) the single-process loss over the whole global batch (one handle, world = 1), and
+  (b) the reference-shaped comparator: NCCL all-gather (lib/utils/comm.py:140-154) + logits + symmetric CE.
+"""
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from msclip_b200 import synth                      # noqa: E402
+from msclip_b200.comm import gather_tensors       # noqa: E402
+from msclip_b200.config import MSCLIPConfig       # noqa: E402
+from msclip_b200.model import CLIP                # noqa: E402
+from oracle import msclip_oracle as O             # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    b_local = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+    layers = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = MSCLIPConfig(layers=layers, gather_tensors=True)
+    sd_np = synth.synth_state_dict(cfg, seed=5, logit_scale=math.log(1 / 0.07))
+    sd = {k: torch.as_tensor(v) for k, v in sd_np.items()}
+    model = CLIP(cfg)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    model.setup_data_parallel(b_local)
+    G = world * b_local
+    img = torch.from_numpy(synth.synth_images(b_local, 21, offset=rank * b_local)).to(dev)
+    tok = torch.from_numpy(synth.synth_tokens(b_local, 21, offset=rank * b_local, ragged=True)).to(dev)
+    out = {}
+    for it in range(3):                               # several epochs: exercises the double-buffered exchange
+        loss = float(model.contrastive_loss(img, tok))
+        out[f"fused_p2p_{it}"] = loss
+    # (b) NCCL comparator with the same per-rank features
+    fi, ft = model.encode_image(img), model.encode_text(tok)
+    fi_all, ft_all = gather_tensors(fi), gather_tensors(ft)
+    logits = math.exp(float(model.logit_scale)) * fi_all.double() @ ft_all.double().t()
+    out["nccl_gather_fp64"] = float(O.contrastive_loss(logits))
+    logits_api = model(img, tok)                      # CLIP.forward with GATHER_TENSORS -> [G, G] on every rank
+    assert logits_api.shape == (G, G)
+    out["forward_logits_loss"] = float(O.contrastive_loss(logits_api.double()))
+    # (a) single-process truth on rank 0 over the whole global batch
+    if rank == 0:
+        solo = CLIP(MSCLIPConfig(layers=layers))
+        solo.load_state_dict(sd)
+        solo = solo.to(dev).eval()
+        img_all = torch.from_numpy(synth.synth_images(G, 21)).to(dev)
+        tok_all = torch.from_numpy(synth.synth_tokens(G, 21, ragged=True)).to(dev)
+        out["single_process"] = float(solo.contrastive_loss(img_all, tok_all))
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_RESULT " + json.dumps(out), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

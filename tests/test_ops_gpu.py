@@ -112,6 +112,8 @@ GEMM_CASES = [
     ("logits_ragged",  1024,  1000, 1536, _lib.EPI_F32,         dict(bias=False, alpha=100.0)),
     ("ragged_bf16",    130,   200,  72,   _lib.EPI_BF16,        {}),
     ("one_row",        1,     64,   8,    _lib.EPI_F32,         {}),
+    ("pair_edge",      257,   256,  64,   _lib.EPI_BF16,        {}),
+    ("pair_big_k",     2048,  512,  3072, _lib.EPI_F32,         {}),
 ]
 
 
@@ -121,6 +123,19 @@ def test_gemm(name, M, N, K, epi, kw):
     _record(f"gemm/{name}", {"rel": r, "max_abs": mx})
     tol = 2e-5 if epi in (_lib.EPI_RESID_F32, _lib.EPI_F32) else 3e-3
     assert r < tol, (name, r, mx)
+
+
+@pytest.mark.parametrize("name", ["qkv", "fc1", "fc2", "many_tiles"])
+def test_gemm_single_cta_path_for_wide_tiles(name):
+    """The 256-wide tiles normally run on CTA pairs; the single-CTA kernel must give the same result."""
+    case = [c for c in GEMM_CASES if c[0] == name][0]
+    _lib.lib().msclip_op_set_gemm_pair_mode(0)
+    try:
+        r, mx = run_gemm(*case[1:5], **case[5])
+    finally:
+        _lib.lib().msclip_op_set_gemm_pair_mode(1)
+    _record(f"gemm_1cta/{name}", {"rel": r, "max_abs": mx})
+    assert r < (2e-5 if case[4] in (_lib.EPI_RESID_F32, _lib.EPI_F32) else 3e-3)
 
 
 def test_gemm_rejects_bad_arguments():

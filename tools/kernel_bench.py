@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Per-kernel timing on the B200 at the benchmark shapes (CUDA events, warm-up, L2 flushed between
+launches by rotating over operand sets larger than the 126 MB L2).  Writes gpurun_out/kernel_bench.json.
+
+    python tools/kernel_bench.py [--batch 4096] [--reps 10]
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch                                   # noqa: E402
+from msclip_b200 import _lib                   # noqa: E402
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def time_ms(fn, reps, warm=3):
+    s = torch.cuda.current_stream()
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(reps):
+        fn()
+    e1.record(s)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    L = _lib.lib()
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    peaks = {"tflops": 1653.1, "hbm": 6545.3}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            j = json.load(f)
+        peaks = {"tflops": j["bf16_tflops"], "hbm": j["hbm_gbs"]}
+    out = {"peaks": peaks, "batch": args.batch, "gemm": [], "other": []}
+    B = args.batch
+    shapes = []
+    for tower, Lseq in (("text", 77), ("image", 50)):
+        M = B * Lseq
+        shapes += [(f"{tower}/qkv", M, 2304, 768, _lib.EPI_BF16), (f"{tower}/out_proj", M, 768, 768, _lib.EPI_RESID_F32),
+                   (f"{tower}/fc1", M, 3072, 768, _lib.EPI_QGELU_BF16), (f"{tower}/fc2", M, 768, 3072, _lib.EPI_RESID_F32)]
+    for name, M, N, K, epi in shapes:
+        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        f32 = epi in (_lib.EPI_RESID_F32, _lib.EPI_F32)
+        o = torch.zeros(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+        for pair in (1, 0):
+            L.msclip_op_set_gemm_pair_mode(pair)
+            fn = lambda: _lib.check(L.msclip_op_gemm(ptr(a), K, ptr(w), K, M, N, K, 1.0, ptr(bias), ptr(o), N,
+                                                     ptr(o) if epi == _lib.EPI_RESID_F32 else None, N, epi, sp))
+            ms = time_ms(fn, args.reps)
+            tf = 2.0 * M * N * K / ms / 1e9
+            gb = (M * K * 2 + N * K * 2 + M * N * (4 if f32 else 2) * (2 if epi == _lib.EPI_RESID_F32 else 1)) / ms / 1e6
+            out["gemm"].append({"name": name, "M": M, "N": N, "K": K, "pair": pair, "ms": ms, "tflops": tf,
+                                "frac_tensor": tf / peaks["tflops"], "algorithmic_GBps": gb})
+            print(f"{name:16s} pair={pair} {ms:8.3f} ms {tf:7.1f} TF/s ({100 * tf / peaks['tflops']:.1f}%)  {gb:7.0f} GB/s", flush=True)
+        L.msclip_op_set_gemm_pair_mode(1)
+        del a, w, o
+    # LayerNorm (HBM-bound): M x 768 fp32 in, bf16 out
+    for tower, Lseq in (("text", 77), ("image", 50)):
+        M = B * Lseq
+        x = torch.randn(M, 768, device="cuda")
+        w, b = torch.randn(768, device="cuda"), torch.randn(768, device="cuda")
+        y = torch.empty(M, 768, device="cuda", dtype=torch.bfloat16)
+        ms = time_ms(lambda: _lib.check(L.msclip_op_layernorm(ptr(x), 1, ptr(w), ptr(b), ptr(y), M, sp)), args.reps)
+        gb = M * 768 * 6 / ms / 1e6
+        out["other"].append({"name": f"{tower}/layernorm", "ms": ms, "GBps": gb, "frac_hbm": gb / peaks["hbm"]})
+        print(f"{tower}/layernorm {ms:8.3f} ms {gb:7.0f} GB/s ({100 * gb / peaks['hbm']:.1f}% of HBM)", flush=True)
+        del x, y
+    # attention
+    for tower, Lseq, causal in (("text", 77, 1), ("image", 50, 0)):
+        M = B * Lseq
+        qkv = (torch.randn(M, 2304, device="cuda") * 0.5).to(torch.bfloat16)
+        o = torch.empty(M, 768, device="cuda", dtype=torch.bfloat16)
+        ms = time_ms(lambda: _lib.check(L.msclip_op_attention(ptr(qkv), ptr(o), B, Lseq, 12, causal, sp)), args.reps)
+        fl = 4.0 * Lseq * Lseq * 768 * B
+        gb = M * (2304 + 768) * 2 / ms / 1e6
+        out["other"].append({"name": f"{tower}/attention", "ms": ms, "tflops": fl / ms / 1e9, "GBps": gb, "frac_hbm": gb / peaks["hbm"]})
+        print(f"{tower}/attention {ms:8.3f} ms {fl / ms / 1e9:7.1f} TF/s {gb:7.0f} GB/s ({100 * gb / peaks['hbm']:.1f}% of HBM)", flush=True)
+        del qkv, o
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "kernel_bench.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
