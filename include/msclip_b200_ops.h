@@ -36,8 +36,9 @@ enum {
 int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, float alpha,
                    const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epilogue,
                    void* stream);
-/* 1 (default): large GEMMs (N % 256 == 0, M >= 256) run on CTA pairs (cta_group::2); 0: always one CTA per tile. */
-void msclip_op_set_gemm_pair_mode(int enable);
+/* Tiling of the large GEMMs (N % 256 == 0): 0 = one CTA per 128x256 tile, 1 = CTA pairs (cta_group::2, 256x256),
+ * 2 / 4 = clusters of 2 / 4 pairs that share the weight tile by TMA multicast; any other value = library default. */
+void msclip_op_set_gemm_pair_mode(int mode);
 /* y[r,:] (bf16) = LN(x[r*row_stride,:]) over 768 columns, eps 1e-12 inside the sqrt. */
 int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
                         void* stream);

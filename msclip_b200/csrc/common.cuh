@@ -179,6 +179,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Multicast variant: the box lands at the same smem offset in every CTA of `mask`; each destination's bytes
+// are reported to the barrier at `bar`'s offset in the even (leader) CTA of the destination's pair, which is
+// what the cleared peer bit (bit 24 of a shared-window address) selects.
+__device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, uint16_t mask,
+                                                       int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
@@ -200,11 +212,11 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a,
       : "memory");
 }
 // arrive on the barrier at the same smem offset in both CTAs of the pair once the MMAs issued so far are done
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
-      "h"(static_cast<uint16_t>(3))
+      "h"(cta_mask)
       : "memory");
 }
 __device__ __forceinline__ float fast_ex2(float x) {

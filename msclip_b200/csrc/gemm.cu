@@ -132,7 +132,9 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ge
 // each CTA stages its own 128 rows of A and one half of the W rows, the leader issues M = 256 MMAs that read
 // both CTAs' shared memory, and each CTA's TMEM holds its 128 rows of the accumulator.  Halving the W bytes
 // per CTA cuts the L2 -> SM operand traffic per flop by a third and deepens the smem ring from 4 to 6 stages.
-template <int BN, int EPI, int CG>
+// NP > 1 (CG = 2 only): NP CTA pairs form one cluster and work on NP vertically adjacent 256-row tiles of the
+// same column tile; every W slice is fetched from L2 once and TMA-multicast to the NP CTAs that need it.
+template <int BN, int EPI, int CG, int NP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
@@ -147,7 +149,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  static_assert(NP == 1 || CG == 2, "multicast clusters are built from CTA pairs");
+  const uint32_t cluster_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_rank & 1u;   // rank inside the CTA pair
+  const uint32_t pair_idx = cluster_rank >> 1;   // which pair of the cluster
+  const uint32_t leader_rank = cluster_rank & ~1u;
   const bool leader = cta_rank == 0;
   const int first_tile = (CG == 2) ? static_cast<int>(cluster_id_x()) : static_cast<int>(blockIdx.x);
   const int tile_step = (CG == 2) ? static_cast<int>(num_clusters_x()) : static_cast<int>(gridDim.x);
@@ -159,7 +165,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], NP);  // every pair that multicasts into this CTA must have consumed the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -187,17 +193,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int s = 0;
       uint32_t ph = 0;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-        const int m0 = (tile / p.tiles_n) * (kBM * CG) + static_cast<int>(cta_rank) * kBM;
+        const int m0 = (tile / p.tiles_n) * (kBM * CG * NP) + static_cast<int>(pair_idx) * (kBM * CG) +
+                       static_cast<int>(cta_rank) * kBM;
         const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1, 1);
           uint8_t* sa = smem + s * Cfg::kStage;
           if (CG == 2) {
             // both CTAs' bytes are counted on the leader's barrier, which the leader arms for the pair
-            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), leader_rank);
             if (leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage * 2);
             tma_load_2d_pair(sa, &tmap_a, bar, kb * kBK, m0);
-            tma_load_2d_pair(sa + Cfg::kStageA, &tmap_b, bar, kb * kBK, n0);
+            if (NP == 1) {
+              tma_load_2d_pair(sa + Cfg::kStageA, &tmap_b, bar, kb * kBK, n0);
+            } else {
+              // this CTA fetches slice `pair_idx` of its W half and multicasts it to the same-rank CTA of every pair
+              constexpr int kSliceRows = Cfg::kBRows / NP;
+              uint16_t mask = 0;
+#pragma unroll
+              for (int q = 0; q < NP; ++q) mask |= static_cast<uint16_t>(1u << (2 * q + cta_rank));
+              tma_load_2d_pair_mcast(sa + Cfg::kStageA + pair_idx * (kSliceRows * 128), &tmap_b, &full_bar[s], mask,
+                                     kb * kBK, n0 + static_cast<int>(pair_idx) * kSliceRows);
+            }
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage);
             tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
@@ -233,14 +250,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs) once these MMAs have read it
-          if (CG == 2) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+          if (CG == 2) umma_commit_pair(&empty_bar[s], static_cast<uint16_t>((1u << (2 * NP)) - 1u));
+          else umma_commit(&empty_bar[s]);
           if (++s == Cfg::kStages) {
             s = 0;
             ph ^= 1;
           }
         }
         // accumulator complete -> epilogue warps (of both CTAs)
-        if (CG == 2) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
+        if (CG == 2) umma_commit_pair(&tfull_bar[as], static_cast<uint16_t>(3u << (2 * pair_idx)));
+        else umma_commit(&tfull_bar[as]);
         as ^= 1;
         if (as == 0) aph ^= 1;
       }
@@ -254,7 +273,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int as = 0;
     uint32_t aph = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-      const int m0 = (tile / p.tiles_n) * (kBM * CG) + static_cast<int>(cta_rank) * kBM;
+      const int m0 = (tile / p.tiles_n) * (kBM * CG * NP) + static_cast<int>(pair_idx) * (kBM * CG) +
+                     static_cast<int>(cta_rank) * kBM;
       const int n0 = (tile % p.tiles_n) * BN;
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
@@ -274,7 +294,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), leader_rank));
         else mbar_arrive(&tempty_bar[as]);
       }
       as ^= 1;
@@ -288,41 +308,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, int NP>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg::kSmemBytes));
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG, NP>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int units = num_sms() / CG;  // CTAs or CTA pairs that can be resident
+  const int units = num_sms() / (CG * NP);  // CTAs, CTA pairs or clusters that can be resident
   const int n = p.total_tiles < units ? p.total_tiles : units;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(n * CG);
+  cfg.gridDim = dim3(n * CG * NP);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CG * NP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, ta, tb, p));
+  MSCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG, NP>, ta, tb, p));
   return 0;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int NP>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t stream) {
   switch (epi) {
-    case EPI_BF16: return launch_variant<BN, EPI_BF16, CG>(ta, tb, p, stream);
-    case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16, CG>(ta, tb, p, stream);
-    case EPI_RELU_BF16: return launch_variant<BN, EPI_RELU_BF16, CG>(ta, tb, p, stream);
-    case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32, CG>(ta, tb, p, stream);
-    case EPI_F32: return launch_variant<BN, EPI_F32, CG>(ta, tb, p, stream);
+    case EPI_BF16: return launch_variant<BN, EPI_BF16, CG, NP>(ta, tb, p, stream);
+    case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16, CG, NP>(ta, tb, p, stream);
+    case EPI_RELU_BF16: return launch_variant<BN, EPI_RELU_BF16, CG, NP>(ta, tb, p, stream);
+    case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32, CG, NP>(ta, tb, p, stream);
+    case EPI_F32: return launch_variant<BN, EPI_F32, CG, NP>(ta, tb, p, stream);
   }
   set_last_error("launch_gemm: unknown epilogue " + std::to_string(epi));
   return 2;
@@ -330,8 +350,12 @@ int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
 
 }  // namespace
 
-static bool g_allow_pairs = true;
-void gemm_set_pair_mode(int enable) { g_allow_pairs = enable != 0; }
+// 0: one CTA per tile; 1: CTA pairs; 2 / 4: clusters of 2 / 4 pairs with TMA multicast of the W tile
+constexpr int kDefaultPairMode = 1;
+static int g_pair_mode = kDefaultPairMode;
+void gemm_set_pair_mode(int mode) {
+  g_pair_mode = (mode == 0 || mode == 1 || mode == 2 || mode == 4) ? mode : kDefaultPairMode;  // anything else: default
+}
 
 int gemm_pick_bn(int N) {
   const int cands[6] = {256, 192, 128, 96, 64, 48};
@@ -360,12 +384,14 @@ int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, i
                 (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   if (epi == EPI_RESID_F32) vec_ok = vec_ok && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;
   // CTA pairs for the large transformer GEMMs (N a multiple of 256, at least one full pair tile of rows)
-  const int cg = (g_allow_pairs && bn == 256 && N % 256 == 0 && M >= 256) ? 2 : 1;
+  const int cg = (g_pair_mode >= 1 && bn == 256 && N % 256 == 0 && M >= 256) ? 2 : 1;
+  int np = 1;
+  if (cg == 2 && g_pair_mode >= 2) np = (g_pair_mode == 4 && M >= 4096) ? 4 : (M >= 1024 ? 2 : 1);
   CUtensorMap ta, tb;
   MSCLIP_TRY(make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
                                kBM));
   MSCLIP_TRY(make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
-                               static_cast<uint32_t>(bn / cg)));
+                               static_cast<uint32_t>(bn / cg / np)));
   GemmParams p;
   p.M = M;
   p.N = N;
@@ -373,20 +399,22 @@ int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, i
   p.tiles_n = (N + bn - 1) / bn;
   p.alpha = alpha;
   p.vec_ok = vec_ok ? 1 : 0;
-  p.total_tiles = ((M + kBM * cg - 1) / (kBM * cg)) * p.tiles_n;
+  p.total_tiles = ((M + kBM * cg * np - 1) / (kBM * cg * np)) * p.tiles_n;
   p.bias = bias;
   p.out = out;
   p.resid = resid;
   p.ldo = ldo;
   p.ldr = ldr;
-  if (cg == 2) return launch_bn<256, 2>(ta, tb, p, epi, stream);
+  if (cg == 2 && np == 4) return launch_bn<256, 2, 4>(ta, tb, p, epi, stream);
+  if (cg == 2 && np == 2) return launch_bn<256, 2, 2>(ta, tb, p, epi, stream);
+  if (cg == 2) return launch_bn<256, 2, 1>(ta, tb, p, epi, stream);
   switch (bn) {
-    case 256: return launch_bn<256, 1>(ta, tb, p, epi, stream);
-    case 192: return launch_bn<192, 1>(ta, tb, p, epi, stream);
-    case 128: return launch_bn<128, 1>(ta, tb, p, epi, stream);
-    case 96: return launch_bn<96, 1>(ta, tb, p, epi, stream);
-    case 64: return launch_bn<64, 1>(ta, tb, p, epi, stream);
-    case 48: return launch_bn<48, 1>(ta, tb, p, epi, stream);
+    case 256: return launch_bn<256, 1, 1>(ta, tb, p, epi, stream);
+    case 192: return launch_bn<192, 1, 1>(ta, tb, p, epi, stream);
+    case 128: return launch_bn<128, 1, 1>(ta, tb, p, epi, stream);
+    case 96: return launch_bn<96, 1, 1>(ta, tb, p, epi, stream);
+    case 64: return launch_bn<64, 1, 1>(ta, tb, p, epi, stream);
+    case 48: return launch_bn<48, 1, 1>(ta, tb, p, epi, stream);
   }
   return 2;
 }

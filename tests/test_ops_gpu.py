@@ -97,7 +97,7 @@ GEMM_CASES = [
     ("qkv",            1000,  2304, 768,  _lib.EPI_BF16,        {}),
     ("out_proj",       300,   768,  768,  _lib.EPI_RESID_F32,   {}),
     ("fc1",            128,   3072, 768,  _lib.EPI_QGELU_BF16,  {}),
-    ("fc2",            4173,  768,  3072, _lib.EPI_RESID_F32,   {}),
+    ("fc2",            5173,  768,  3072, _lib.EPI_RESID_F32,   {}),
     ("many_tiles",     40000, 768,  768,  _lib.EPI_BF16,        {}),
     ("conv_first",     5000,  96,   32,   _lib.EPI_RELU_BF16,   {}),
     ("conv_stem0",     3136,  96,   432,  _lib.EPI_RELU_BF16,   {}),
@@ -125,16 +125,17 @@ def test_gemm(name, M, N, K, epi, kw):
     assert r < tol, (name, r, mx)
 
 
-@pytest.mark.parametrize("name", ["qkv", "fc1", "fc2", "many_tiles"])
-def test_gemm_single_cta_path_for_wide_tiles(name):
-    """The 256-wide tiles normally run on CTA pairs; the single-CTA kernel must give the same result."""
+@pytest.mark.parametrize("mode", [0, 1, 2, 4])
+@pytest.mark.parametrize("name", ["qkv", "fc1", "fc2", "many_tiles", "pair_big_k"])
+def test_gemm_tile_modes_agree(name, mode):
+    """256-wide tiles can run on one CTA (0), a CTA pair (1) or multicast clusters of 2 / 4 pairs: same result."""
     case = [c for c in GEMM_CASES if c[0] == name][0]
-    _lib.lib().msclip_op_set_gemm_pair_mode(0)
+    _lib.lib().msclip_op_set_gemm_pair_mode(mode)
     try:
         r, mx = run_gemm(*case[1:5], **case[5])
     finally:
-        _lib.lib().msclip_op_set_gemm_pair_mode(1)
-    _record(f"gemm_1cta/{name}", {"rel": r, "max_abs": mx})
+        _lib.lib().msclip_op_set_gemm_pair_mode(-1)
+    _record(f"gemm_mode{mode}/{name}", {"rel": r, "max_abs": mx})
     assert r < (2e-5 if case[4] in (_lib.EPI_RESID_F32, _lib.EPI_F32) else 3e-3)
 
 

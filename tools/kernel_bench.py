@@ -21,7 +21,11 @@ def ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def time_ms(fn, reps, warm=3):
+WARM = 3
+
+
+def time_ms(fn, reps, warm=None):
+    warm = WARM if warm is None else warm
     s = torch.cuda.current_stream()
     for _ in range(warm):
         fn()
@@ -39,7 +43,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--only", default="", help="substring filter on the kernel names (profiling)")
     args = ap.parse_args()
+    global WARM
+    WARM = args.warm
     L = _lib.lib()
     sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     peaks = {"tflops": 1653.1, "hbm": 6545.3}
@@ -56,12 +64,14 @@ def main():
         shapes += [(f"{tower}/qkv", M, 2304, 768, _lib.EPI_BF16), (f"{tower}/out_proj", M, 768, 768, _lib.EPI_RESID_F32),
                    (f"{tower}/fc1", M, 3072, 768, _lib.EPI_QGELU_BF16), (f"{tower}/fc2", M, 768, 3072, _lib.EPI_RESID_F32)]
     for name, M, N, K, epi in shapes:
+        if args.only not in name:
+            continue
         a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
         bias = torch.randn(N, device="cuda")
         f32 = epi in (_lib.EPI_RESID_F32, _lib.EPI_F32)
         o = torch.zeros(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
-        for pair in (1, 0):
+        for pair in (4, 2, 1, 0):
             L.msclip_op_set_gemm_pair_mode(pair)
             fn = lambda: _lib.check(L.msclip_op_gemm(ptr(a), K, ptr(w), K, M, N, K, 1.0, ptr(bias), ptr(o), N,
                                                      ptr(o) if epi == _lib.EPI_RESID_F32 else None, N, epi, sp))
@@ -71,10 +81,12 @@ def main():
             out["gemm"].append({"name": name, "M": M, "N": N, "K": K, "pair": pair, "ms": ms, "tflops": tf,
                                 "frac_tensor": tf / peaks["tflops"], "algorithmic_GBps": gb})
             print(f"{name:16s} pair={pair} {ms:8.3f} ms {tf:7.1f} TF/s ({100 * tf / peaks['tflops']:.1f}%)  {gb:7.0f} GB/s", flush=True)
-        L.msclip_op_set_gemm_pair_mode(1)
+        L.msclip_op_set_gemm_pair_mode(-1)
         del a, w, o
     # LayerNorm (HBM-bound): M x 768 fp32 in, bf16 out
     for tower, Lseq in (("text", 77), ("image", 50)):
+        if args.only not in f"{tower}/layernorm":
+            continue
         M = B * Lseq
         x = torch.randn(M, 768, device="cuda")
         w, b = torch.randn(768, device="cuda"), torch.randn(768, device="cuda")
@@ -86,6 +98,8 @@ def main():
         del x, y
     # attention
     for tower, Lseq, causal in (("text", 77, 1), ("image", 50, 0)):
+        if args.only not in f"{tower}/attention":
+            continue
         M = B * Lseq
         qkv = (torch.randn(M, 2304, device="cuda") * 0.5).to(torch.bfloat16)
         o = torch.empty(M, 768, device="cuda", dtype=torch.bfloat16)
