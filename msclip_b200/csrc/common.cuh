@@ -166,8 +166,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics: ordering against the TMEM reads it publishes comes
+// from tcgen05.wait::ld + tcgen05.fence::before_thread_sync; a cluster-scope release would add a MEMBAR.ALL.GPU
+// that stalls the epilogue warp until all of its global stores have drained.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair: data lands in this CTA's smem, the transaction bytes are
 // reported to the mbarrier at `bar_cluster_addr` (the leader CTA's barrier)

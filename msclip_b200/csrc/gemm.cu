@@ -61,12 +61,40 @@ __device__ __forceinline__ float quick_gelu(float x) {
   return x * fast_rcp(1.0f + fast_ex2(-2.4554669595930157f * x));
 }
 
+// Operands the epilogue needs from global memory for one chunk (bias slice, residual row segment); fetched
+// before the accumulator chunk is waited for so that their latency overlaps the TMEM load.
 template <int EPI, int CH>
-__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const GemmParams& p, int row, int col0) {
+struct EpiOperands {
+  float4 bias[CH / 4];
+  float4 resid[(EPI == EPI_RESID_F32) ? CH / 4 : 1];
+};
+
+template <int EPI, int CH>
+__device__ __forceinline__ void epilogue_prefetch(EpiOperands<EPI, CH>& o, const GemmParams& p, int row, int col0,
+                                                  bool fast) {
+  if (!fast) return;
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) o.bias[j] = __ldg(b4 + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) o.bias[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (EPI == EPI_RESID_F32) {
+    const float4* x4 = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) o.resid[j] = x4[j];
+  }
+}
+
+template <int EPI, int CH>
+__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const EpiOperands<EPI, CH>& o,
+                                               const GemmParams& p, int row, int col0, bool fast) {
   float v[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-  if (!p.vec_ok || col0 + CH > p.N) {
+  if (!fast) {
     // ragged edge (N not a multiple of the tile) or unaligned rows: scalar, bounds-checked
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -84,16 +112,12 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ge
     }
     return;
   }
-  if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-    for (int j = 0; j < CH / 4; ++j) {
-      const float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x;
-      v[4 * j + 1] += b.y;
-      v[4 * j + 2] += b.z;
-      v[4 * j + 3] += b.w;
-    }
+  for (int j = 0; j < CH / 4; ++j) {
+    v[4 * j + 0] += o.bias[j].x;
+    v[4 * j + 1] += o.bias[j].y;
+    v[4 * j + 2] += o.bias[j].z;
+    v[4 * j + 3] += o.bias[j].w;
   }
   if (EPI == EPI_QGELU_BF16) {
 #pragma unroll
@@ -103,28 +127,33 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ge
     for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
   if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
-    float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
     if (EPI == EPI_RESID_F32) {
-      const float4* x4 = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
 #pragma unroll
       for (int j = 0; j < CH / 4; ++j) {
-        const float4 x = x4[j];
-        v[4 * j + 0] += x.x;
-        v[4 * j + 1] += x.y;
-        v[4 * j + 2] += x.z;
-        v[4 * j + 3] += x.w;
+        v[4 * j + 0] += o.resid[j].x;
+        v[4 * j + 1] += o.resid[j].y;
+        v[4 * j + 2] += o.resid[j].z;
+        v[4 * j + 3] += o.resid[j].w;
       }
     }
-    float4* o4 = reinterpret_cast<float4*>(o);
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
 #pragma unroll
     for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   } else {
-    bf16* o = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
 #pragma unroll
     for (int j = 0; j < CH / 8; ++j)
       o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH]) {
+  if constexpr (CH == 32) {
+    tmem_ld_32x32(taddr, r);
+  } else {
+    tmem_ld_32x16(taddr, r);
   }
 }
 
@@ -280,16 +309,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const int row = m0 + q * 32 + lane;
-#pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[Cfg::kChunk];
-        if constexpr (Cfg::kChunk == 32) {
-          tmem_ld_32x32(taddr + c * 32, reinterpret_cast<uint32_t(&)[32]>(r));
-        } else {
-          tmem_ld_32x16(taddr + c * 16, reinterpret_cast<uint32_t(&)[16]>(r));
+      // software pipeline: the TMEM load of chunk c+1 and the global operands of chunk c are in flight while
+      // chunk c is converted and stored (tcgen05.wait::ld waits for every outstanding load, so the next load
+      // is issued right after the wait)
+      const bool row_ok = row < p.M;
+      uint32_t acc[2][Cfg::kChunk];
+      tmem_ld_chunk<Cfg::kChunk>(taddr + c_begin * Cfg::kChunk, acc[0]);
+#pragma unroll
+      for (int i = 0; i < kPerHalf; ++i) {
+        const int c = c_begin + i;
+        if (c < c_end) {
+          const int col0 = n0 + c * Cfg::kChunk;
+          const bool fast = p.vec_ok && (col0 + Cfg::kChunk <= p.N);
+          EpiOperands<EPI, Cfg::kChunk> ops;
+          if (row_ok) epilogue_prefetch<EPI, Cfg::kChunk>(ops, p, row, col0, fast);
+          tmem_ld_wait();
+          if (c + 1 < c_end) tmem_ld_chunk<Cfg::kChunk>(taddr + (c + 1) * Cfg::kChunk, acc[(i + 1) & 1]);
+          if (row_ok) epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, p, row, col0, fast);
         }
-        tmem_ld_wait();
-        if (row < p.M) epilogue_store<EPI, Cfg::kChunk>(r, p, row, n0 + c * Cfg::kChunk);
       }
       tc_fence_before();
       __syncwarp();

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--modes", type=int, nargs="+", default=[1, 0], help="GEMM tiling modes to time (0, 1, 2, 4)")
     ap.add_argument("--only", default="", help="substring filter on the kernel names (profiling)")
     args = ap.parse_args()
     global WARM
@@ -71,7 +72,14 @@ def main():
         bias = torch.randn(N, device="cuda")
         f32 = epi in (_lib.EPI_RESID_F32, _lib.EPI_F32)
         o = torch.zeros(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
-        for pair in (4, 2, 1, 0):
+        # comparator only (not on the product path): cuBLAS via torch.matmul on the same operands, same moment
+        o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ms = time_ms(lambda: torch.matmul(a, w.t(), out=o16), args.reps)
+        tf = 2.0 * M * N * K / ms / 1e9
+        out["gemm"].append({"name": name, "M": M, "N": N, "K": K, "pair": "cublas(no epilogue)", "ms": ms, "tflops": tf})
+        print(f"{name:16s} cuBLAS {ms:8.3f} ms {tf:7.1f} TF/s  (plain bf16 GEMM, no bias/activation/residual)", flush=True)
+        del o16
+        for pair in args.modes:
             L.msclip_op_set_gemm_pair_mode(pair)
             fn = lambda: _lib.check(L.msclip_op_gemm(ptr(a), K, ptr(w), K, M, N, K, 1.0, ptr(bias), ptr(o), N,
                                                      ptr(o) if epi == _lib.EPI_RESID_F32 else None, N, epi, sp))
