@@ -9,6 +9,7 @@
  *   msclip_op_attention       Attention_CUST.forward core           M.py:707-738
  *   msclip_op_im2col_first    gather for the 3x3/s2 first convs     M.py:1952, 2154 (EarlyconvRes / branch)
  *   msclip_op_im2col_nhwc     gather for the later convs            M.py:1920-1936, 1842-1861
+ *   msclip_op_conv_gemm       conv3x3 / strided conv1x1 (+BN+ReLU)  M.py:1920-1936, 1842-1861 (implicit GEMM)
  *   msclip_op_patch_pool      Lateral_Adapter.top2bottom_dw_conv    M.py:1756
  *   msclip_op_adapter_fuse_ln Lateral_Adapter tail                  M.py:1760-1777
  *   msclip_op_contrastive_lse similarity + symmetric CE partials    M.py:3141 + north-star loss
@@ -48,6 +49,12 @@ int msclip_op_attention(const void* qkv_bf16, void* out_bf16, int batch, int seq
 int msclip_op_im2col_first(const void* img, int dtype, void* out_bf16, int batch, int height, int width, void* stream);
 int msclip_op_im2col_nhwc(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                           int ksize, int stride, int pad, void* out_bf16, int64_t out_ld, int out_off, void* stream);
+/* Implicit-GEMM convolution: out[batch*ho*wo, n] = epi(patches . w^T + bias); K = (ky,kx,c) patch of source 0
+ * followed by that of the optional source 1 (in1 = NULL: single source).  NHWC bf16 inputs. */
+int msclip_op_conv_gemm(const void* in0, int h0, int w0, int cpix0, int coff0, int c0, int k0, int s0, int p0, const void* in1,
+                        int h1, int w1, int cpix1, int coff1, int c1, int k1, int s1, int p1, int batch, int ho, int wo,
+                        const void* w_bf16, int64_t ldw, int n, const float* bias, void* out, int64_t ldo, int epilogue,
+                        void* stream);
 int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                          int k, const float* w, const float* bias, void* out_bf16, void* stream);
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,

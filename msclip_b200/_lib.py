@@ -57,6 +57,8 @@ _SIGNATURES = {
     "msclip_op_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "msclip_op_im2col_first": (_I, [_P, _I, _P, _I, _I, _I, _P]),
     "msclip_op_im2col_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P]),
+    "msclip_op_conv_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P,
+                                _P, _L, _I, _P]),
     "msclip_op_patch_pool": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "msclip_op_adapter_fuse_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "msclip_op_contrastive_lse": (_I, [_P, _P, _I, _F, _P, _P, _P]),

@@ -16,8 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(HERE, "libmsclip_b200.so")
-SOURCES = ["runtime.cu", "gemm.cu", "elementwise.cu", "conv.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
-HEADERS = ["common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
+SOURCES = ["runtime.cu", "gemm.cu", "conv_gemm.cu", "elementwise.cu", "conv.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
+HEADERS = ["common.cuh", "gemm_common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
            os.path.join("..", "..", "include", "msclip_b200_ops.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -196,6 +196,14 @@ int msclip_op_im2col_nhwc(const void* in_bf16, int batch, int height, int width,
   return launch_im2col_nhwc(static_cast<const bf16*>(in_bf16), batch, height, width, cpix, c_off, channels, ksize, stride,
                             pad, static_cast<bf16*>(out_bf16), out_ld, out_off, as_stream(stream));
 }
+int msclip_op_conv_gemm(const void* in0, int h0, int w0, int cpix0, int coff0, int c0, int k0, int s0, int p0, const void* in1,
+                        int h1, int w1, int cpix1, int coff1, int c1, int k1, int s1, int p1, int batch, int ho, int wo,
+                        const void* w_bf16, int64_t ldw, int n, const float* bias, void* out, int64_t ldo, int epilogue,
+                        void* stream) {
+  ConvSource src[2] = {{in0, h0, w0, cpix0, coff0, c0, k0, s0, p0}, {in1, h1, w1, cpix1, coff1, c1, k1, s1, p1}};
+  return launch_conv_gemm(src, in1 ? 2 : 1, batch, ho, wo, static_cast<const bf16*>(w_bf16), ldw, n, bias, out, ldo, epilogue,
+                          as_stream(stream));
+}
 int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                          int k, const float* w, const float* bias, void* out_bf16, void* stream) {
   return launch_patch_pool(static_cast<const bf16*>(in_bf16), batch, height, width, cpix, c_off, channels, k, w, bias,

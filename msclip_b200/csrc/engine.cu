@@ -2,6 +2,7 @@
 // sequences of encode_image / encode_text / forward / contrastive loss.  See engine.h.
 #include "engine.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -525,6 +526,11 @@ static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch,
   return 0;
 }
 
+// MSCLIP_CONV_IM2COL=1 selects the explicit im2col + GEMM formulation of the convolutions (A/B timing)
+static const bool g_conv_im2col = [] {
+  const char* e = getenv("MSCLIP_CONV_IM2COL");
+  return e != nullptr && e[0] == '1';
+}();
 static const int kLateral[5] = {2, 4, 6, 8, 10};  // PARALLEL_LATERAL_LAYER, b32-yfcc-msclips.yaml:18
 static const int kConvChunk = 256;                 // images per pass through the conv stages
 static const int kTowerChunk = 4096;               // sequences per pass through the transformer
@@ -593,11 +599,17 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
       bf16* outs[2] = {actA, actB};
       for (int i = 0; i < 4; ++i) {
         const int st = c.early_strides[i], Ho = Hc / st;
-        MSCLIP_TRY(launch_im2col_nhwc(cur, nb, Hc, Hc, cpix, 0, ch, 3, st, 1, col, 9 * ch, 0, s));
         bf16* o = outs[i & 1];
-        MSCLIP_TRY(launch_gemm(col, 9 * ch, h->stem[i].w, 9 * ch, nb * Ho * Ho, 2 * ch, 9 * ch, h->stem[i].b, o, 2 * ch,
-                               nullptr, 0, EPI_RELU_BF16, s));
-        count_launch(2);
+        if (g_conv_im2col) {
+          MSCLIP_TRY(launch_im2col_nhwc(cur, nb, Hc, Hc, cpix, 0, ch, 3, st, 1, col, 9 * ch, 0, s));
+          MSCLIP_TRY(launch_gemm(col, 9 * ch, h->stem[i].w, 9 * ch, nb * Ho * Ho, 2 * ch, 9 * ch, h->stem[i].b, o, 2 * ch,
+                                 nullptr, 0, EPI_RELU_BF16, s));
+        } else {
+          const ConvSource src = {cur, Hc, Hc, cpix, 0, ch, 3, st, 1};
+          MSCLIP_TRY(launch_conv_gemm(&src, 1, nb, Ho, Ho, h->stem[i].w, 9 * ch, 2 * ch, h->stem[i].b, o, 2 * ch,
+                                      EPI_RELU_BF16, s));
+        }
+        count_launch(g_conv_im2col ? 2 : 1);
         cur = o;
         cpix = 2 * ch;
         ch *= 2;
@@ -621,24 +633,36 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         // y1 = relu(bn1(conv1x1(p)))
         MSCLIP_TRY(launch_gemm(p + coff, cpix, h->br1[j].w, cin, nb * Hc * Hc, cin, cin, h->br1[j].b, actC, cin, nullptr,
                                0, EPI_RELU_BF16, s));
-        // y2 = relu(bn2(conv3x3_s(y1)))  -> columns [0, cin) of the concatenated operand
-        MSCLIP_TRY(launch_im2col_nhwc(actC, nb, Hc, Hc, cin, 0, cin, 3, st, 1, col, 9 * cin, 0, s));
-        bf16* cat = actC;  // y1 is dead once its im2col exists
-        MSCLIP_TRY(launch_gemm(col, 9 * cin, h->br2[j].w, 9 * cin, nb * Ho * Ho, cin, 9 * cin, h->br2[j].b, cat, 2 * cin,
-                               nullptr, 0, EPI_RELU_BF16, s));
-        // strided shortcut input -> columns [cin, 2cin)
-        MSCLIP_TRY(launch_im2col_nhwc(p, nb, Hc, Hc, cpix, coff, cin, 1, st, 0, cat, 2 * cin, cin, s));
-        // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p)))
         bf16* pn = pbuf[j & 1];
-        MSCLIP_TRY(launch_gemm(cat, 2 * cin, h->br3[j].w, 2 * cin, nb * Ho * Ho, 2 * cin, 2 * cin, h->br3[j].b, pn,
-                               2 * cin, nullptr, 0, EPI_RELU_BF16, s));
+        if (g_conv_im2col) {
+          // y2 = relu(bn2(conv3x3_s(y1)))  -> columns [0, cin) of the concatenated operand
+          MSCLIP_TRY(launch_im2col_nhwc(actC, nb, Hc, Hc, cin, 0, cin, 3, st, 1, col, 9 * cin, 0, s));
+          bf16* cat = actC;  // y1 is dead once its im2col exists
+          MSCLIP_TRY(launch_gemm(col, 9 * cin, h->br2[j].w, 9 * cin, nb * Ho * Ho, cin, 9 * cin, h->br2[j].b, cat, 2 * cin,
+                                 nullptr, 0, EPI_RELU_BF16, s));
+          // strided shortcut input -> columns [cin, 2cin)
+          MSCLIP_TRY(launch_im2col_nhwc(p, nb, Hc, Hc, cpix, coff, cin, 1, st, 0, cat, 2 * cin, cin, s));
+          // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p)))
+          MSCLIP_TRY(launch_gemm(cat, 2 * cin, h->br3[j].w, 2 * cin, nb * Ho * Ho, 2 * cin, 2 * cin, h->br3[j].b, pn,
+                                 2 * cin, nullptr, 0, EPI_RELU_BF16, s));
+          count_launch(2);
+        } else {
+          // y2 = relu(bn2(conv3x3_s(y1))): implicit GEMM straight from y1
+          bf16* y2 = col;
+          const ConvSource s2 = {actC, Hc, Hc, cin, 0, cin, 3, st, 1};
+          MSCLIP_TRY(launch_conv_gemm(&s2, 1, nb, Ho, Ho, h->br2[j].w, 9 * cin, cin, h->br2[j].b, y2, cin, EPI_RELU_BF16, s));
+          // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p))): one GEMM over K = [y2 | strided p]
+          const ConvSource s3[2] = {{y2, Ho, Ho, cin, 0, cin, 1, 1, 0}, {p, Hc, Hc, cpix, coff, cin, 1, st, 0}};
+          MSCLIP_TRY(launch_conv_gemm(s3, 2, nb, Ho, Ho, h->br3[j].w, 2 * cin, 2 * cin, h->br3[j].b, pn, 2 * cin,
+                                      EPI_RELU_BF16, s));
+        }
         p = pn;
         cpix = 2 * cin;
         coff = 0;
         Hc = Ho;
         MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, 0, dims[j], h->adapters[j].k, h->adapters[j].dw_w,
                                      h->adapters[j].dw_b, pooled[j] + static_cast<size_t>(b0) * g * g * dims[j], s));
-        count_launch(6);
+        count_launch(4);
       }
     }
   }

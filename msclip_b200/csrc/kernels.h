@@ -61,6 +61,16 @@ int launch_im2col_nhwc(const bf16* in, int batch, int H, int W, int cpix, int c_
 int launch_patch_pool(const bf16* in, int batch, int H, int W, int cpix, int c_off, int C, int k, const float* w,
                       const float* bias, bf16* out, cudaStream_t stream);
 
+// ---- implicit-GEMM convolution (conv_gemm.cu): out[B*Ho*Wo, N] = epi(patches . W^T + bias) ---------------
+// K is the concatenation of the sources' (ky, kx, c) patch vectors; every source must map onto the same
+// Ho x Wo output grid.  NHWC bf16 inputs with pixel pitch cpix, channel window [c_off, c_off + C).
+struct ConvSource {
+  const void* in;
+  int H, W, cpix, c_off, C, ksize, stride, pad;
+};
+int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const bf16* W, int64_t ldw, int N,
+                     const float* bias, void* out, int64_t ldo, int epi, cudaStream_t stream);
+
 // ---- attention (attention.cu): qkv bf16 [B*L, 3*768] (q pre-scaled) -> out bf16 [B*L, 768] ------
 int launch_attention(const bf16* qkv, bf16* out, int batch, int L, int heads, int causal, cudaStream_t stream);
 

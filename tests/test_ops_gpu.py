@@ -211,6 +211,60 @@ def test_im2col_nhwc_bit_exact(H, cpix, coff, Cc, k, s, p):
     assert torch.all(out[:, :off] == 5.0) and torch.all(out[:, off + k * k * Cc:] == 5.0)
 
 
+CONV_CASES = [
+    # name,        B, H,   cpix, coff, C,   k, s, p, N
+    ("stem0",      3, 112, 96,   0,    48,  3, 2, 1, 96),
+    ("stem1",      3, 56,  96,   0,    96,  3, 2, 1, 192),
+    ("stem3",      5, 14,  384,  0,    384, 3, 2, 1, 768),
+    ("b16_stem3",  2, 14,  384,  0,    384, 3, 1, 1, 768),
+    ("branch2_48", 2, 112, 48,   0,    48,  3, 2, 1, 48),
+    ("one_image",  1, 28,  192,  0,    192, 3, 2, 1, 384),
+]
+
+
+@pytest.mark.parametrize("name,B,H,cpix,coff,Cc,k,s,p,N", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm_matches_conv2d(name, B, H, cpix, coff, Cc, k, s, p, N):
+    """Implicit-GEMM conv (+bias+ReLU) against F.conv2d on the same bf16-rounded operands."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, H, H, cpix, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, Cc, k, k, device="cuda", generator=g) / math.sqrt(Cc * k * k)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    Ho = (H + 2 * p - k) // s + 1
+    wk = w.permute(0, 2, 3, 1).reshape(N, k * k * Cc).contiguous()         # K order (ky, kx, c)
+    out = torch.zeros(B * Ho * Ho, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_conv_gemm(ptr(x), H, H, cpix, coff, Cc, k, s, p, None, 0, 0, 0, 0, 0, 0, 0, 0, B, Ho, Ho,
+                                              ptr(wk), k * k * Cc, N, ptr(bias), ptr(out), N, _lib.EPI_RELU_BF16, stream()))
+    nchw = x[..., coff:coff + Cc].permute(0, 3, 1, 2).float()
+    ref = torch.relu(F.conv2d(nchw, w.float(), bias, stride=s, padding=p)).permute(0, 2, 3, 1).reshape(B * Ho * Ho, N)
+    r = rel(out.float(), ref)
+    _record(f"conv_gemm/{name}", {"rel": r})
+    assert r < 3e-3, r
+
+
+@pytest.mark.parametrize("H,cin,stride", [(112, 48, 2), (28, 192, 2), (14, 384, 1)])
+def test_conv_gemm_two_sources(H, cin, stride):
+    """ConvResBlock tail (M.py:1855-1861): relu(conv1x1(y2) + conv1x1_stride(p)) as one GEMM over K = [y2 | p]."""
+    B = 2
+    Ho = H // stride
+    g = torch.Generator(device="cuda").manual_seed(2)
+    cpix, coff = (2 * cin, cin) if H == 112 else (cin, 0)
+    pfeat = torch.randn(B, H, H, cpix, device="cuda", generator=g).to(torch.bfloat16)
+    y2 = torch.randn(B, Ho, Ho, cin, device="cuda", generator=g).to(torch.bfloat16)
+    w3 = (torch.randn(2 * cin, cin, device="cuda", generator=g) / math.sqrt(cin)).to(torch.bfloat16)
+    wr = (torch.randn(2 * cin, cin, device="cuda", generator=g) / math.sqrt(cin)).to(torch.bfloat16)
+    bias = torch.randn(2 * cin, device="cuda", generator=g)
+    wk = torch.cat([w3, wr], dim=1).contiguous()
+    out = torch.zeros(B * Ho * Ho, 2 * cin, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.lib().msclip_op_conv_gemm(ptr(y2), Ho, Ho, cin, 0, cin, 1, 1, 0, ptr(pfeat), H, H, cpix, coff, cin, 1, stride, 0,
+                                              B, Ho, Ho, ptr(wk), 2 * cin, 2 * cin, ptr(bias), ptr(out), 2 * cin,
+                                              _lib.EPI_RELU_BF16, stream()))
+    ps = pfeat[:, ::stride, ::stride, coff:coff + cin].float().reshape(-1, cin)
+    ref = torch.relu(y2.float().reshape(-1, cin) @ w3.float().t() + ps @ wr.float().t() + bias)
+    r = rel(out.float(), ref)
+    _record(f"conv_gemm2/H{H}", {"rel": r})
+    assert r < 3e-3, r
+
+
 @pytest.mark.parametrize("H,cpix,coff,Cc,k", [(112, 96, 48, 48, 16), (56, 96, 0, 96, 8), (14, 384, 0, 384, 1), (7, 768, 0, 768, 1)])
 def test_patch_pool(H, cpix, coff, Cc, k):
     B = 2
