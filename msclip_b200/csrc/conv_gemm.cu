@@ -23,7 +23,6 @@ using namespace gemm_detail;
 
 constexpr int kConvThreads = 512;
 constexpr int kGatherThreads = 128;
-constexpr int kLag = 3;           // cp.async groups a gather thread keeps in flight
 constexpr int kMaxKChunks = 512;  // K <= 4096
 
 struct ConvSeg {
@@ -46,11 +45,14 @@ struct ConvCfg {
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStagesRaw = (184 * 1024) / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTableBytes = kMaxKChunks * 4;
+  static constexpr int kTableBytes = kMaxKChunks * 8;
   static constexpr int kSmemBytes = kStages * kStage + kTableBytes + 256 + 1024;
   static constexpr int kChunk = (BN % 32 == 0) ? 32 : 16;
   static constexpr int kNumChunks = BN / kChunk;
-  static_assert(kStages > kLag, "ring must be deeper than the cp.async lag");
+  // cp.async groups a gather thread keeps in flight: as deep as the ring allows (the small-N convolutions are
+  // latency-bound on the A gather, bytes in flight are what buys bandwidth)
+  static constexpr int kLag = kStages - 1;
+  static_assert(kStages >= 2, "ring too shallow");
 };
 
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* src, uint32_t src_bytes) {
@@ -69,7 +71,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
   const GemmParams& p = cp.g;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint32_t* ktab = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStage);
+  int2* ktab = reinterpret_cast<int2*>(smem + Cfg::kStages * Cfg::kStage);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ktab) + Cfg::kTableBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
@@ -80,18 +82,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + kBK - 1) / kBK;
 
-  // K-chunk table: chunk q (K indices 8q .. 8q+7) -> source, tap and channel; 0xFFFFFFFF = beyond K (zero)
+  // K-chunk table: chunk q (K indices 8q .. 8q+7) -> x: element offset of the tap inside the source
+  // ((ky*W + kx)*cpix + c), y: kx | ky << 8 | source << 16; y = 0xFFFFFFFF marks chunks beyond K (zero filled)
   for (int q = threadIdx.x; q < num_kb * 8; q += kConvThreads) {
     const int k = q * 8;
-    uint32_t e = 0xFFFFFFFFu;
+    int2 e = make_int2(0, -1);
     if (k < p.K) {
       const int sidx = (cp.nseg > 1 && k >= cp.seg[1].k_begin) ? 1 : 0;
       const ConvSeg& sg = cp.seg[sidx];
       const int kk = k - sg.k_begin;
       const int tap = kk / sg.C, c = kk - tap * sg.C;
       const int ky = tap / sg.ksize, kx = tap - ky * sg.ksize;
-      e = static_cast<uint32_t>(c) | (static_cast<uint32_t>(kx) << 16) | (static_cast<uint32_t>(ky) << 20) |
-          (static_cast<uint32_t>(sidx) << 24);
+      e.x = (ky * sg.W + kx) * sg.cpix + c;
+      e.y = kx | (ky << 8) | (sidx << 16);
     }
     ktab[q] = e;
   }
@@ -117,55 +120,65 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ------------------------------------------------------------------ A gather (one tile row per thread)
-    const int r = threadIdx.x;
-    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
-    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    // ------------------------------------------------------------------ A gather
+    // Lane l of warp w copies chunk j = l & 7 of rows w*32 + 4*i + (l >> 3), i = 0..7: the eight lanes that share
+    // a row fetch its 128 contiguous-in-K bytes (one or two contiguous NHWC segments) and write one full,
+    // conflict-free swizzled smem row, so each warp-wide cp.async touches 4 rows instead of 32.
+    const int j = lane & 7;
+    const int rsub = lane >> 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m = (tile / p.tiles_n) * kBM + r;
-      const bool row_ok = m < p.M;
+      const int m_base = (tile / p.tiles_n) * kBM + warp * 32 + rsub;
       const int hw = cp.Ho * cp.Wo;
-      const int b = row_ok ? m / hw : 0;
-      const int rem = row_ok ? m - b * hw : 0;
-      const int oy = rem / cp.Wo, ox = rem - oy * cp.Wo;
-      int iy0[2], ix0[2];
-      const bf16* base[2];
+      // per row: element offset of the patch origin in each source and the origin coordinates (for the bounds test)
+      int pix_off[2][8];
+      int org[2][8];  // (iy0 + 64) | (ix0 + 64) << 16 ; -1 = row beyond M
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const ConvSeg& sg = cp.seg[s2 < cp.nseg ? s2 : 0];
-        iy0[s2] = oy * sg.stride - sg.pad;
-        ix0[s2] = ox * sg.stride - sg.pad;
-        base[s2] = sg.in + static_cast<long long>(b) * sg.H * sg.W * sg.cpix + sg.c_off;
+      for (int i = 0; i < 8; ++i) {
+        const int m = m_base + 4 * i;
+        const bool row_ok = m < p.M;
+        const int b = row_ok ? m / hw : 0;
+        const int rem = row_ok ? m - b * hw : 0;
+        const int oy = rem / cp.Wo, ox = rem - oy * cp.Wo;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const ConvSeg& sg = cp.seg[s2];
+          const int iy0 = oy * sg.stride - sg.pad, ix0 = ox * sg.stride - sg.pad;
+          pix_off[s2][i] = ((b * sg.H + iy0) * sg.W + ix0) * sg.cpix + sg.c_off;
+          org[s2][i] = row_ok ? ((iy0 + 64) | ((ix0 + 64) << 16)) : -1;
+        }
       }
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % Cfg::kStages;
         const uint32_t ph = static_cast<uint32_t>(it / Cfg::kStages) & 1u;
+        const int2 e = ktab[kb * 8 + j];
+        const int sidx = (e.y >> 16) & 1;
+        const int kx = e.y & 0xFF, ky = (e.y >> 8) & 0xFF;
+        const ConvSeg& sg = cp.seg[sidx];
         mbar_wait(&empty_bar[s], ph ^ 1u, 21);
-        const uint32_t dst_row = smem_u32(smem + s * Cfg::kStage) + row_off;
+        const uint32_t dst_base = smem_u32(smem + s * Cfg::kStage) + static_cast<uint32_t>(warp * 32 + rsub) * 128u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t e = ktab[kb * 8 + j];
-          const int sidx = (e >> 24) & 1;
-          const ConvSeg& sg = cp.seg[sidx];
-          const int iy = iy0[sidx] + static_cast<int>((e >> 20) & 0xF);
-          const int ix = ix0[sidx] + static_cast<int>((e >> 16) & 0xF);
-          const bool ok = row_ok && e != 0xFFFFFFFFu && iy >= 0 && iy < sg.H && ix >= 0 && ix < sg.W;
-          const bf16* src = ok ? base[sidx] + (static_cast<long long>(iy) * sg.W + ix) * sg.cpix + (e & 0xFFFFu)
-                               : cp.seg[0].in;
-          cp_async_16_zfill(dst_row + ((static_cast<uint32_t>(j) ^ swz) << 4), src, ok ? 16u : 0u);
+        for (int i = 0; i < 8; ++i) {
+          const int o = sidx ? org[1][i] : org[0][i];
+          const int iy = (o & 0xFFFF) - 64 + ky, ix = ((o >> 16) & 0xFFFF) - 64 + kx;
+          const bool ok = e.y != -1 && o != -1 && iy >= 0 && iy < sg.H && ix >= 0 && ix < sg.W;
+          const int off = (sidx ? pix_off[1][i] : pix_off[0][i]) + e.x;
+          const bf16* src = ok ? sg.in + off : cp.seg[0].in;
+          const uint32_t row = static_cast<uint32_t>(warp * 32 + rsub + 4 * i);
+          cp_async_16_zfill(dst_base + static_cast<uint32_t>(4 * i) * 128u + ((static_cast<uint32_t>(j) ^ (row & 7u)) << 4),
+                            src, ok ? 16u : 0u);
         }
         cp_async_commit();
-        if (it >= kLag) {
-          cp_async_wait<kLag>();     // the group issued kLag iterations ago has landed
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-          mbar_arrive(&full_bar[(it - kLag) % Cfg::kStages]);
+        if (it >= Cfg::kLag) {
+          cp_async_wait<Cfg::kLag>();  // the group issued kLag iterations ago has landed
+          fence_proxy_async_smem();    // generic-proxy writes -> visible to the tensor core's async proxy
+          mbar_arrive(&full_bar[(it - Cfg::kLag) % Cfg::kStages]);
         }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    for (int d = (it < kLag ? it : kLag); d > 0; --d) mbar_arrive(&full_bar[(it - d) % Cfg::kStages]);
+    for (int d = (it < Cfg::kLag ? it : Cfg::kLag); d > 0; --d) mbar_arrive(&full_bar[(it - d) % Cfg::kStages]);
   } else if (warp == 4) {
     if (lane == 0) {
       int s = 0;
@@ -328,6 +341,9 @@ int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo,
                                static_cast<uint32_t>(bn)));
   const long long M = static_cast<long long>(batch) * Ho * Wo;
   MSCLIP_REQUIRE(M < (1ll << 31), "conv_gemm: too many output pixels for one launch");
+  for (int i = 0; i < nsrc; ++i)
+    MSCLIP_REQUIRE(static_cast<long long>(batch) * src[i].H * src[i].W * src[i].cpix < (1ll << 31) && src[i].pad <= 32,
+                   "conv_gemm: source too large for 32-bit element offsets");
   GemmParams& p = cp.g;
   p.M = static_cast<int>(M);
   p.N = N;

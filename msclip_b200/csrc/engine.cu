@@ -600,7 +600,9 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
       for (int i = 0; i < 4; ++i) {
         const int st = c.early_strides[i], Ho = Hc / st;
         bf16* o = outs[i & 1];
-        if (g_conv_im2col) {
+        // the gather-fed kernel wins while the MMA work per gathered byte is small (N <= 384); the widest stage
+        // is better served by the TMA-fed GEMM on an explicit patch matrix (profiles/r01_kernel_bench.md)
+        if (g_conv_im2col || 2 * ch >= 768) {
           MSCLIP_TRY(launch_im2col_nhwc(cur, nb, Hc, Hc, cpix, 0, ch, 3, st, 1, col, 9 * ch, 0, s));
           MSCLIP_TRY(launch_gemm(col, 9 * ch, h->stem[i].w, 9 * ch, nb * Ho * Ho, 2 * ch, 9 * ch, h->stem[i].b, o, 2 * ch,
                                  nullptr, 0, EPI_RELU_BF16, s));
@@ -609,7 +611,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
           MSCLIP_TRY(launch_conv_gemm(&src, 1, nb, Ho, Ho, h->stem[i].w, 9 * ch, 2 * ch, h->stem[i].b, o, 2 * ch,
                                       EPI_RELU_BF16, s));
         }
-        count_launch(g_conv_im2col ? 2 : 1);
+        count_launch((g_conv_im2col || 2 * ch >= 768) ? 2 : 1);
         cur = o;
         cpix = 2 * ch;
         ch *= 2;

@@ -91,6 +91,33 @@ def main():
             print(f"{name:16s} pair={pair} {ms:8.3f} ms {tf:7.1f} TF/s ({100 * tf / peaks['tflops']:.1f}%)  {gb:7.0f} GB/s", flush=True)
         L.msclip_op_set_gemm_pair_mode(-1)
         del a, w, o
+    # convolutions of the stem / parallel branch at one chunk of 256 images: implicit GEMM vs im2col + GEMM
+    nbc = 256
+    convs = [("stem0 3x3s2 48->96", 112, 96, 0, 48, 3, 2, 1, 96), ("stem1 3x3s2 96->192", 56, 96, 0, 96, 3, 2, 1, 192),
+             ("stem2 3x3s2 192->384", 28, 192, 0, 192, 3, 2, 1, 384), ("stem3 3x3s2 384->768", 14, 384, 0, 384, 3, 2, 1, 768),
+             ("branch1.conv2 3x3s2 48->48", 112, 48, 0, 48, 3, 2, 1, 48), ("branch2.conv2 3x3s2 96->96", 56, 96, 0, 96, 3, 2, 1, 96)]
+    for name, H, cpix, coff, Cc, k, st, pd, N in convs:
+        if args.only not in "conv/" + name:
+            continue
+        Ho = (H + 2 * pd - k) // st + 1
+        x = torch.randn(nbc, H, H, cpix, device="cuda").to(torch.bfloat16)
+        K = k * k * Cc
+        w = (torch.randn(N, K, device="cuda") / math.sqrt(K)).to(torch.bfloat16)
+        bias = torch.randn(N, device="cuda")
+        o = torch.empty(nbc * Ho * Ho, N, device="cuda", dtype=torch.bfloat16)
+        col = torch.empty(nbc * Ho * Ho, K, device="cuda", dtype=torch.bfloat16)
+        ms_i = time_ms(lambda: _lib.check(L.msclip_op_conv_gemm(ptr(x), H, H, cpix, coff, Cc, k, st, pd, None, 0, 0, 0, 0, 0, 0, 0, 0, nbc,
+                                                                  Ho, Ho, ptr(w), K, N, ptr(bias), ptr(o), N, _lib.EPI_RELU_BF16, sp)), args.reps)
+        ms_c = time_ms(lambda: _lib.check(L.msclip_op_im2col_nhwc(ptr(x), nbc, H, H, cpix, coff, Cc, k, st, pd, ptr(col), K, 0, sp)), args.reps)
+        ms_g = time_ms(lambda: _lib.check(L.msclip_op_gemm(ptr(col), K, ptr(w), K, nbc * Ho * Ho, N, K, 1.0, ptr(bias), ptr(o), N, None, 0,
+                                                            _lib.EPI_RELU_BF16, sp)), args.reps)
+        fl = 2.0 * nbc * Ho * Ho * N * K
+        algo = (x.numel() * Cc // cpix + o.numel() + w.numel()) * 2      # read input once, write output once
+        out["other"].append({"name": "conv/" + name, "ms": ms_i, "ms_im2col": ms_c, "ms_gemm": ms_g, "tflops": fl / ms_i / 1e9,
+                             "GBps": algo / ms_i / 1e6, "frac_hbm": algo / ms_i / 1e6 / peaks["hbm"]})
+        print(f"conv/{name:28s} implicit {ms_i:7.3f} ms ({fl / ms_i / 1e9:6.1f} TF/s, {algo / ms_i / 1e6:6.0f} GB/s algorithmic) | "
+              f"im2col {ms_c:7.3f} + gemm {ms_g:7.3f} ms", flush=True)
+        del x, w, o, col
     # LayerNorm (HBM-bound): M x 768 fp32 in, bf16 out
     for tower, Lseq in (("text", 77), ("image", 50)):
         if args.only not in f"{tower}/layernorm":
