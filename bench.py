@@ -170,7 +170,7 @@ def run_ours(args, cfg, rank, world, local):
         torch.distributed.init_process_group("nccl", device_id=dev)
     B = args.batch
     sd_np = synth.synth_state_dict(cfg, seed=0)
-    model = CLIP(cfg)
+    model = CLIP(cfg, precision=args.precision)
     model.load_state_dict({k: torch.as_tensor(v) for k, v in sd_np.items()})
     model = model.to(dev).eval()
     model._sync_weights()
@@ -184,7 +184,7 @@ def run_ours(args, cfg, rank, world, local):
     tok_dev = torch.from_numpy(tok_np).to(dev)
     parts = torch.zeros(2, device=dev)
     loss_dev = torch.zeros((), device=dev)
-    L = _lib.lib()
+    L = _lib.lib(args.precision)
     h = model._handle
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
@@ -255,10 +255,11 @@ def run_ours(args, cfg, rank, world, local):
     # ---- roofline of the dominant kernel: the shared-block fc1 GEMM (+bias+QuickGELU) at the text-tower M
     pk = peaks()
     M, N, K = B * cfg.context_length, 4 * cfg.width, cfg.width
-    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
-    w = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(torch.bfloat16)
+    odt = _lib.torch_operand_dtype(args.precision)
+    a = torch.randn(M, K, device=dev).to(odt)
+    w = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(odt)
     bias = torch.randn(N, device=dev)
-    o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    o = torch.empty(M, N, device=dev, dtype=odt)
 
     def gemm():
         _lib.check(L.msclip_op_gemm(C.c_void_p(a.data_ptr()), K, C.c_void_p(w.data_ptr()), K, M, N, K, 1.0,
@@ -294,7 +295,7 @@ def run_ours(args, cfg, rank, world, local):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, world), "impl": "ours",
+        "dtype": args.precision, "data": "synthetic", "config": workload_config(args, cfg, world), "impl": "ours",
         "loss": loss_value, "loss_expected_ln_G": math.log(B * world),
         "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary, "roofline": roofline, "cpu_baseline": cpu,
         "device_bytes": int(L.msclip_device_bytes(h)),
@@ -313,6 +314,7 @@ def main():
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--cpu-sample", type=int, default=32, help="pairs per CPU-oracle step")
     ap.add_argument("--min-warmup", type=int, default=3, help="timing rule: at least 3 warm-up steps (lower only for profiling)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="MMA operand type (library build)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -10,7 +10,21 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmsclip_b200.so")
+# one library per MMA operand type (same sources, -DMSCLIP_FP16 for the second): bf16 is the default
+LIB_PATHS = {"bf16": os.path.join(HERE, "libmsclip_b200.so"), "fp16": os.path.join(HERE, "libmsclip_b200_fp16.so")}
+LIB_PATH = LIB_PATHS["bf16"]
+
+
+def default_precision() -> str:
+    p = os.environ.get("MSCLIP_PRECISION", "bf16").lower()
+    if p not in LIB_PATHS:
+        raise MsclipError(f"MSCLIP_PRECISION must be one of {sorted(LIB_PATHS)}, got {p!r}")
+    return p
+
+
+def torch_operand_dtype(precision: Optional[str] = None):
+    import torch
+    return torch.float16 if (precision or default_precision()) == "fp16" else torch.bfloat16
 
 F32, BF16, F16, I64 = 0, 1, 2, 3
 EPI_BF16, EPI_QGELU_BF16, EPI_RELU_BF16, EPI_RESID_F32, EPI_F32 = range(5)
@@ -67,7 +81,7 @@ _SIGNATURES = {
     "msclip_key_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I), C.POINTER(_L)]),
 }
 
-_lib: Optional[C.CDLL] = None
+_libs = {}
 
 
 def exported_symbols():
@@ -75,29 +89,31 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def lib(precision: Optional[str] = None) -> C.CDLL:
+    precision = precision or default_precision()
+    if precision not in _libs:
+        path = LIB_PATHS[precision]
+        if not os.path.exists(path):
             raise MsclipError(
-                f"{LIB_PATH} is missing: build it with `python -m msclip_b200.build` "
+                f"{path} is missing: build it with `python -m msclip_b200.build` "
                 "(there is no Python or CPU fallback for the MS-CLIP-S path)")
-        handle = C.CDLL(LIB_PATH)
+        handle = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)      # AttributeError here = header / library mismatch
             fn.restype = res
             fn.argtypes = args
-        _lib = handle
-    return _lib
+        _libs[precision] = handle
+    return _libs[precision]
 
 
-def last_error() -> str:
-    return lib().msclip_last_error().decode("utf-8", "replace")
+def last_error(precision: Optional[str] = None) -> str:
+    return lib(precision).msclip_last_error().decode("utf-8", "replace")
 
 
-def check(rc: int, what: str = "") -> None:
+def check(rc: int, what: str = "", precision: Optional[str] = None) -> None:
     if rc != 0:
-        raise MsclipError(f"{what}: {last_error()}" if what else last_error())
+        msg = last_error(precision)
+        raise MsclipError(f"{what}: {msg}" if what else msg)
 
 
 def device_count() -> int:

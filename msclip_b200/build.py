@@ -15,7 +15,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
-LIB_PATH = os.path.join(HERE, "libmsclip_b200.so")
+# two builds of the same sources: MMA operands in bf16 (default) or IEEE fp16 (-DMSCLIP_FP16)
+LIB_PATHS = {"bf16": os.path.join(HERE, "libmsclip_b200.so"), "fp16": os.path.join(HERE, "libmsclip_b200_fp16.so")}
+LIB_PATH = LIB_PATHS["bf16"]
 SOURCES = ["runtime.cu", "gemm.cu", "conv_gemm.cu", "elementwise.cu", "conv.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
 HEADERS = ["common.cuh", "gemm_common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
            os.path.join("..", "..", "include", "msclip_b200_ops.h")]
@@ -34,26 +36,33 @@ def _mtime(path: str) -> float:
     return os.path.getmtime(path) if os.path.exists(path) else 0.0
 
 
-def needs_build() -> bool:
-    lib = _mtime(LIB_PATH)
+def needs_build(precision: str = "bf16") -> bool:
+    lib = _mtime(LIB_PATHS[precision])
     if lib == 0.0:
         return True
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(_mtime(d) > lib for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build_all(force: bool = False, verbose: bool = False):
+    return [build(force, verbose, p) for p in ("bf16", "fp16")]
+
+
+def build(force: bool = False, verbose: bool = False, precision: str = "bf16") -> str:
+    lib_path = LIB_PATHS[precision]
+    if not force and not needs_build(precision):
+        return lib_path
+    obj_dir = os.path.join(OBJ_DIR, precision)
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = NVCC_FLAGS + (["-DMSCLIP_FP16"] if precision == "fp16" else [])
     nvcc = _nvcc()
     newest_header = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         if not force and _mtime(obj) > max(_mtime(os.path.join(CSRC, src)), newest_header):
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -63,15 +72,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib_path] + objs + ["-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
     if verbose:
         print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose=True)
-    print("built", path)
+    for path in build_all(force="--force" in sys.argv, verbose="--quiet" not in sys.argv):
+        print("built", path)

@@ -62,18 +62,18 @@ def exchange_bytes(payload: bytes, group=None) -> bytes:
     return b"".join(bytes(p.cpu().tolist()) for p in parts)
 
 
-def setup_peer_exchange(handle, max_b_local: int, group=None):
+def setup_peer_exchange(handle, max_b_local: int, group=None, precision=None):
     """comm_init -> export IPC handle -> all-gather the 64-byte handles -> import.  Returns
     (rank, world, max_b_local)."""
     rank, world = rank_world(group)
-    L = _lib.lib()
-    _lib.check(L.msclip_comm_init(handle, rank, world, int(max_b_local)), "msclip_comm_init")
+    L = _lib.lib(precision)
+    _lib.check(L.msclip_comm_init(handle, rank, world, int(max_b_local)), "msclip_comm_init", precision)
     if world > 1:
         buf = (C.c_uint8 * 64)()
-        _lib.check(L.msclip_comm_export(handle, buf), "msclip_comm_export")
+        _lib.check(L.msclip_comm_export(handle, buf), "msclip_comm_export", precision)
         everyone = exchange_bytes(bytes(buf), group)
         assert len(everyone) == 64 * world
         arr = (C.c_uint8 * len(everyone)).from_buffer_copy(everyone)
-        _lib.check(L.msclip_comm_import(handle, arr), "msclip_comm_import")
+        _lib.check(L.msclip_comm_import(handle, arr), "msclip_comm_import", precision)
         dist.barrier(group)
     return rank, world, int(max_b_local)

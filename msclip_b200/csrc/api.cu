@@ -12,7 +12,7 @@ static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 extern "C" {
 
-const char* msclip_version(void) { return "msclip_b200 0.1.0 (sm_100a)"; }
+const char* msclip_version(void) { return "msclip_b200 0.1.0 (sm_100a, " MSCLIP_OPERAND_NAME " operands)"; }
 const char* msclip_last_error(void) { return get_last_error(); }
 
 int msclip_device_count(void) {
@@ -175,39 +175,39 @@ int64_t msclip_device_bytes(msclip_handle h) {
 int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, float alpha,
                    const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epilogue,
                    void* stream) {
-  return launch_gemm_scaled(static_cast<const bf16*>(a), lda, static_cast<const bf16*>(w), ldw, m, n, k, alpha, bias,
+  return launch_gemm_scaled(static_cast<const op16*>(a), lda, static_cast<const op16*>(w), ldw, m, n, k, alpha, bias,
                             out, ldo, resid, ldr, epilogue, as_stream(stream));
 }
 void msclip_op_set_gemm_pair_mode(int enable) { gemm_set_pair_mode(enable); }
 int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
                         void* stream) {
-  return launch_layernorm_bf16(x, row_stride, w, b, static_cast<bf16*>(y_bf16), rows, as_stream(stream));
+  return launch_layernorm_bf16(x, row_stride, w, b, static_cast<op16*>(y_bf16), rows, as_stream(stream));
 }
 int msclip_op_attention(const void* qkv_bf16, void* out_bf16, int batch, int seq_len, int heads, int causal,
                         void* stream) {
-  return launch_attention(static_cast<const bf16*>(qkv_bf16), static_cast<bf16*>(out_bf16), batch, seq_len, heads,
+  return launch_attention(static_cast<const op16*>(qkv_bf16), static_cast<op16*>(out_bf16), batch, seq_len, heads,
                           causal, as_stream(stream));
 }
 int msclip_op_im2col_first(const void* img, int dtype, void* out_bf16, int batch, int height, int width, void* stream) {
-  return launch_im2col_first(img, dtype, static_cast<bf16*>(out_bf16), batch, height, width, as_stream(stream));
+  return launch_im2col_first(img, dtype, static_cast<op16*>(out_bf16), batch, height, width, as_stream(stream));
 }
 int msclip_op_im2col_nhwc(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                           int ksize, int stride, int pad, void* out_bf16, int64_t out_ld, int out_off, void* stream) {
-  return launch_im2col_nhwc(static_cast<const bf16*>(in_bf16), batch, height, width, cpix, c_off, channels, ksize, stride,
-                            pad, static_cast<bf16*>(out_bf16), out_ld, out_off, as_stream(stream));
+  return launch_im2col_nhwc(static_cast<const op16*>(in_bf16), batch, height, width, cpix, c_off, channels, ksize, stride,
+                            pad, static_cast<op16*>(out_bf16), out_ld, out_off, as_stream(stream));
 }
 int msclip_op_conv_gemm(const void* in0, int h0, int w0, int cpix0, int coff0, int c0, int k0, int s0, int p0, const void* in1,
                         int h1, int w1, int cpix1, int coff1, int c1, int k1, int s1, int p1, int batch, int ho, int wo,
                         const void* w_bf16, int64_t ldw, int n, const float* bias, void* out, int64_t ldo, int epilogue,
                         void* stream) {
   ConvSource src[2] = {{in0, h0, w0, cpix0, coff0, c0, k0, s0, p0}, {in1, h1, w1, cpix1, coff1, c1, k1, s1, p1}};
-  return launch_conv_gemm(src, in1 ? 2 : 1, batch, ho, wo, static_cast<const bf16*>(w_bf16), ldw, n, bias, out, ldo, epilogue,
+  return launch_conv_gemm(src, in1 ? 2 : 1, batch, ho, wo, static_cast<const op16*>(w_bf16), ldw, n, bias, out, ldo, epilogue,
                           as_stream(stream));
 }
 int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                          int k, const float* w, const float* bias, void* out_bf16, void* stream) {
-  return launch_patch_pool(static_cast<const bf16*>(in_bf16), batch, height, width, cpix, c_off, channels, k, w, bias,
-                           static_cast<bf16*>(out_bf16), as_stream(stream));
+  return launch_patch_pool(static_cast<const op16*>(in_bf16), batch, height, width, cpix, c_off, channels, k, w, bias,
+                           static_cast<op16*>(out_bf16), as_stream(stream));
 }
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                               const float* b, float* x_out, int batch, int grid, void* stream) {
@@ -220,8 +220,8 @@ int msclip_op_contrastive_lse(const void* img_bf16, const void* txt_bf16, int b,
   const void** tab = reinterpret_cast<const void**>(static_cast<uint8_t*>(workspace) + ((need + 15) & ~size_t(15)));
   const void* host_tab[2] = {img_bf16, txt_bf16};
   MSCLIP_CHECK_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice, as_stream(stream)));
-  return launch_contrastive_loss_ex(static_cast<const bf16*>(img_bf16), static_cast<const bf16*>(txt_bf16),
-                                    reinterpret_cast<const bf16* const*>(tab), reinterpret_cast<const bf16* const*>(tab + 1),
+  return launch_contrastive_loss_ex(static_cast<const op16*>(img_bf16), static_cast<const op16*>(txt_bf16),
+                                    reinterpret_cast<const op16* const*>(tab), reinterpret_cast<const op16* const*>(tab + 1),
                                     nullptr, 0, 1, 0, b, 512, scale, workspace, parts2, as_stream(stream));
 }
 size_t msclip_op_contrastive_lse_workspace(int b) { return ((contrastive_loss_workspace_bytes(1, b) + 15) & ~size_t(15)) + 64; }

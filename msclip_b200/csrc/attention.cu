@@ -7,7 +7,7 @@
 // One CTA per (batch, head); Q/K/V head slices are staged once in padded shared memory; every warp owns
 // 16 query rows and walks the keys in chunks (online softmax across chunks for L = 197).
 // Attention is 1-2 % of the path's FLOPs and the per-head problems are far
-// smaller than one 128-row tcgen05 tile, so the contractions use warp-level mma.sync m16n8k16 (bf16 in,
+// smaller than one 128-row tcgen05 tile, so the contractions use warp-level mma.sync m16n8k16 (op16 in,
 // fp32 accumulate); the GEMMs that carry the other 98 % are tcgen05 (gemm.cu).
 #include "common.cuh"
 #include "kernels.h"
@@ -31,7 +31,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "mma.sync.aligned.m16n8k16.row.col.f32." MSCLIP_MMA_OPERANDS ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
       "{%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -39,20 +39,20 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
 __global__ void __launch_bounds__(QPAD * 2)
-attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, int heads) {
+attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, int heads) {
   constexpr int KVPAD = KC * NCHUNK;
   constexpr int NT = KC / 8;  // score n-tiles per chunk
   static_assert(QPAD % 16 == 0 && KC % 16 == 0 && KVPAD >= QPAD, "tile shapes");
   extern __shared__ __align__(16) uint8_t att_smem[];
-  bf16* sq = reinterpret_cast<bf16*>(att_smem);
-  bf16* sk = sq + QPAD * kLds;
-  bf16* sv = sk + KVPAD * kLds;
+  op16* sq = reinterpret_cast<op16*>(att_smem);
+  op16* sk = sq + QPAD * kLds;
+  op16* sv = sk + KVPAD * kLds;
 
   const int b = blockIdx.x / heads;
   const int h = blockIdx.x % heads;
   const int width = heads * kHeadDim;
   const long long pitch = 3ll * width;
-  const bf16* base = qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim;
+  const op16* base = qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim;
 
   // stage Q, K, V head slices (rows >= L are zero)
   for (int i = threadIdx.x; i < (QPAD + 2 * KVPAD) * 8; i += blockDim.x) {
@@ -69,7 +69,7 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, in
     }
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (row < L) v = *reinterpret_cast<const uint4*>(base + row * pitch + which * width + c * 8);
-    bf16* dst = which == 0 ? sq : (which == 1 ? sk : sv);
+    op16* dst = which == 0 ? sq : (which == 1 ? sk : sv);
     *reinterpret_cast<uint4*>(dst + row * kLds + c * 8) = v;
   }
   __syncthreads();
@@ -171,10 +171,10 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, in
     for (int kk2 = 0; kk2 < NT / 2; ++kk2) {
       if (kk2 < ng) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kk2][0], s[2 * kk2][1]);
-        pa[1] = pack_bf16(s[2 * kk2][2], s[2 * kk2][3]);
-        pa[2] = pack_bf16(s[2 * kk2 + 1][0], s[2 * kk2 + 1][1]);
-        pa[3] = pack_bf16(s[2 * kk2 + 1][2], s[2 * kk2 + 1][3]);
+        pa[0] = pack16(s[2 * kk2][0], s[2 * kk2][1]);
+        pa[1] = pack16(s[2 * kk2][2], s[2 * kk2][3]);
+        pa[2] = pack16(s[2 * kk2 + 1][0], s[2 * kk2 + 1][1]);
+        pa[3] = pack16(s[2 * kk2 + 1][2], s[2 * kk2 + 1][3]);
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t vf[4];
@@ -193,21 +193,21 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int L, in
     l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
   }
   const float inv_lo = 1.0f / l_run[0], inv_hi = 1.0f / l_run[1];
-  bf16* obase = out + static_cast<long long>(b) * L * width + h * kHeadDim;
+  op16* obase = out + static_cast<long long>(b) * L * width + h * kHeadDim;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = 8 * j + 2 * t;
     if (row_lo < L)
       *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(row_lo) * width + col) =
-          pack_bf16(o[j][0] * inv_lo, o[j][1] * inv_lo);
+          pack16(o[j][0] * inv_lo, o[j][1] * inv_lo);
     if (row_hi < L)
       *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(row_hi) * width + col) =
-          pack_bf16(o[j][2] * inv_hi, o[j][3] * inv_hi);
+          pack16(o[j][2] * inv_hi, o[j][3] * inv_hi);
   }
 }
 
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
-int launch_variant(const bf16* qkv, bf16* out, int batch, int L, int heads, cudaStream_t stream) {
+int launch_variant(const op16* qkv, op16* out, int batch, int L, int heads, cudaStream_t stream) {
   constexpr int smem = (QPAD + 2 * KC * NCHUNK) * kLds * 2;
   static bool configured = false;
   if (!configured) {
@@ -222,7 +222,7 @@ int launch_variant(const bf16* qkv, bf16* out, int batch, int L, int heads, cuda
 
 }  // namespace
 
-int launch_attention(const bf16* qkv, bf16* out, int batch, int L, int heads, int causal, cudaStream_t stream) {
+int launch_attention(const op16* qkv, op16* out, int batch, int L, int heads, int causal, cudaStream_t stream) {
   if (batch <= 0) return 0;
   MSCLIP_REQUIRE(L >= 1 && L <= 208, "attention: sequence length must be in [1, 208]");
   MSCLIP_REQUIRE(heads >= 1, "attention: heads must be positive");

@@ -7,8 +7,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
 #include <cuda.h>
+
+#include "kernels.h"
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -71,9 +72,20 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+#ifdef MSCLIP_FP16
+  __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.0f), 65504.0f), fminf(fmaxf(hi, -65504.0f), 65504.0f));
+#else
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+#endif
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 op162_to_float2(op162 v) {
+#ifdef MSCLIP_FP16
+  return __half22float2(v);
+#else
+  return __bfloat1622float2(v);
+#endif
 }
 
 // ------------------------------------------------------------------------------------ mbarrier
@@ -251,7 +263,7 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16/bf16 operands with fp32 accumulate.
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16/op16 operands with fp32 accumulate.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -293,7 +305,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 }
 
 // K-major operand tile in shared memory, 128-byte swizzle (what TMA SWIZZLE_128B writes for a box
-// whose inner extent is 64 bf16 = 128 B): rows are 128 B apart, 8-row groups 1024 B apart.
+// whose inner extent is 64 op16 = 128 B): rows are 128 B apart, 8-row groups 1024 B apart.
 //   bits  0-13 start address >> 4        bits 16-29 leading byte offset >> 4 (unused for SW128 K-major: 1)
 //   bits 32-45 stride byte offset >> 4   bits 46-47 descriptor version (1 on sm_100)
 //   bits 49-51 base offset (0: tiles are 1024-B aligned)   bits 61-63 layout (2 = SWIZZLE_128B)
@@ -308,15 +320,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 #endif  // __CUDACC__
 
-// Instruction descriptor for kind::f16: D=fp32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
+// Instruction descriptor for kind::f16: D=fp32 (bits 4-5 = 1), A=B=op16 (bits 7-9, 10-12 = 1),
 // both operands K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+  return (1u << 4) | (kUmmaOperandFormat << 7) | (kUmmaOperandFormat << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------ host: TMA maps
-// rows x cols bf16 row-major (pitch ld elements), box = box_rows x 64 columns, 128-B swizzle,
+// rows x cols op16 row-major (pitch ld elements), box = box_rows x 64 columns, 128-B swizzle,
 // out-of-bounds elements read as zero.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);

@@ -1,6 +1,6 @@
 // Data-movement kernels that turn the convolutions of the early-conv stem (EarlyconvRes, M.py:1993-2000),
 // the parallel branch (Resnet_Stage / ConvResBlock, M.py:1842-1861) and the lateral adapters
-// (M.py:1752-1759) into GEMM operands for gemm.cu.  Activations are NHWC bf16 so that 8 channels of one
+// (M.py:1752-1759) into GEMM operands for gemm.cu.  Activations are NHWC op16 so that 8 channels of one
 // tap are one 16-byte vector; BatchNorm (eval) is folded into the packed weights.  All kernels are
 // HBM-bound: 16-byte loads/stores, adjacent threads on adjacent vectors.
 #include "common.cuh"
@@ -14,13 +14,13 @@ namespace {
 
 __device__ __forceinline__ float load_pixel(const void* img, int dtype, long long idx) {
   if (dtype == 0) return reinterpret_cast<const float*>(img)[idx];
-  if (dtype == 1) return __bfloat162float(reinterpret_cast<const bf16*>(img)[idx]);
+  if (dtype == 1) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(img)[idx]);
   return __half2float(reinterpret_cast<const __half*>(img)[idx]);
 }
 
 // One thread per output pixel: 27 taps (c, ky, kx) of a 3x3 / stride 2 / pad 1 window + 5 zero columns.
 __global__ void __launch_bounds__(256)
-im2col_first_kernel(const void* __restrict__ img, int dtype, bf16* __restrict__ out, long long total, int H, int W) {
+im2col_first_kernel(const void* __restrict__ img, int dtype, op16* __restrict__ out, long long total, int H, int W) {
   const int Ho = H / 2, Wo = W / 2;
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
     const int ox = static_cast<int>(idx % Wo);
@@ -45,15 +45,15 @@ im2col_first_kernel(const void* __restrict__ img, int dtype, bf16* __restrict__ 
     uint4* o4 = reinterpret_cast<uint4*>(out + idx * 32);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      o4[j] = make_uint4(pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
+                         pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
   }
 }
 
 // One thread per (output pixel, tap, 8-channel vector).
 __global__ void __launch_bounds__(256)
-im2col_nhwc_kernel(const bf16* __restrict__ in, int H, int W, int cpix, int c_off, int C, int ksize, int stride,
-                   int pad, int Ho, int Wo, bf16* __restrict__ out, long long out_ld, int out_off, long long total) {
+im2col_nhwc_kernel(const op16* __restrict__ in, int H, int W, int cpix, int c_off, int C, int ksize, int stride,
+                   int pad, int Ho, int Wo, op16* __restrict__ out, long long out_ld, int out_off, long long total) {
   const int cv = C / 8;
   const int per_pixel = ksize * ksize * cv;
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
@@ -75,8 +75,8 @@ im2col_nhwc_kernel(const bf16* __restrict__ in, int H, int W, int cpix, int c_of
 
 // One thread per (output cell, 8-channel vector): fp32 accumulation over the k x k patch.
 __global__ void __launch_bounds__(256)
-patch_pool_kernel(const bf16* __restrict__ in, int H, int W, int cpix, int c_off, int C, int k,
-                  const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out, long long total) {
+patch_pool_kernel(const op16* __restrict__ in, int H, int W, int cpix, int c_off, int C, int k,
+                  const float* __restrict__ w, const float* __restrict__ bias, op16* __restrict__ out, long long total) {
   const int cv = C / 8;
   const int Ho = H / k, Wo = W / k;
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
@@ -93,15 +93,15 @@ patch_pool_kernel(const bf16* __restrict__ in, int H, int W, int cpix, int c_off
       acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
     }
     for (int ky = 0; ky < k; ++ky) {
-      const bf16* row = in + ((bi * H + oy * k + ky) * W + ox * k) * cpix + c_off + c8 * 8;
+      const op16* row = in + ((bi * H + oy * k + ky) * W + ox * k) * cpix + c_off + c8 * 8;
       for (int kx = 0; kx < k; ++kx) {
         const uint4 raw = *reinterpret_cast<const uint4*>(row + static_cast<long long>(kx) * cpix);
         const float* wp = w + static_cast<long long>(ky * k + kx) * C + c8 * 8;
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
-        const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+        const op162* h = reinterpret_cast<const op162*>(&raw);
+        const float2 f0 = op162_to_float2(h[0]), f1 = op162_to_float2(h[1]);
+        const float2 f2 = op162_to_float2(h[2]), f3 = op162_to_float2(h[3]);
         acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
         acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
         acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
@@ -109,21 +109,21 @@ patch_pool_kernel(const bf16* __restrict__ in, int H, int W, int cpix, int c_off
       }
     }
     *reinterpret_cast<uint4*>(out + cell * C + c8 * 8) =
-        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
-                   pack_bf16(acc[6], acc[7]));
+        make_uint4(pack16(acc[0], acc[1]), pack16(acc[2], acc[3]), pack16(acc[4], acc[5]),
+                   pack16(acc[6], acc[7]));
   }
 }
 
 __global__ void __launch_bounds__(256)
-pack_bf16_kernel(const float* __restrict__ src, long long sn, long long sk, const float* __restrict__ row_scale,
-                 bf16* __restrict__ dst, long long ldd, int N, int K) {
+pack_op16_kernel(const float* __restrict__ src, long long sn, long long sk, const float* __restrict__ row_scale,
+                 op16* __restrict__ dst, long long ldd, int N, int K) {
   const long long total = static_cast<long long>(N) * K;
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
     const int k = static_cast<int>(idx % K);
     const long long n = idx / K;
     float v = src[n * sn + k * sk];
     if (row_scale) v *= row_scale[n];
-    dst[n * ldd + k] = __float2bfloat16_rn(v);
+    dst[n * ldd + k] = to_op16(v);
   }
 }
 
@@ -135,7 +135,7 @@ inline int flat_grid(long long total) {
 
 }  // namespace
 
-int launch_im2col_first(const void* img, int img_dtype, bf16* out, int batch, int H, int W, cudaStream_t stream) {
+int launch_im2col_first(const void* img, int img_dtype, op16* out, int batch, int H, int W, cudaStream_t stream) {
   if (batch <= 0) return 0;
   MSCLIP_REQUIRE(img_dtype >= 0 && img_dtype <= 2, "image dtype must be 0 (f32), 1 (bf16) or 2 (f16)");
   MSCLIP_REQUIRE(H % 2 == 0 && W % 2 == 0, "image height/width must be even");
@@ -145,8 +145,8 @@ int launch_im2col_first(const void* img, int img_dtype, bf16* out, int batch, in
   return 0;
 }
 
-int launch_im2col_nhwc(const bf16* in, int batch, int H, int W, int cpix, int c_off, int C, int ksize, int stride,
-                       int pad, bf16* out, int64_t out_ld, int out_off, cudaStream_t stream) {
+int launch_im2col_nhwc(const op16* in, int batch, int H, int W, int cpix, int c_off, int C, int ksize, int stride,
+                       int pad, op16* out, int64_t out_ld, int out_off, cudaStream_t stream) {
   if (batch <= 0) return 0;
   MSCLIP_REQUIRE(C % 8 == 0 && cpix % 8 == 0 && c_off % 8 == 0 && out_ld % 8 == 0 && out_off % 8 == 0,
                  "im2col: channel counts / pitches must be multiples of 8");
@@ -158,8 +158,8 @@ int launch_im2col_nhwc(const bf16* in, int batch, int H, int W, int cpix, int c_
   return 0;
 }
 
-int launch_patch_pool(const bf16* in, int batch, int H, int W, int cpix, int c_off, int C, int k, const float* w,
-                      const float* bias, bf16* out, cudaStream_t stream) {
+int launch_patch_pool(const op16* in, int batch, int H, int W, int cpix, int c_off, int C, int k, const float* w,
+                      const float* bias, op16* out, cudaStream_t stream) {
   if (batch <= 0) return 0;
   MSCLIP_REQUIRE(C % 8 == 0 && cpix % 8 == 0 && c_off % 8 == 0, "patch_pool: channels must be multiples of 8");
   MSCLIP_REQUIRE(H % k == 0 && W % k == 0, "patch_pool: kernel must tile the feature map");
@@ -169,10 +169,10 @@ int launch_patch_pool(const bf16* in, int batch, int H, int W, int cpix, int c_o
   return 0;
 }
 
-int launch_pack_bf16(const float* src, int64_t sn, int64_t sk, const float* row_scale, bf16* dst, int64_t ldd, int N,
+int launch_pack_op16(const float* src, int64_t sn, int64_t sk, const float* row_scale, op16* dst, int64_t ldd, int N,
                      int K, cudaStream_t stream) {
   if (N <= 0 || K <= 0) return 0;
-  pack_bf16_kernel<<<flat_grid(static_cast<long long>(N) * K), 256, 0, stream>>>(src, sn, sk, row_scale, dst, ldd, N, K);
+  pack_op16_kernel<<<flat_grid(static_cast<long long>(N) * K), 256, 0, stream>>>(src, sn, sk, row_scale, dst, ldd, N, K);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

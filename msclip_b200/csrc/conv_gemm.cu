@@ -26,7 +26,7 @@ constexpr int kGatherThreads = 128;
 constexpr int kMaxKChunks = 512;  // K <= 4096
 
 struct ConvSeg {
-  const bf16* in;
+  const op16* in;
   int H, W, cpix, c_off, C, ksize, stride, pad;
   int k_begin;  // first K index of this source
 };
@@ -163,7 +163,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
           const int iy = (o & 0xFFFF) - 64 + ky, ix = ((o >> 16) & 0xFFFF) - 64 + kx;
           const bool ok = e.y != -1 && o != -1 && iy >= 0 && iy < sg.H && ix >= 0 && ix < sg.W;
           const int off = (sidx ? pix_off[1][i] : pix_off[0][i]) + e.x;
-          const bf16* src = ok ? sg.in + off : cp.seg[0].in;
+          const op16* src = ok ? sg.in + off : cp.seg[0].in;
           const uint32_t row = static_cast<uint32_t>(warp * 32 + rsub + 4 * i);
           cp_async_16_zfill(dst_base + static_cast<uint32_t>(4 * i) * 128u + ((static_cast<uint32_t>(j) ^ (row & 7u)) << 4),
                             src, ok ? 16u : 0u);
@@ -310,7 +310,7 @@ static int conv_pick_bn(int N) {  // 256-wide tiles would leave only 3 smem stag
   return 192;
 }
 
-int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const bf16* W, int64_t ldw, int N,
+int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const op16* W, int64_t ldw, int N,
                      const float* bias, void* out, int64_t ldo, int epi, cudaStream_t stream) {
   MSCLIP_REQUIRE(nsrc == 1 || nsrc == 2, "conv_gemm: one or two sources");
   MSCLIP_REQUIRE(batch > 0 && Ho > 0 && Wo > 0 && N > 0, "conv_gemm: empty problem");
@@ -326,7 +326,7 @@ int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo,
     MSCLIP_REQUIRE((s.H + 2 * s.pad - s.ksize) / s.stride + 1 == Ho && (s.W + 2 * s.pad - s.ksize) / s.stride + 1 == Wo,
                    "conv_gemm: source geometry does not produce the output grid");
     MSCLIP_REQUIRE((reinterpret_cast<uintptr_t>(s.in) & 15) == 0, "conv_gemm: input must be 16-byte aligned");
-    cp.seg[i] = ConvSeg{static_cast<const bf16*>(s.in), s.H, s.W, s.cpix, s.c_off, s.C, s.ksize, s.stride, s.pad, K};
+    cp.seg[i] = ConvSeg{static_cast<const op16*>(s.in), s.H, s.W, s.cpix, s.c_off, s.C, s.ksize, s.stride, s.pad, K};
     K += s.ksize * s.ksize * s.C;
   }
   if (nsrc == 1) cp.seg[1] = cp.seg[0];

@@ -51,10 +51,10 @@ __device__ __forceinline__ void layer_norm_row(float4 (&v)[kVec], const float* _
   }
 }
 
-__device__ __forceinline__ void store_row_bf16(bf16* __restrict__ dst, int lane, const float4 (&v)[kVec]) {
+__device__ __forceinline__ void store_row_bf16(op16* __restrict__ dst, int lane, const float4 (&v)[kVec]) {
   uint2* d2 = reinterpret_cast<uint2*>(dst);
 #pragma unroll
-  for (int i = 0; i < kVec; ++i) d2[lane + 32 * i] = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+  for (int i = 0; i < kVec; ++i) d2[lane + 32 * i] = make_uint2(pack16(v[i].x, v[i].y), pack16(v[i].z, v[i].w));
 }
 __device__ __forceinline__ void store_row_f32(float* __restrict__ dst, int lane, const float4 (&v)[kVec]) {
   float4* d4 = reinterpret_cast<float4*>(dst);
@@ -64,7 +64,7 @@ __device__ __forceinline__ void store_row_f32(float* __restrict__ dst, int lane,
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 layernorm_bf16_kernel(const float* __restrict__ x, int row_stride, const float* __restrict__ w,
-                      const float* __restrict__ b, bf16* __restrict__ y, int rows) {
+                      const float* __restrict__ b, op16* __restrict__ y, int rows) {
   const int lane = threadIdx.x & 31;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
        r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
@@ -78,7 +78,7 @@ layernorm_bf16_kernel(const float* __restrict__ x, int row_stride, const float* 
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 eot_layernorm_bf16_kernel(const float* __restrict__ x, const int64_t* __restrict__ tok, int L,
-                          const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ y, int batch) {
+                          const float* __restrict__ w, const float* __restrict__ b, op16* __restrict__ y, int batch) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   if (r >= batch) return;
@@ -218,7 +218,7 @@ adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t,
 
 // one warp per row of width E (multiple of 4, <= 1024)
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
-l2norm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int rows, int E,
+l2norm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, op16* __restrict__ out_bf16, int rows, int E,
               int normalise) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
@@ -242,7 +242,7 @@ l2norm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, bf16* __
     if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(r) * E)[c] = o;
     if (out_bf16)
       reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(r) * E)[c] =
-          make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+          make_uint2(pack16(o.x, o.y), pack16(o.z, o.w));
   }
 }
 
@@ -254,7 +254,7 @@ inline int row_grid(long long rows) {
 
 }  // namespace
 
-int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const float* b, bf16* y, int rows,
+int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
                           cudaStream_t stream) {
   if (rows <= 0) return 0;
   layernorm_bf16_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, row_stride, w, b, y, rows);
@@ -262,7 +262,7 @@ int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const 
   return 0;
 }
 
-int launch_eot_layernorm_bf16(const float* x, const int64_t* tok, int L, const float* w, const float* b, bf16* y,
+int launch_eot_layernorm_bf16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
                               int batch, cudaStream_t stream) {
   if (batch <= 0) return 0;
   eot_layernorm_bf16_kernel<<<(batch + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(
@@ -324,7 +324,7 @@ int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, c
   return 0;
 }
 
-int launch_l2norm(const float* x, float* out_f32, bf16* out_bf16, int rows, int E, int normalise,
+int launch_l2norm(const float* x, float* out_f32, op16* out_bf16, int rows, int E, int normalise,
                   cudaStream_t stream) {
   if (rows <= 0) return 0;
   MSCLIP_REQUIRE(E % 4 == 0 && E <= 1024, "l2norm: width must be a multiple of 4 and <= 1024");

@@ -116,12 +116,11 @@ void build_spec(msclip_ctx* h) {
 }
 
 // ------------------------------------------------------------------------------------ packing helpers
-static inline uint16_t f2bf(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
-  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
-  return static_cast<uint16_t>((u + r) >> 16);
+static inline uint16_t f2op16_bits(float f) {  // host-side round-to-nearest-even conversion to the operand type
+  const op16 h = to_op16(f);
+  uint16_t bits;
+  memcpy(&bits, &h, 2);
+  return bits;
 }
 
 struct Packer {
@@ -155,10 +154,10 @@ struct Packer {
     if (d && cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1;
     return d;
   }
-  bf16* up_bf16(const std::vector<float>& v) {
+  op16* up_bf16(const std::vector<float>& v) {
     std::vector<uint16_t> b(v.size());
-    for (size_t i = 0; i < v.size(); ++i) b[i] = f2bf(v[i]);
-    bf16* d = static_cast<bf16*>(dalloc(std::max<size_t>(b.size(), 8) * 2));
+    for (size_t i = 0; i < v.size(); ++i) b[i] = f2op16_bits(v[i]);
+    op16* d = static_cast<op16*>(dalloc(std::max<size_t>(b.size(), 8) * 2));
     if (d && cudaMemcpy(d, b.data(), b.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) rc = 1;
     return d;
   }
@@ -168,20 +167,20 @@ struct Packer {
     if (d && cudaMemcpyAsync(d, t.dev, t.numel * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) rc = 1;
     return d;
   }
-  // nn.Linear weight [N,K] -> bf16 [N,K]; optional per-row scale (device)
-  bf16* linear(const std::string& k, const float* row_scale) {
+  // nn.Linear weight [N,K] -> op16 [N,K]; optional per-row scale (device)
+  op16* linear(const std::string& k, const float* row_scale) {
     const RawTensor& t = raw(k);
     const int N = static_cast<int>(t.shape[0]), K = static_cast<int>(t.shape[1]);
-    bf16* d = static_cast<bf16*>(dalloc(static_cast<size_t>(N) * K * 2));
-    if (d && launch_pack_bf16(t.dev, K, 1, row_scale, d, K, N, K, stream)) rc = 1;
+    op16* d = static_cast<op16*>(dalloc(static_cast<size_t>(N) * K * 2));
+    if (d && launch_pack_op16(t.dev, K, 1, row_scale, d, K, N, K, stream)) rc = 1;
     return d;
   }
   // x @ P with P [K,N] -> stored transposed [N,K] so the GEMM sees a K-major B operand
-  bf16* transposed(const std::string& k) {
+  op16* transposed(const std::string& k) {
     const RawTensor& t = raw(k);
     const int K = static_cast<int>(t.shape[0]), N = static_cast<int>(t.shape[1]);
-    bf16* d = static_cast<bf16*>(dalloc(static_cast<size_t>(N) * K * 2));
-    if (d && launch_pack_bf16(t.dev, 1, N, nullptr, d, K, N, K, stream)) rc = 1;
+    op16* d = static_cast<op16*>(dalloc(static_cast<size_t>(N) * K * 2));
+    if (d && launch_pack_op16(t.dev, 1, N, nullptr, d, K, N, K, stream)) rc = 1;
     return d;
   }
   // eval-mode BatchNorm as per-channel scale / shift
@@ -438,8 +437,8 @@ static int require_ready(msclip_ctx* h) {
 
 // exchange buffer layout helpers ------------------------------------------------------------------------
 static size_t xchg_feat_bytes(const msclip_ctx* h) { return static_cast<size_t>(h->max_b_local) * h->cfg.embed_dim * 2; }
-static bf16* xchg_slot(const msclip_ctx* h, void* base, int parity, int modality) {
-  return reinterpret_cast<bf16*>(static_cast<uint8_t*>(base) + (parity * 2 + modality) * xchg_feat_bytes(h));
+static op16* xchg_slot(const msclip_ctx* h, void* base, int parity, int modality) {
+  return reinterpret_cast<op16*>(static_cast<uint8_t*>(base) + (parity * 2 + modality) * xchg_feat_bytes(h));
 }
 static uint32_t* xchg_flags(const msclip_ctx* h, void* base) {
   return reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(base) + 4 * xchg_feat_bytes(h));
@@ -511,8 +510,8 @@ static int ensure_xchg(msclip_ctx* h, int batch) {
 }
 
 // ------------------------------------------------------------------------------------ shared block
-static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, bf16* hbuf,
-                     bf16* qkv, bf16* attn, bf16* fc1, cudaStream_t s) {
+static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, op16* hbuf,
+                     op16* qkv, op16* attn, op16* fc1, cudaStream_t s) {
   const int w = h->cfg.width;
   const int M = batch * L;
   MSCLIP_TRY(launch_layernorm_bf16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
@@ -535,10 +534,10 @@ static const int kLateral[5] = {2, 4, 6, 8, 10};  // PARALLEL_LATERAL_LAYER, b32
 static const int kConvChunk = 256;                 // images per pass through the conv stages
 static const int kTowerChunk = 4096;               // sequences per pass through the transformer
 
-// image tower for `batch` images already on the device; feat_bf16 (optional) receives the bf16 copy of
+// image tower for `batch` images already on the device; feat_bf16 (optional) receives the op16 copy of
 // the normalised features for the loss kernel
 static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, float* out_dev, int normalize,
-                        bf16* feat_bf16, cudaStream_t s) {
+                        op16* feat_bf16, cudaStream_t s) {
   const msclip_config& c = h->cfg;
   const int w = c.width, R = c.image_resolution, g = h->grid, L = h->l_img, c0 = w / 16;
   const int H1 = R / 2;
@@ -550,8 +549,8 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   const int nbmax = std::min(batch, kConvChunk);
   const size_t px1 = static_cast<size_t>(H1) * H1;  // pixels after the first conv
 
-  WS(col0, bf16, "col0", nbmax * px1 * 32);
-  WS(a1, bf16, "a1", nbmax * px1 * 2 * c0);
+  WS(col0, op16, "col0", nbmax * px1 * 32);
+  WS(a1, op16, "a1", nbmax * px1 * 2 * c0);
   // largest im2col matrix and activation of the later stages (stage 0 of the stem dominates)
   size_t col_max = 0, act_max = 0;
   {
@@ -573,12 +572,12 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
       Hc = Ho;
     }
   }
-  WS(col, bf16, "col", nbmax * col_max);
-  WS(actA, bf16, "actA", nbmax * act_max);
-  WS(actB, bf16, "actB", nbmax * act_max);
-  WS(actC, bf16, "actC", nbmax * act_max);
+  WS(col, op16, "col", nbmax * col_max);
+  WS(actA, op16, "actA", nbmax * act_max);
+  WS(actB, op16, "actB", nbmax * act_max);
+  WS(actC, op16, "actC", nbmax * act_max);
   WS(gridtmp, float, "gridtmp", static_cast<size_t>(batch) * g * g * w);
-  bf16* pooled[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  op16* pooled[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int j = 0; j < n_active; ++j) {
     const std::string nm = "pooled" + std::to_string(j);
     MSCLIP_TRY(ws_get(h, nm.c_str(), static_cast<size_t>(batch) * g * g * dims[j] * 2, reinterpret_cast<void**>(&pooled[j])));
@@ -594,12 +593,12 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     count_launch(2);
     // ---- stem: 4 residual stride blocks, then the 1x1 last_conv (M.py:1995-2000)
     {
-      const bf16* cur = a1;
+      const op16* cur = a1;
       int cpix = 2 * c0, ch = c0, Hc = H1;
-      bf16* outs[2] = {actA, actB};
+      op16* outs[2] = {actA, actB};
       for (int i = 0; i < 4; ++i) {
         const int st = c.early_strides[i], Ho = Hc / st;
-        bf16* o = outs[i & 1];
+        op16* o = outs[i & 1];
         // the gather-fed kernel wins while the MMA work per gathered byte is small (N <= 384); the widest stage
         // is better served by the TMA-fed GEMM on an explicit patch matrix (profiles/r01_kernel_bench.md)
         if (g_conv_im2col || 2 * ch >= 768) {
@@ -624,22 +623,22 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     }
     // ---- parallel branch (M.py:2436-2442) -> only the patch-pooled features the adapters need are kept
     if (n_active > 0) {
-      const bf16* p = a1;
+      const op16* p = a1;
       int cpix = 2 * c0, coff = c0, Hc = H1;
       MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, coff, dims[0], h->adapters[0].k, h->adapters[0].dw_w,
                                    h->adapters[0].dw_b, pooled[0] + static_cast<size_t>(b0) * g * g * dims[0], s));
       count_launch(1);
-      bf16* pbuf[2] = {actA, actB};
+      op16* pbuf[2] = {actA, actB};
       for (int j = 1; j < n_active; ++j) {
         const int cin = dims[j - 1], st = c.parallel_strides[j], Ho = Hc / st;
         // y1 = relu(bn1(conv1x1(p)))
         MSCLIP_TRY(launch_gemm(p + coff, cpix, h->br1[j].w, cin, nb * Hc * Hc, cin, cin, h->br1[j].b, actC, cin, nullptr,
                                0, EPI_RELU_BF16, s));
-        bf16* pn = pbuf[j & 1];
+        op16* pn = pbuf[j & 1];
         if (g_conv_im2col) {
           // y2 = relu(bn2(conv3x3_s(y1)))  -> columns [0, cin) of the concatenated operand
           MSCLIP_TRY(launch_im2col_nhwc(actC, nb, Hc, Hc, cin, 0, cin, 3, st, 1, col, 9 * cin, 0, s));
-          bf16* cat = actC;  // y1 is dead once its im2col exists
+          op16* cat = actC;  // y1 is dead once its im2col exists
           MSCLIP_TRY(launch_gemm(col, 9 * cin, h->br2[j].w, 9 * cin, nb * Ho * Ho, cin, 9 * cin, h->br2[j].b, cat, 2 * cin,
                                  nullptr, 0, EPI_RELU_BF16, s));
           // strided shortcut input -> columns [cin, 2cin)
@@ -650,7 +649,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
           count_launch(2);
         } else {
           // y2 = relu(bn2(conv3x3_s(y1))): implicit GEMM straight from y1
-          bf16* y2 = col;
+          op16* y2 = col;
           const ConvSource s2 = {actC, Hc, Hc, cin, 0, cin, 3, st, 1};
           MSCLIP_TRY(launch_conv_gemm(&s2, 1, nb, Ho, Ho, h->br2[j].w, 9 * cin, cin, h->br2[j].b, y2, cin, EPI_RELU_BF16, s));
           // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p))): one GEMM over K = [y2 | strided p]
@@ -674,11 +673,11 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   const size_t Mmax = static_cast<size_t>(tb) * std::max(L, c.context_length);
   WS(x, float, "x", Mmax * w);
   WS(x2, float, "x2", Mmax * w);
-  WS(hbuf, bf16, "h", Mmax * w);
-  WS(qkv, bf16, "qkv", Mmax * 3 * w);
-  WS(attn, bf16, "attn", Mmax * w);
-  WS(fc1, bf16, "fc1", Mmax * 4 * w);
-  WS(pool_ln, bf16, "pool_ln", static_cast<size_t>(tb) * w);
+  WS(hbuf, op16, "h", Mmax * w);
+  WS(qkv, op16, "qkv", Mmax * 3 * w);
+  WS(attn, op16, "attn", Mmax * w);
+  WS(fc1, op16, "fc1", Mmax * 4 * w);
+  WS(pool_ln, op16, "pool_ln", static_cast<size_t>(tb) * w);
   WS(feat_raw, float, "feat_raw", static_cast<size_t>(tb) * c.embed_dim);
   for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
     const int nb = std::min(kTowerChunk, batch - b0);
@@ -712,18 +711,18 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   return 0;
 }
 
-static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_dev, int normalize, bf16* feat_bf16,
+static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_dev, int normalize, op16* feat_bf16,
                       cudaStream_t s) {
   const msclip_config& c = h->cfg;
   const int w = c.width, L = c.context_length;
   const int tb = std::min(batch, kTowerChunk);
   const size_t Mmax = static_cast<size_t>(tb) * std::max(h->l_img, L);
   WS(x, float, "x", Mmax * w);
-  WS(hbuf, bf16, "h", Mmax * w);
-  WS(qkv, bf16, "qkv", Mmax * 3 * w);
-  WS(attn, bf16, "attn", Mmax * w);
-  WS(fc1, bf16, "fc1", Mmax * 4 * w);
-  WS(pool_ln, bf16, "pool_ln", static_cast<size_t>(tb) * w);
+  WS(hbuf, op16, "h", Mmax * w);
+  WS(qkv, op16, "qkv", Mmax * 3 * w);
+  WS(attn, op16, "attn", Mmax * w);
+  WS(fc1, op16, "fc1", Mmax * 4 * w);
+  WS(pool_ln, op16, "pool_ln", static_cast<size_t>(tb) * w);
   WS(feat_raw, float, "feat_raw", static_cast<size_t>(tb) * c.embed_dim);
   for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
     const int nb = std::min(kTowerChunk, batch - b0);
@@ -773,7 +772,7 @@ int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, 
     WS(o, float, "img_out", static_cast<size_t>(batch) * c.embed_dim);
     out_dev = o;
   }
-  bf16* fb = nullptr;
+  op16* fb = nullptr;
   if (normalize) {
     MSCLIP_TRY(ensure_xchg(h, batch));
     if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 0);
@@ -804,7 +803,7 @@ int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* o
     WS(o, float, "txt_out", static_cast<size_t>(batch) * c.embed_dim);
     out_dev = o;
   }
-  bf16* fb = nullptr;
+  op16* fb = nullptr;
   if (normalize) {
     MSCLIP_TRY(ensure_xchg(h, batch));
     if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 1);
@@ -819,18 +818,18 @@ int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* o
   return 0;
 }
 
-// split-bf16 operands: [hi | hi | lo] . [hi | lo | hi]^T = hi.hi + hi.lo + lo.hi  (fp32-grade similarity
-// on the bf16 tensor cores; the lo.lo term is below fp32 rounding)
+// split-op16 operands: [hi | hi | lo] . [hi | lo | hi]^T = hi.hi + hi.lo + lo.hi  (fp32-grade similarity
+// on the op16 tensor cores; the lo.lo term is below fp32 rounding)
 __global__ void __launch_bounds__(256)
-split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long rows, int E, int role) {
+split_bf16_kernel(const float* __restrict__ x, op16* __restrict__ out, long long rows, int E, int role) {
   const long long total = rows * E;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
     const long long r = i / E;
     const int k = static_cast<int>(i % E);
     const float v = x[i];
-    const bf16 hi = __float2bfloat16_rn(v);
-    const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    bf16* o = out + r * 3 * E;
+    const op16 hi = to_op16(v);
+    const op16 lo = to_op16(v - op16_to_float(hi));
+    op16* o = out + r * 3 * E;
     o[k] = hi;
     o[E + k] = role == 0 ? hi : lo;
     o[2 * E + k] = role == 0 ? lo : hi;
@@ -854,8 +853,8 @@ int engine_similarity_logits(msclip_ctx* h, const float* img, int n_img, const f
     MSCLIP_CHECK_CUDA(cudaMemcpyAsync(sb, txt, static_cast<size_t>(n_txt) * E * 4, cudaMemcpyHostToDevice, s));
     b = sb;
   }
-  WS(a3, bf16, "sim_a", static_cast<size_t>(n_img) * 3 * E);
-  WS(b3, bf16, "sim_b", static_cast<size_t>(n_txt) * 3 * E);
+  WS(a3, op16, "sim_a", static_cast<size_t>(n_img) * 3 * E);
+  WS(b3, op16, "sim_b", static_cast<size_t>(n_txt) * 3 * E);
   const bool out_dev_ptr = is_device_pointer(logits);
   float* o = logits;
   if (!out_dev_ptr) {
@@ -912,8 +911,8 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
   h->epoch += 1;
   const int par = static_cast<int>(h->epoch & 1);
   void** tables = static_cast<void**>(h->shard_tables);
-  const bf16* const* img_tab = reinterpret_cast<const bf16* const*>(tables + (par * 2 + 0) * W);
-  const bf16* const* txt_tab = reinterpret_cast<const bf16* const*>(tables + (par * 2 + 1) * W);
+  const op16* const* img_tab = reinterpret_cast<const op16* const*>(tables + (par * 2 + 0) * W);
+  const op16* const* txt_tab = reinterpret_cast<const op16* const*>(tables + (par * 2 + 1) * W);
   const uint32_t* flags = nullptr;
   if (W > 1) {
     publish_kernel<<<1, 32, 0, s>>>(h->peer_flag_tables, W, h->rank, h->epoch);

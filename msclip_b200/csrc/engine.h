@@ -27,20 +27,20 @@ struct DevBuf {
 };
 
 struct BlockWeights {
-  bf16 *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
+  op16 *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
   float *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
 };
 
 struct ConvWeights {
-  bf16* w = nullptr;   // [N, K] bf16, BN scale folded
+  op16* w = nullptr;   // [N, K] op16, BN scale folded
   float* b = nullptr;  // [N] BN shift (null = no bias)
   int N = 0, K = 0;
 };
 
 struct AdapterWeights {
   float *dw_w = nullptr, *dw_b = nullptr;    // top2bottom depth-wise k x k (+BN): [k*k][C], [C]
-  bf16* pw = nullptr;                        // top2bottom point-wise: [768, C]
+  op16* pw = nullptr;                        // top2bottom point-wise: [768, C]
   float *bdw_w9 = nullptr, *bdw_b = nullptr; // bottom depth-wise 3x3 (+BN): [9][768], [768]
   float *ln_w = nullptr, *ln_b = nullptr;
   int C = 0, k = 0;
@@ -63,7 +63,7 @@ struct msclip_ctx {
   float *cls = nullptr, *vpos = nullptr, *ln_pre_w = nullptr, *ln_pre_b = nullptr, *ln_post_w = nullptr,
         *ln_post_b = nullptr;
   float *tok_emb = nullptr, *tpos = nullptr, *ln_final_w = nullptr, *ln_final_b = nullptr;
-  msclip::bf16 *vproj = nullptr, *tproj = nullptr;  // [embed, width] (transposed projections)
+  msclip::op16 *vproj = nullptr, *tproj = nullptr;  // [embed, width] (transposed projections)
   std::vector<void*> weight_allocs;
   size_t weight_bytes = 0;
 
@@ -75,7 +75,7 @@ struct msclip_ctx {
 
   // embedding exchange (data-parallel contrastive loss)
   int rank = 0, world = 1, max_b_local = 0;
-  void* xchg = nullptr;  // [2 parity][2 modality][max_b_local, E] bf16, then uint32 flags[world]
+  void* xchg = nullptr;  // [2 parity][2 modality][max_b_local, E] op16, then uint32 flags[world]
   size_t xchg_bytes = 0;
   std::vector<void*> peer_base;    // imported peer bases (own base at [rank])
   void* shard_tables = nullptr;    // device: [2 parity][2 modality][world] pointers

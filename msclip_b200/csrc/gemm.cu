@@ -2,7 +2,7 @@
 //
 // Replaces every F.linear of the shared block (QKV M.py:612, out-proj M.py:747, MLP M.py:794-798), the
 // projections (M.py:2690, 3074) and - through im2col - the convolutions of the stem / parallel branch
-// (M.py:1993-2000, 1842-1861).  Both operands are K-major bf16 (A = activations [M,K], W = nn.Linear
+// (M.py:1993-2000, 1842-1861).  Both operands are K-major op16 (A = activations [M,K], W = nn.Linear
 // weight [N,K]), accumulation is fp32 in TMEM, and the epilogue (bias, QuickGELU / ReLU, residual add
 // on the fp32 stream) is fused so no GEMM output ever makes an extra HBM round trip.
 //
@@ -286,12 +286,12 @@ int gemm_pick_bn(int N) {
   return 256;
 }
 
-int launch_gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, const float* bias,
+int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
                 void* out, int64_t ldo, const float* resid, int64_t ldr, int epi, cudaStream_t stream) {
   return launch_gemm_scaled(A, lda, W, ldw, M, N, K, 1.0f, bias, out, ldo, resid, ldr, epi, stream);
 }
 
-int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, float alpha,
+int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
                        cudaStream_t stream) {
   MSCLIP_REQUIRE(M > 0 && N > 0 && K > 0, "launch_gemm: empty problem");

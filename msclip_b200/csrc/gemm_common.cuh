@@ -9,7 +9,7 @@ namespace msclip {
 namespace gemm_detail {
 
 constexpr int kBM = 128;
-constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kBK = 64;  // 64 op16 = 128 B = one swizzle row
 constexpr int kNumEpilogueWarps = 8;
 constexpr int kGemmThreads = 128 + 32 * kNumEpilogueWarps;  // TMA, MMA, TMEM-alloc, spare + epilogue warps
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
@@ -77,7 +77,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
         if (EPI == EPI_RESID_F32 || EPI == EPI_F32)
           reinterpret_cast<float*>(p.out)[static_cast<long long>(row) * p.ldo + col] = x;
         else
-          reinterpret_cast<bf16*>(p.out)[static_cast<long long>(row) * p.ldo + col] = __float2bfloat16_rn(x);
+          reinterpret_cast<op16*>(p.out)[static_cast<long long>(row) * p.ldo + col] = to_op16(x);
       }
     }
     return;
@@ -110,11 +110,11 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
 #pragma unroll
     for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   } else {
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<op16*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
 #pragma unroll
     for (int j = 0; j < CH / 8; ++j)
-      o4[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                         pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      o4[j] = make_uint4(pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
+                         pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
   }
 }
 

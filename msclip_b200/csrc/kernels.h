@@ -5,36 +5,69 @@
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace msclip {
 
-typedef __nv_bfloat16 bf16;
+// 16-bit operand type of every MMA (activations, packed weights, embeddings): bf16 by default, IEEE fp16 when
+// the library is compiled with -DMSCLIP_FP16 (same tensor-core rate, 3 more mantissa bits, 5-bit less exponent;
+// conversions saturate at +-65504).  Accumulation is fp32 in both builds.
+#ifdef MSCLIP_FP16
+typedef __half op16;
+typedef __half2 op162;
+#define MSCLIP_OPERAND_NAME "fp16"
+#define MSCLIP_MMA_OPERANDS "f16.f16"
+#define MSCLIP_TMA_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+constexpr uint32_t kUmmaOperandFormat = 0;  // kind::f16 A/B format field: 0 = F16, 1 = BF16
+#else
+typedef __nv_bfloat16 op16;
+typedef __nv_bfloat162 op162;
+#define MSCLIP_OPERAND_NAME "bf16"
+#define MSCLIP_MMA_OPERANDS "bf16.bf16"
+#define MSCLIP_TMA_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+constexpr uint32_t kUmmaOperandFormat = 1;
+#endif
+
+__host__ __device__ inline op16 to_op16(float x) {
+#ifdef MSCLIP_FP16
+  return __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
+#else
+  return __float2bfloat16_rn(x);
+#endif
+}
+__host__ __device__ inline float op16_to_float(op16 x) {
+#ifdef MSCLIP_FP16
+  return __half2float(x);
+#else
+  return __bfloat162float(x);
+#endif
+}
 
 int num_sms();
 
 // ---- tcgen05 GEMM: out[M,N] = epi(A[M,K] . W[N,K]^T + bias)  (gemm.cu) ----------------------
 enum GemmEpilogue {
-  EPI_BF16 = 0,        // bf16 out = acc + bias
-  EPI_QGELU_BF16 = 1,  // bf16 out = quickgelu(acc + bias)          (M.py:222-224)
-  EPI_RELU_BF16 = 2,   // bf16 out = relu(acc + bias)               (conv + folded BN + ReLU)
+  EPI_BF16 = 0,        // op16 out = acc + bias
+  EPI_QGELU_BF16 = 1,  // op16 out = quickgelu(acc + bias)          (M.py:222-224)
+  EPI_RELU_BF16 = 2,   // op16 out = relu(acc + bias)               (conv + folded BN + ReLU)
   EPI_RESID_F32 = 3,   // f32  out = resid + acc + bias             (residual stream, may alias out)
   EPI_F32 = 4,         // f32  out = acc + bias
 };
-int launch_gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, const float* bias,
+int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
                 void* out, int64_t ldo, const float* resid, int64_t ldr, int epi, cudaStream_t stream);
 
 void gemm_set_pair_mode(int mode);  // 0: 1 CTA per tile, 1: CTA pairs, 2|4: multicast clusters of 2|4 pairs
-int launch_gemm_scaled(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int M, int N, int K, float alpha,
+int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
                        cudaStream_t stream);
 
 // ---- LayerNorm family, D = 768 (elementwise.cu) ----------------------------------------------
-// y[r] = LN(x[r * row_stride]) ; out bf16 (GEMM operand).  row_stride = L picks the CLS rows.
-int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const float* b, bf16* y, int rows,
+// y[r] = LN(x[r * row_stride]) ; out op16 (GEMM operand).  row_stride = L picks the CLS rows.
+int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
                           cudaStream_t stream);
 // text pooling: row b <- LN(x[b*L + argmax_j tok[b,j]])  (M.py:3057-3060, 3072)
-int launch_eot_layernorm_bf16(const float* x, const int64_t* tok, int L, const float* w, const float* b, bf16* y,
+int launch_eot_layernorm_bf16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
                               int batch, cudaStream_t stream);
 // x[b*L+l] = tok_emb[tok[b,l]] + pos[l]   (M.py:3047-3048)
 int launch_text_embed(const int64_t* tok, const float* tok_emb, const float* pos, float* x, int batch, int L,
@@ -45,34 +78,34 @@ int launch_image_embed_ln_pre(const float* grid, const float* cls, const float* 
 // Lateral adapter tail (M.py:1760-1777): x_out = ln_adapt(concat(2*cls, BN(dw3x3(grid(x))) + t))
 int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                            const float* b, float* x_out, int batch, int g, cudaStream_t stream);
-// out[r] = x[r] / ||x[r]|| (optional) as f32 and bf16 copies; width E (<= 1024, multiple of 4)
+// out[r] = x[r] / ||x[r]|| (optional) as f32 and op16 copies; width E (<= 1024, multiple of 4)
 int check_token_error(cudaStream_t stream);  // synchronises; non-zero if an out-of-range token id was seen
-int launch_l2norm(const float* x, float* out_f32, bf16* out_bf16, int rows, int E, int normalise, cudaStream_t stream);
+int launch_l2norm(const float* x, float* out_f32, op16* out_bf16, int rows, int E, int normalise, cudaStream_t stream);
 
 // ---- conv helpers (conv.cu) -------------------------------------------------------------------
-// NCHW fp32 image -> im2col rows [B*Ho*Wo, 32] bf16 for the 3x3 stride-2 pad-1 first convs; k = c*9+ky*3+kx
-int launch_im2col_first(const void* img, int img_dtype, bf16* out, int batch, int H, int W, cudaStream_t stream);
-// NHWC bf16 (pixel pitch cpix, channel offset c_off, C channels, C % 8 == 0) -> rows [B*Ho*Wo] of
+// NCHW fp32 image -> im2col rows [B*Ho*Wo, 32] op16 for the 3x3 stride-2 pad-1 first convs; k = c*9+ky*3+kx
+int launch_im2col_first(const void* img, int img_dtype, op16* out, int batch, int H, int W, cudaStream_t stream);
+// NHWC op16 (pixel pitch cpix, channel offset c_off, C channels, C % 8 == 0) -> rows [B*Ho*Wo] of
 // ksize*ksize*C columns (k = (ky*ksize+kx)*C + c) written at out[row*out_ld + out_off + k]
-int launch_im2col_nhwc(const bf16* in, int batch, int H, int W, int cpix, int c_off, int C, int ksize, int stride,
-                       int pad, bf16* out, int64_t out_ld, int out_off, cudaStream_t stream);
+int launch_im2col_nhwc(const op16* in, int batch, int H, int W, int cpix, int c_off, int C, int ksize, int stride,
+                       int pad, op16* out, int64_t out_ld, int out_off, cudaStream_t stream);
 // depth-wise k x k / stride k patch pooling + folded BN (Lateral_Adapter top2bottom_dw_conv, M.py:1756)
-// in NHWC bf16 [B,H,W,cpix] (+c_off), w [k*k][C] f32, bias [C] f32 -> out [B*(H/k)*(W/k), C] bf16
-int launch_patch_pool(const bf16* in, int batch, int H, int W, int cpix, int c_off, int C, int k, const float* w,
-                      const float* bias, bf16* out, cudaStream_t stream);
+// in NHWC op16 [B,H,W,cpix] (+c_off), w [k*k][C] f32, bias [C] f32 -> out [B*(H/k)*(W/k), C] op16
+int launch_patch_pool(const op16* in, int batch, int H, int W, int cpix, int c_off, int C, int k, const float* w,
+                      const float* bias, op16* out, cudaStream_t stream);
 
 // ---- implicit-GEMM convolution (conv_gemm.cu): out[B*Ho*Wo, N] = epi(patches . W^T + bias) ---------------
 // K is the concatenation of the sources' (ky, kx, c) patch vectors; every source must map onto the same
-// Ho x Wo output grid.  NHWC bf16 inputs with pixel pitch cpix, channel window [c_off, c_off + C).
+// Ho x Wo output grid.  NHWC op16 inputs with pixel pitch cpix, channel window [c_off, c_off + C).
 struct ConvSource {
   const void* in;
   int H, W, cpix, c_off, C, ksize, stride, pad;
 };
-int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const bf16* W, int64_t ldw, int N,
+int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const op16* W, int64_t ldw, int N,
                      const float* bias, void* out, int64_t ldo, int epi, cudaStream_t stream);
 
-// ---- attention (attention.cu): qkv bf16 [B*L, 3*768] (q pre-scaled) -> out bf16 [B*L, 768] ------
-int launch_attention(const bf16* qkv, bf16* out, int batch, int L, int heads, int causal, cudaStream_t stream);
+// ---- attention (attention.cu): qkv op16 [B*L, 3*768] (q pre-scaled) -> out op16 [B*L, 768] ------
+int launch_attention(const op16* qkv, op16* out, int batch, int L, int heads, int causal, cudaStream_t stream);
 
 // ---- contrastive loss (loss.cu) ---------------------------------------------------------------
 // Fused similarity + log-sum-exp for the local rows against all G = world*b_local columns, both
@@ -80,18 +113,18 @@ int launch_attention(const bf16* qkv, bf16* out, int batch, int L, int heads, in
 // loss_parts[0] = sum_i (lse_i - s_ii) over local image rows, [1] = same over local text rows;
 // loss = (sum over ranks of parts[0] + parts[1]) / (2 G).  img_shards / txt_shards: device arrays of
 // `world` rank-ordered shard pointers; flags: this rank's device array of `world` publish flags or null.
-int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, const bf16* const* img_shards,
-                               const bf16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
+int launch_contrastive_loss_ex(const op16* img_local, const op16* txt_local, const op16* const* img_shards,
+                               const op16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
                                int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
                                cudaStream_t stream);
 size_t contrastive_loss_workspace_bytes(int world, int b_local);
 // plain logits (eval path / parity): out[i,j] = scale * <a_i, b_j>, f32 [Ma, Mb]
-int launch_similarity_logits(const bf16* a, const bf16* b, int Ma, int Mb, int E, float scale, float* out,
+int launch_similarity_logits(const op16* a, const op16* b, int Ma, int Mb, int E, float scale, float* out,
                              cudaStream_t stream);
 
 // ---- weight packing (pack.cu) -------------------------------------------------------------------
-// dst[n, k] (bf16, pitch ldd) = src[n*sn + k*sk] * (row_scale ? row_scale[n] : 1)
-int launch_pack_bf16(const float* src, int64_t sn, int64_t sk, const float* row_scale, bf16* dst, int64_t ldd, int N,
+// dst[n, k] (op16, pitch ldd) = src[n*sn + k*sk] * (row_scale ? row_scale[n] : 1)
+int launch_pack_op16(const float* src, int64_t sn, int64_t sk, const float* row_scale, op16* dst, int64_t ldd, int N,
                      int K, cudaStream_t stream);
 
 }  // namespace msclip

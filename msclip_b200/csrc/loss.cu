@@ -30,7 +30,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct LossParams {
-  const bf16* const* col_shards[2];  // [dir] -> device table of `world` shard pointers (columns of that direction)
+  const op16* const* col_shards[2];  // [dir] -> device table of `world` shard pointers (columns of that direction)
   const uint32_t* flags;             // optional: this rank's flag array [world], raised by the owners; null for world == 1
   uint32_t epoch;
   int world, rank, b_local, tiles_per_shard, n_col_tiles, n_row_blocks, b_pad;
@@ -100,7 +100,7 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
     __syncthreads();
   }
   {
-    const bf16* src = p.col_shards[dir][owner] + static_cast<long long>(c0) * kLossE;
+    const op16* src = p.col_shards[dir][owner] + static_cast<long long>(c0) * kLossE;
     // 128 rows x 64 chunks of 16 B; adjacent threads read adjacent chunks of one row (coalesced)
     for (int i = threadIdx.x; i < kLossBN * (kLossE / 8); i += kLossThreads) {
       const int r = i >> 6;
@@ -265,8 +265,8 @@ size_t contrastive_loss_workspace_bytes(int world, int b_local) {
          2 * static_cast<size_t>(b_local) * sizeof(float);
 }
 
-int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, const bf16* const* img_shards,
-                               const bf16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
+int launch_contrastive_loss_ex(const op16* img_local, const op16* txt_local, const op16* const* img_shards,
+                               const op16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
                                int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
                                cudaStream_t stream) {
   MSCLIP_REQUIRE(E == kLossE, "contrastive loss: embedding width must be 512");
@@ -306,7 +306,7 @@ int launch_contrastive_loss_ex(const bf16* img_local, const bf16* txt_local, con
   return 0;
 }
 
-int launch_similarity_logits(const bf16* a, const bf16* b, int Ma, int Mb, int E, float scale, float* out,
+int launch_similarity_logits(const op16* a, const op16* b, int Ma, int Mb, int E, float scale, float* out,
                              cudaStream_t stream) {
   return launch_gemm_scaled(a, E, b, E, Ma, Mb, E, scale, nullptr, out, Mb, nullptr, 0, EPI_F32, stream);
 }

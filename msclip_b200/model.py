@@ -70,9 +70,13 @@ def _init_tensor(key: str, shape) -> torch.Tensor:
 
 
 class CLIP(nn.Module):
-    def __init__(self, cfg: MSCLIPConfig):
+    def __init__(self, cfg: MSCLIPConfig, precision: Optional[str] = None):
+        """``precision``: MMA operand type of the library build to use - "bf16" (default, the north star's
+        dtype) or "fp16" (same speed, 3 more mantissa bits, saturating conversions); env MSCLIP_PRECISION
+        sets the default.  Accumulation, residual stream, LayerNorm and softmax are fp32 in both."""
         super().__init__()
         self.cfg = cfg
+        self.precision = precision or _lib.default_precision()
         self._spec = state_dict_spec(cfg)
         made = {}
         for key, shape in self._spec.items():
@@ -99,19 +103,25 @@ class CLIP(nn.Module):
         return self.visual.proj.device
 
     # ---- library handle ------------------------------------------------------------------------------
+    def _library(self):
+        return _lib.lib(self.precision)
+
+    def _check(self, rc, what=""):
+        _lib.check(rc, what, self.precision)
+
     def _ensure_handle(self):
         if not self._handle:
             c = self.cfg
             cc = _lib.Config(c.patch_size, c.layers, c.width, c.embed_dim, c.image_resolution, c.context_length,
                              c.vocab_size, (C.c_int32 * 4)(*c.early_strides), (C.c_int32 * 5)(*c.parallel_strides),
                              (C.c_int32 * 5)(*c.t2b_kernels))
-            _lib.check(_lib.lib().msclip_create(C.byref(cc), C.byref(self._handle)), "msclip_create")
+            self._check(self._library().msclip_create(C.byref(cc), C.byref(self._handle)), "msclip_create")
         return self._handle
 
     def __del__(self):
         try:
             if getattr(self, "_handle", None):
-                _lib.lib().msclip_destroy(self._handle)
+                self._library().msclip_destroy(self._handle)
                 self._handle = C.c_void_p()
         except Exception:
             pass
@@ -128,16 +138,16 @@ class CLIP(nn.Module):
         if not torch.cuda.is_available():
             raise _lib.MsclipError("msclip_b200 needs an sm_100 GPU: there is no CPU fallback")
         h = self._ensure_handle()
-        L = _lib.lib()
+        L = self._library()
         for key, t in sd.items():
             if t.dtype == torch.long:
                 dt, tt = _lib.I64, t
             else:
                 dt, tt = _lib.F32, t.detach().to(torch.float32).contiguous()
             shape = (C.c_int64 * max(tt.dim(), 1))(*tt.shape)
-            _lib.check(L.msclip_set_weight(h, key.encode(), C.c_void_p(tt.data_ptr()), dt, tt.dim(), shape),
+            self._check(L.msclip_set_weight(h, key.encode(), C.c_void_p(tt.data_ptr()), dt, tt.dim(), shape),
                        f"msclip_set_weight({key})")
-        _lib.check(L.msclip_finalize_weights(h, self._stream()), "msclip_finalize_weights")
+        self._check(L.msclip_finalize_weights(h, self._stream()), "msclip_finalize_weights")
         self._synced = finger
 
     # ---- reference methods ---------------------------------------------------------------------------
@@ -153,7 +163,7 @@ class CLIP(nn.Module):
         image = image.contiguous()
         self._sync_weights()
         out = torch.empty((image.shape[0], c.embed_dim), dtype=torch.float32, device=image.device)
-        _lib.check(_lib.lib().msclip_encode_image(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+        self._check(self._library().msclip_encode_image(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
                                                   image.shape[0], C.c_void_p(out.data_ptr()), int(bool(norm)),
                                                   self._stream()), "msclip_encode_image")
         return out
@@ -168,7 +178,7 @@ class CLIP(nn.Module):
         text = text.to(torch.long).contiguous()
         self._sync_weights()
         out = torch.empty((text.shape[0], c.embed_dim), dtype=torch.float32, device=text.device)
-        _lib.check(_lib.lib().msclip_encode_text(self._handle, C.c_void_p(text.data_ptr()), text.shape[0],
+        self._check(self._library().msclip_encode_text(self._handle, C.c_void_p(text.data_ptr()), text.shape[0],
                                                  C.c_void_p(out.data_ptr()), int(bool(norm)), self._stream()),
                    "msclip_encode_text")
         return out
@@ -180,7 +190,7 @@ class CLIP(nn.Module):
         ft = text_features.float().contiguous()
         self._ensure_handle()
         out = torch.empty((fi.shape[0], ft.shape[0]), dtype=torch.float32, device=fi.device)
-        _lib.check(_lib.lib().msclip_similarity_logits(self._handle, C.c_void_p(fi.data_ptr()), fi.shape[0],
+        self._check(self._library().msclip_similarity_logits(self._handle, C.c_void_p(fi.data_ptr()), fi.shape[0],
                                                        C.c_void_p(ft.data_ptr()), ft.shape[0], float(scale),
                                                        C.c_void_p(out.data_ptr()), self._stream()),
                    "msclip_similarity_logits")
@@ -206,7 +216,7 @@ class CLIP(nn.Module):
         """Register the peer-visible embedding buffers of all ranks (one process per GPU)."""
         from .comm import setup_peer_exchange
         self._sync_weights()
-        self._comm = setup_peer_exchange(self._handle, max_b_local, group)
+        self._comm = setup_peer_exchange(self._handle, max_b_local, group, self.precision)
         return self._comm
 
     @torch.no_grad()
@@ -225,7 +235,7 @@ class CLIP(nn.Module):
         dev = self.device
         parts = torch.empty(2, dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib().msclip_forward_loss(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+        self._check(self._library().msclip_forward_loss(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
                                                   C.c_void_p(text.data_ptr()), b, C.c_void_p(parts.data_ptr()),
                                                   C.c_void_p(loss.data_ptr()) if world == 1 else None, self._stream()),
                    "msclip_forward_loss")
@@ -236,13 +246,14 @@ class CLIP(nn.Module):
         return parts.sum() / (2.0 * world * b)
 
     def launch_count(self) -> int:
-        return int(_lib.lib().msclip_launch_count(self._handle)) if self._handle else 0
+        return int(self._library().msclip_launch_count(self._handle)) if self._handle else 0
 
 
-def get_clip_model(config: Any, vocab_size: Optional[int] = None, eot_token: Optional[int] = None, **kwargs) -> CLIP:
+def get_clip_model(config: Any, vocab_size: Optional[int] = None, eot_token: Optional[int] = None,
+                   precision: Optional[str] = None, **kwargs) -> CLIP:
     """Drop-in for ``clip_openai_pe_res_v1.get_clip_model`` (M.py:3182-3227): accepts the reference's
     yacs config (or any duck-typed equivalent) and refuses flag combinations outside MS-CLIP-S."""
     cfg = config if isinstance(config, MSCLIPConfig) else from_reference_config(config)
     if vocab_size is not None and int(vocab_size) != cfg.vocab_size:
         cfg = MSCLIPConfig(**{**cfg.to_dict(), "vocab_size": int(vocab_size)})
-    return CLIP(cfg)
+    return CLIP(cfg, precision)

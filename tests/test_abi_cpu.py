@@ -42,7 +42,11 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
     assert decl == set(_lib.exported_symbols()), decl ^ set(_lib.exported_symbols())
-    assert b"sm_100a" in lib.msclip_version()
+    assert b"sm_100a" in lib.msclip_version() and b"bf16" in lib.msclip_version()
+    lib16 = _lib.lib("fp16")                                   # the fp16-operand build exports the same ABI
+    for name in decl:
+        assert hasattr(lib16, name), name
+    assert b"fp16" in lib16.msclip_version()
 
 
 @pytest.mark.parametrize("tag", ["b32_l2", "b32_l12", "b16_l3", "b16_l12"])
