@@ -46,7 +46,7 @@ def tol16():
 
 
 def check(rc, what=""):
-    check(rc, what, PREC)
+    _lib.check(rc, what, PREC)
 
 
 @pytest.fixture(params=["bf16", "fp16"], autouse=True)
