@@ -253,10 +253,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
             const int col0 = n0 + c * Cfg::kChunk;
             const bool fast = p.vec_ok && (col0 + Cfg::kChunk <= p.N);
             EpiOperands<EPI, Cfg::kChunk> ops;
-            if (row_ok) epilogue_prefetch<EPI, Cfg::kChunk>(ops, p, row, col0, fast);
+            epilogue_prefetch<EPI, Cfg::kChunk>(ops, p, row, col0, fast);
             tmem_ld_wait();
             if (c + 1 < c_end) tmem_ld_chunk<Cfg::kChunk>(taddr + (c + 1) * Cfg::kChunk, acc[(i + 1) & 1]);
-            if (row_ok) epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, p, row, col0, fast);
+            epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, p, row, col0, fast);
           }
         }
       }

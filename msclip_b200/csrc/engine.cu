@@ -531,7 +531,7 @@ static const bool g_conv_im2col = [] {
   return e != nullptr && e[0] == '1';
 }();
 static const int kLateral[5] = {2, 4, 6, 8, 10};  // PARALLEL_LATERAL_LAYER, b32-yfcc-msclips.yaml:18
-static const int kConvChunk = 256;                 // images per pass through the conv stages
+static const int kConvChunk = 1024;                // images per pass through the conv stages
 static const int kTowerChunk = 4096;               // sequences per pass through the transformer
 
 // image tower for `batch` images already on the device; feat_bf16 (optional) receives the op16 copy of

@@ -187,6 +187,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m0 = (tile / p.tiles_n) * (kBM * CG * NP) + static_cast<int>(pair_idx) * (kBM * CG) +
                      static_cast<int>(cta_rank) * kBM;
       const int n0 = (tile % p.tiles_n) * BN;
+      if (EPI == EPI_RESID_F32 && p.vec_ok) {
+        // the residual rows of this tile are known long before its accumulator is complete: pull them into L2
+        // while the MMAs run, so the epilogue's loads see L2 latency instead of DRAM latency
+        const int prow = m0 + q * 32 + lane;
+        if (prow < p.M) {
+          const float* rp = p.resid + static_cast<long long>(prow) * p.ldr + n0 + c_begin * Cfg::kChunk;
+#pragma unroll
+          for (int i = 0; i < kPerHalf; ++i)
+            if (c_begin + i < c_end && n0 + (c_begin + i + 1) * Cfg::kChunk <= p.N)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + i * Cfg::kChunk));
+        }
+      }
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
@@ -204,10 +216,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int col0 = n0 + c * Cfg::kChunk;
           const bool fast = p.vec_ok && (col0 + Cfg::kChunk <= p.N);
           EpiOperands<EPI, Cfg::kChunk> ops;
-          if (row_ok) epilogue_prefetch<EPI, Cfg::kChunk>(ops, p, row, col0, fast);
+          epilogue_prefetch<EPI, Cfg::kChunk>(ops, p, row, col0, fast);
           tmem_ld_wait();
           if (c + 1 < c_end) tmem_ld_chunk<Cfg::kChunk>(taddr + (c + 1) * Cfg::kChunk, acc[(i + 1) & 1]);
-          if (row_ok) epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, p, row, col0, fast);
+          epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, p, row, col0, fast);
         }
       }
       tc_fence_before();

@@ -31,12 +31,20 @@ __device__ __forceinline__ float quick_gelu(float x) {
   return x * fast_rcp(1.0f + fast_ex2(-2.4554669595930157f * x));
 }
 
-// Operands the epilogue needs from global memory for one chunk (bias slice, residual row segment); fetched
-// before the accumulator chunk is waited for so that their latency overlaps the TMEM load.
+// ---- fused epilogue ---------------------------------------------------------------------------------------
+// TMEM hands every thread one accumulator row (32 lanes = 32 rows, CH consecutive columns each).  Storing that
+// layout directly makes each warp-wide 16-byte access touch 32 different sectors and use half of each, which
+// doubles the L2 sector traffic of the epilogue.  Lane pairs therefore swap half of their values first: after the
+// swap lanes 2i / 2i+1 hold the even / odd 16-byte pieces of BOTH rows of the pair, so each warp-wide access
+// covers whole 32-byte sectors (rows are processed as "even row" then "odd row" of every pair).
+
+// Operands the epilogue needs from global memory for one chunk (bias slice, residual pieces in the swapped
+// layout); fetched before the accumulator chunk is waited for so their latency overlaps the TMEM load.
 template <int EPI, int CH>
 struct EpiOperands {
   float4 bias[CH / 4];
-  float4 resid[(EPI == EPI_RESID_F32) ? CH / 4 : 1];
+  float4 resid_even[(EPI == EPI_RESID_F32) ? CH / 8 : 1];  // even row of the lane pair, pieces 2j + (lane & 1)
+  float4 resid_odd[(EPI == EPI_RESID_F32) ? CH / 8 : 1];   // odd row of the lane pair
 };
 
 template <int EPI, int CH>
@@ -52,12 +60,20 @@ __device__ __forceinline__ void epilogue_prefetch(EpiOperands<EPI, CH>& o, const
     for (int j = 0; j < CH / 4; ++j) o.bias[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (EPI == EPI_RESID_F32) {
-    const float4* x4 = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row) * p.ldr + col0);
+    const int par = threadIdx.x & 1;
+    const int row_e = row & ~1, row_o = row | 1;
+    const float4* xe = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row_e) * p.ldr + col0);
+    const float4* xo = reinterpret_cast<const float4*>(p.resid + static_cast<long long>(row_o) * p.ldr + col0);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < CH / 4; ++j) o.resid[j] = x4[j];
+    for (int j = 0; j < CH / 8; ++j) {
+      o.resid_even[j] = row_e < p.M ? xe[2 * j + par] : z;
+      o.resid_odd[j] = row_o < p.M ? xo[2 * j + par] : z;
+    }
   }
 }
 
+// Must be called by all 32 lanes of the warp (it shuffles); rows >= M are masked inside.
 template <int EPI, int CH>
 __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const EpiOperands<EPI, CH>& o,
                                                const GemmParams& p, int row, int col0, bool fast) {
@@ -66,6 +82,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
   for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
   if (!fast) {
     // ragged edge (N not a multiple of the tile) or unaligned rows: scalar, bounds-checked
+    if (row >= p.M) return;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int col = col0 + j;
@@ -96,25 +113,52 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
+  const bool par = (threadIdx.x & 1) != 0;
+  const int row_e = row & ~1, row_o = row | 1;
+  const bool ok_e = row_e < p.M, ok_o = row_o < p.M;
   if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
-    if (EPI == EPI_RESID_F32) {
+    // pieces = float4 (4 columns); lane parity selects pieces 2j + par of both rows
+    float4* oe = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row_e) * p.ldo + col0);
+    float4* oo = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row_o) * p.ldo + col0);
 #pragma unroll
-      for (int j = 0; j < CH / 4; ++j) {
-        v[4 * j + 0] += o.resid[j].x;
-        v[4 * j + 1] += o.resid[j].y;
-        v[4 * j + 2] += o.resid[j].z;
-        v[4 * j + 3] += o.resid[j].w;
+    for (int j = 0; j < CH / 8; ++j) {
+      float e[4], d[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float lo = v[8 * j + t], hi = v[8 * j + 4 + t];  // pieces 2j and 2j+1 of this lane's own row
+        const float keep = par ? hi : lo;
+        const float recv = __shfl_xor_sync(0xffffffffu, par ? lo : hi, 1);
+        e[t] = par ? recv : keep;  // even row of the pair
+        d[t] = par ? keep : recv;  // odd row of the pair
       }
+      if (EPI == EPI_RESID_F32) {
+        e[0] += o.resid_even[j].x; e[1] += o.resid_even[j].y; e[2] += o.resid_even[j].z; e[3] += o.resid_even[j].w;
+        d[0] += o.resid_odd[j].x;  d[1] += o.resid_odd[j].y;  d[2] += o.resid_odd[j].z;  d[3] += o.resid_odd[j].w;
+      }
+      if (ok_e) oe[2 * j + par] = make_float4(e[0], e[1], e[2], e[3]);
+      if (ok_o) oo[2 * j + par] = make_float4(d[0], d[1], d[2], d[3]);
     }
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
-#pragma unroll
-    for (int j = 0; j < CH / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   } else {
-    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<op16*>(p.out) + static_cast<long long>(row) * p.ldo + col0);
+    // pieces = uint4 (8 columns of 16-bit values)
+    uint32_t u[CH / 2];
 #pragma unroll
-    for (int j = 0; j < CH / 8; ++j)
-      o4[j] = make_uint4(pack16(v[8 * j], v[8 * j + 1]), pack16(v[8 * j + 2], v[8 * j + 3]),
-                         pack16(v[8 * j + 4], v[8 * j + 5]), pack16(v[8 * j + 6], v[8 * j + 7]));
+    for (int j = 0; j < CH / 2; ++j) u[j] = pack16(v[2 * j], v[2 * j + 1]);
+    uint4* oe = reinterpret_cast<uint4*>(reinterpret_cast<op16*>(p.out) + static_cast<long long>(row_e) * p.ldo + col0);
+    uint4* oo = reinterpret_cast<uint4*>(reinterpret_cast<op16*>(p.out) + static_cast<long long>(row_o) * p.ldo + col0);
+#pragma unroll
+    for (int j = 0; j < CH / 16; ++j) {
+      uint32_t e[4], d[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t lo = u[8 * j + t], hi = u[8 * j + 4 + t];
+        const uint32_t keep = par ? hi : lo;
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, par ? lo : hi, 1);
+        e[t] = par ? recv : keep;
+        d[t] = par ? keep : recv;
+      }
+      if (ok_e) oe[2 * j + par] = make_uint4(e[0], e[1], e[2], e[3]);
+      if (ok_o) oo[2 * j + par] = make_uint4(d[0], d[1], d[2], d[3]);
+    }
   }
 }
 
