@@ -237,19 +237,27 @@ def run_ours(args, cfg, rank, world, local):
         tok_host = torch.from_numpy(tok_np).pin_memory()
         out_host = torch.zeros(3).pin_memory()
 
+        def stage_host():
+            _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host.data_ptr()), _lib.F32, B, sp), "msclip_stage_images")
+
         def step_host():
+            # a training loop's input pipeline: the images of the NEXT step start their H2D copy (second staging
+            # slot) before this step is issued, so every step still moves its full 2.47 GB over PCIe, overlapped
+            # with compute; tokens (2.5 MB) and the loss read-back ride the compute stream
+            stage_host()
             _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_host.data_ptr()), _lib.F32, C.c_void_p(tok_host.data_ptr()), B,
                                              C.c_void_p(out_host.data_ptr()),
                                              C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
                        "msclip_forward_loss(host)")
 
+        stage_host()
         for _ in range(3):
             step_host()
         e2e_steps = max(3, min(args.steps, 10))
         sec_h, _ = timed(step_host, e2e_steps)
         e2e = {"value": B * world * e2e_steps / sec_h, "unit": UNIT, "ms_per_step": sec_h / e2e_steps * 1e3,
                "h2d_bytes_per_step": int(img_host.numel() * 4 + tok_host.numel() * 8), "d2h_bytes_per_step": 12 if world == 1 else 8,
-               "steps": e2e_steps, "api": "msclip_forward_loss(host pointers)"}
+               "steps": e2e_steps, "api": "msclip_stage_images (prefetch of the next step) + msclip_forward_loss, pinned host pointers"}
         del img_host
 
     # ---- roofline of the dominant kernel: the shared-block fc1 GEMM (+bias+QuickGELU) at the text-tower M

@@ -8,6 +8,7 @@
  *   msclip_set_weight           <- model.load_state_dict(sd), one call per key    tools/zero_shot.py:223-224
  *   msclip_finalize_weights     <- model.to(device) / .eval()                     tools/zero_shot.py:225-228
  *   msclip_encode_image         <- CLIP.encode_image(image, norm)                 M.py:2979-2985
+ *   msclip_stage_images         <- images.cuda(non_blocking=True) (input prefetch)    tools/zero_shot.py:262
  *   msclip_encode_text          <- CLIP.encode_text(text, norm)                   M.py:3043-3079
  *   msclip_similarity_logits    <- logit_scale.exp() * I @ T.t()                  M.py:3136, 3141/3146; zero_shot.py:266
  *   msclip_forward              <- CLIP.forward(image, text) -> logits            M.py:3126-3155
@@ -73,6 +74,12 @@ int msclip_logit_scale_exp(msclip_handle h, float* out);
 /* image: [batch, 3, R, R] NCHW of `image_dtype`; out: [batch, embed_dim] f32. */
 int msclip_encode_image(msclip_handle h, const void* image, int image_dtype, int batch, float* out, int normalize,
                         void* stream);
+/* Input prefetch (the DataLoader's `.cuda(non_blocking=True)`, tools/zero_shot.py:262): start the host->device copy
+ * of a batch of images now, on a private copy stream.  A later msclip_encode_image / msclip_forward_loss call that
+ * is given the SAME host pointer and batch consumes the staged copy instead of transferring again, so the copy
+ * of step i+1 overlaps the compute of step i.  Two slots (double buffering); the host buffer must stay unchanged
+ * until it has been consumed. */
+int msclip_stage_images(msclip_handle h, const void* image_host, int image_dtype, int batch, void* stream);
 /* tokens: [batch, context_length] int64; out: [batch, embed_dim] f32.  Out-of-range ids are an error. */
 int msclip_encode_text(msclip_handle h, const int64_t* tokens, int batch, float* out, int normalize, void* stream);
 /* logits[n_img, n_txt] = scale * img_feat . txt_feat^T (f32 in, f32 out; split-bf16 tensor-core product). */

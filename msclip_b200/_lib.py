@@ -54,6 +54,7 @@ _SIGNATURES = {
     "msclip_finalize_weights": (_I, [_P, _P]),
     "msclip_logit_scale_exp": (_I, [_P, C.POINTER(_F)]),
     "msclip_encode_image": (_I, [_P, _P, _I, _I, _P, _I, _P]),
+    "msclip_stage_images": (_I, [_P, _P, _I, _I, _P]),
     "msclip_encode_text": (_I, [_P, _P, _I, _P, _I, _P]),
     "msclip_similarity_logits": (_I, [_P, _P, _I, _P, _I, _F, _P, _P]),
     "msclip_forward": (_I, [_P, _P, _I, _P, _I, _P, _P]),

@@ -125,6 +125,11 @@ int msclip_encode_image(msclip_handle h, const void* image, int image_dtype, int
   return engine_encode_image(h, image, image_dtype, batch, out, normalize, as_stream(stream));
 }
 
+int msclip_stage_images(msclip_handle h, const void* image_host, int image_dtype, int batch, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_stage_images(h, image_host, image_dtype, batch, as_stream(stream));
+}
+
 int msclip_encode_text(msclip_handle h, const int64_t* tokens, int batch, float* out, int normalize, void* stream) {
   MSCLIP_REQUIRE(h != nullptr, "null handle");
   return engine_encode_text(h, tokens, batch, out, normalize, as_stream(stream));

@@ -741,6 +741,62 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_d
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ input prefetch
+// Start the host->device copy of a batch of images now (on the private copy stream) so that a later
+// encode_image / forward_loss call on the SAME host pointer finds them resident: the transfer of step i+1
+// overlaps the compute of step i.  Two slots; the caller must not modify the host buffer until it is consumed.
+int engine_stage_images(msclip_ctx* h, const void* image_host, int dtype, int batch, cudaStream_t s) {
+  MSCLIP_REQUIRE(h != nullptr && image_host != nullptr && batch > 0, "stage_images: bad arguments");
+  MSCLIP_REQUIRE(dtype == MSCLIP_F32 || dtype == MSCLIP_BF16 || dtype == MSCLIP_F16, "stage_images: unsupported image dtype");
+  MSCLIP_REQUIRE(!is_device_pointer(image_host), "stage_images: expects a host pointer");
+  MSCLIP_TRY(ensure_streams(h));
+  const msclip_config& c = h->cfg;
+  const size_t bytes = static_cast<size_t>(batch) * 3 * c.image_resolution * c.image_resolution * (dtype == MSCLIP_F32 ? 4 : 2);
+  msclip_ctx::Staged& st = h->staged[h->stage_next];
+  h->stage_next ^= 1;
+  if (!st.ready) {
+    MSCLIP_CHECK_CUDA(cudaEventCreateWithFlags(&st.ready, cudaEventDisableTiming));
+    MSCLIP_CHECK_CUDA(cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming));
+  }
+  if (st.capacity < bytes) {
+    MSCLIP_CHECK_CUDA(cudaDeviceSynchronize());
+    if (st.dev) {
+      cudaFree(st.dev);
+      h->ws_bytes -= st.capacity;
+    }
+    st.dev = nullptr;
+    st.capacity = 0;
+    MSCLIP_CHECK_CUDA(cudaMalloc(&st.dev, bytes));
+    st.capacity = bytes;
+    h->ws_bytes += bytes;
+  } else {
+    // the slot's previous contents may still be read by kernels of an earlier step
+    MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, st.consumed, 0));
+  }
+  (void)s;
+  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(st.dev, image_host, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  MSCLIP_CHECK_CUDA(cudaEventRecord(st.ready, h->copy_stream));
+  st.host = image_host;
+  st.bytes = bytes;
+  st.pending = true;
+  st.seq = ++h->stage_seq;
+  return 0;
+}
+
+// If `image` was staged, make stream s wait for the copy and return the device copy (else nullptr).
+static const void* take_staged(msclip_ctx* h, const void* image, size_t bytes, cudaStream_t s, msclip_ctx::Staged** slot) {
+  msclip_ctx::Staged* best = nullptr;  // oldest pending copy of this buffer (FIFO)
+  for (int i = 0; i < 2; ++i) {
+    msclip_ctx::Staged& st = h->staged[i];
+    if (st.pending && st.host == image && st.bytes == bytes && (best == nullptr || st.seq < best->seq)) best = &st;
+  }
+  if (best == nullptr) return nullptr;
+  cudaStreamWaitEvent(s, best->ready, 0);
+  best->pending = false;
+  *slot = best;
+  return best->dev;
+}
+
 // ------------------------------------------------------------------------------------ public operations
 // parity of the exchange buffer the *next* loss call will read
 static int next_parity(const msclip_ctx* h) { return static_cast<int>((h->epoch + 1) & 1); }
@@ -756,7 +812,10 @@ int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, 
   const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
   const size_t img_bytes = static_cast<size_t>(batch) * 3 * c.image_resolution * c.image_resolution * esz;
   const void* img_dev = image;
-  if (!is_device_pointer(image)) {
+  msclip_ctx::Staged* slot = nullptr;
+  if (const void* pre = take_staged(h, image, img_bytes, s, &slot)) {
+    img_dev = pre;  // handed over earlier with msclip_stage_images
+  } else if (!is_device_pointer(image)) {
     // host input: stage on the copy stream so the transfer overlaps whatever the compute stream is doing
     WS(stage, uint8_t, "img_stage", img_bytes);
     MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_main, s));
@@ -778,6 +837,7 @@ int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, 
     if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 0);
   }
   MSCLIP_TRY(vision_tower(h, img_dev, dtype, batch, out_dev, normalize, fb, s));
+  if (slot) MSCLIP_CHECK_CUDA(cudaEventRecord(slot->consumed, s));
   h->last_img_batch = fb ? batch : -1;
   if (!out_dev_ptr) {
     MSCLIP_CHECK_CUDA(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(batch) * c.embed_dim * 4, cudaMemcpyDeviceToHost, s));
@@ -958,7 +1018,14 @@ int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64
   WS(ft, float, "fwd_txt", static_cast<size_t>(b_local) * E);
   // host images: start the (large) transfer first, run the text tower while it is in flight
   const void* img_dev = image;
-  if (!is_device_pointer(image)) {
+  bool prestaged = false;
+  {
+    const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
+    const size_t img_bytes = static_cast<size_t>(b_local) * 3 * c.image_resolution * c.image_resolution * esz;
+    for (int i = 0; i < 2; ++i)
+      prestaged |= h->staged[i].pending && h->staged[i].host == image && h->staged[i].bytes == img_bytes;
+  }
+  if (!prestaged && !is_device_pointer(image)) {
     const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
     const size_t img_bytes = static_cast<size_t>(b_local) * 3 * c.image_resolution * c.image_resolution * esz;
     WS(stage, uint8_t, "img_stage", img_bytes);
@@ -983,6 +1050,11 @@ msclip_ctx::~msclip_ctx() {
   for (auto& kv : ws) cudaFree(kv.second.p);
   for (int r = 0; r < static_cast<int>(peer_base.size()); ++r)
     if (r != rank && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
+  for (auto& st : staged) {
+    if (st.dev) cudaFree(st.dev);
+    if (st.ready) cudaEventDestroy(st.ready);
+    if (st.consumed) cudaEventDestroy(st.consumed);
+  }
   if (xchg) cudaFree(xchg);
   if (shard_tables) cudaFree(shard_tables);
   if (copy_stream) cudaStreamDestroy(copy_stream);

@@ -72,6 +72,17 @@ struct msclip_ctx {
   size_t ws_bytes = 0;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr, ev_main = nullptr;
+  // images handed over early with msclip_stage_images (input prefetch, double buffered)
+  struct Staged {
+    const void* host = nullptr;
+    void* dev = nullptr;
+    size_t bytes = 0, capacity = 0;
+    cudaEvent_t ready = nullptr, consumed = nullptr;
+    bool pending = false;
+    uint64_t seq = 0;
+  } staged[2];
+  int stage_next = 0;
+  uint64_t stage_seq = 0;
 
   // embedding exchange (data-parallel contrastive loss)
   int rank = 0, world = 1, max_b_local = 0;
@@ -102,6 +113,7 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
                             cudaStream_t stream);
 int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,
                         float* partial_out, float* loss_out, cudaStream_t stream);
+int engine_stage_images(msclip_ctx* h, const void* image_host, int dtype, int batch, cudaStream_t stream);
 int comm_init(msclip_ctx* h, int rank, int world, int max_b_local);
 int comm_export(msclip_ctx* h, void* handle_out);
 int comm_import(msclip_ctx* h, const void* handles);

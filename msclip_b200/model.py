@@ -168,6 +168,17 @@ class CLIP(nn.Module):
                                                   self._stream()), "msclip_encode_image")
         return out
 
+    def prefetch_images(self, image: torch.Tensor) -> None:
+        """Start the host->device copy of a (pinned) CPU image batch now; the next encode_image / contrastive_loss
+        call on the same tensor consumes it (tools/zero_shot.py:262 does `.cuda(non_blocking=True)`)."""
+        if image.is_cuda:
+            return
+        if image.dtype not in _IMAGE_DTYPES or not image.is_contiguous():
+            raise ValueError("prefetch_images needs a contiguous float32 / bfloat16 / float16 CPU tensor")
+        self._sync_weights()
+        self._check(self._library().msclip_stage_images(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+                                                       image.shape[0], self._stream()), "msclip_stage_images")
+
     @torch.no_grad()
     def encode_text(self, text: torch.Tensor, norm: bool = True, action=None) -> torch.Tensor:
         if action is not None:

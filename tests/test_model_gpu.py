@@ -234,3 +234,22 @@ def test_get_clip_model_accepts_reference_config():
     model = get_clip_model(config).cuda().eval()
     out = model.encode_image(torch.randn(2, 3, 224, 224).cuda())
     assert out.shape == (2, 512) and torch.allclose(out.norm(dim=-1), torch.ones(2, device="cuda"), atol=1e-5)
+
+
+def test_prefetched_images_equal_direct_transfer():
+    """msclip_stage_images (input prefetch, double buffered, FIFO) feeds the same bits as a direct host call."""
+    cfg, sd_np, img, tok, z, meta = load_case("b32_l2_b8")
+    model = build_model(cfg, sd_np)
+    a = torch.from_numpy(img).pin_memory()
+    b = torch.from_numpy(img[::-1].copy()).pin_memory()
+    ref_a, ref_b = model.encode_image(a.cuda()).cpu(), model.encode_image(b.cuda()).cpu()
+    model.prefetch_images(a)
+    model.prefetch_images(b)                       # two slots in flight
+    assert torch.equal(model.encode_image(a), ref_a)
+    model.prefetch_images(a)                       # slot of `a` is reused while `b` is still pending
+    assert torch.equal(model.encode_image(b), ref_b)
+    assert torch.equal(model.encode_image(a), ref_a)
+    ttok = torch.from_numpy(tok).pin_memory()
+    l_direct = float(model.contrastive_loss(a, ttok))
+    model.prefetch_images(a)
+    assert float(model.contrastive_loss(a, ttok)) == l_direct
