@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: the zero-shot IN-1K evaluation path at full size on synthetic data -
+encode_text over 1000 classes x 80 templates (tools/zero_shot.py:122-134), class-mean + renormalise,
+encode_image of a 1024 batch, 100 * I @ W (tools/zero_shot.py:265-266), top-1.
+
+Two ways of building the classifier are timed: the reference's loop (1000 sequential batch-80 calls) and one
+batched call over all 80 000 prompts; both must give the same weights.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np                               # noqa: E402
+import torch                                     # noqa: E402
+from msclip_b200 import synth                    # noqa: E402
+from msclip_b200.config import MSCLIPConfig      # noqa: E402
+from msclip_b200.model import CLIP               # noqa: E402
+
+
+def main():
+    n_cls, n_tpl, n_img = 1000, 80, 1024
+    cfg = MSCLIPConfig()
+    sd = synth.synth_state_dict(cfg, seed=0)
+    model = CLIP(cfg)
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    model = model.cuda().eval()
+    toks = torch.from_numpy(synth.synth_tokens(n_cls * n_tpl, 7, ragged=True)).cuda()      # [80000, 77]
+    img = torch.randn(n_img, 3, 224, 224, device="cuda")
+    model.encode_text(toks[:80])
+    torch.cuda.synchronize()
+
+    t0 = time.perf_counter()
+    ws = []
+    for c in range(n_cls):                                    # the reference's loop, tools/zero_shot.py:125-131
+        e = model.encode_text(toks[c * n_tpl:(c + 1) * n_tpl]).mean(dim=0)
+        ws.append(e / e.norm())
+    w_loop = torch.stack(ws, dim=0)
+    torch.cuda.synchronize()
+    t_loop = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    e = model.encode_text(toks).view(n_cls, n_tpl, -1).mean(dim=1)
+    w_batched = e / e.norm(dim=-1, keepdim=True)
+    torch.cuda.synchronize()
+    t_batched = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    feats = model.encode_image(img)
+    logits = model.similarity_logits(feats, w_batched, 100.0)
+    top1 = logits.argmax(dim=1)
+    torch.cuda.synchronize()
+    t_img = time.perf_counter() - t0
+    out = {"classifier_loop_s": t_loop, "classifier_batched_s": t_batched, "prompts_per_s_loop": n_cls * n_tpl / t_loop,
+           "prompts_per_s_batched": n_cls * n_tpl / t_batched, "image_batch_s": t_img, "images_per_s": n_img / t_img,
+           "max_abs_diff_loop_vs_batched": float((w_loop - w_batched).abs().max()),
+           "logits_shape": list(logits.shape), "top1_agree_loop_vs_batched":
+               float((model.similarity_logits(feats, w_loop, 100.0).argmax(dim=1) == top1).float().mean())}
+    print(json.dumps(out))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "zeroshot_bench.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
