@@ -37,47 +37,15 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// scores, softmax and P.V for the 16 query rows of this warp; Q/K/V head slices are in shared memory
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
-__global__ void __launch_bounds__(QPAD * 2)
-attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, int heads) {
-  constexpr int KVPAD = KC * NCHUNK;
+__device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk, const op16* sv, op16* out_base, int L,
+                                                  int width) {
   constexpr int NT = KC / 8;  // score n-tiles per chunk
-  static_assert(QPAD % 16 == 0 && KC % 16 == 0 && KVPAD >= QPAD, "tile shapes");
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  op16* sq = reinterpret_cast<op16*>(att_smem);
-  op16* sk = sq + QPAD * kLds;
-  op16* sv = sk + KVPAD * kLds;
-
-  const int b = blockIdx.x / heads;
-  const int h = blockIdx.x % heads;
-  const int width = heads * kHeadDim;
-  const long long pitch = 3ll * width;
-  const op16* base = qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim;
-
-  // stage Q, K, V head slices (rows >= L are zero)
-  for (int i = threadIdx.x; i < (QPAD + 2 * KVPAD) * 8; i += blockDim.x) {
-    const int c = i & 7;
-    int row = i >> 3;
-    int which = 0;
-    if (row >= QPAD) {
-      row -= QPAD;
-      which = 1;
-      if (row >= KVPAD) {
-        row -= KVPAD;
-        which = 2;
-      }
-    }
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < L) v = *reinterpret_cast<const uint4*>(base + row * pitch + which * width + c * 8);
-    op16* dst = which == 0 ? sq : (which == 1 ? sk : sv);
-    *reinterpret_cast<uint4*>(dst + row * kLds + c * 8) = v;
-  }
-  __syncthreads();
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m0 = warp * 16;
-  if (m0 >= L) return;
+  if (m0 >= L) return;  // this warp has no query rows (it still took part in the staging)
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, r8 = lane & 7;
 
@@ -143,7 +111,7 @@ attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, in
       mnew[hh] = fmaxf(m_run[hh], mx[hh]);
       // rows of the padding region may be fully masked in a chunk: keep the maths finite
       const float msafe = (mnew[hh] == -INFINITY) ? 0.f : mnew[hh];
-      alpha[hh] = exp2f((m_run[hh] - msafe) * kLog2e);
+      alpha[hh] = fast_ex2((m_run[hh] - msafe) * kLog2e);
       m_run[hh] = mnew[hh];
       mnew[hh] = msafe;
     }
@@ -152,7 +120,7 @@ attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, in
     for (int j = 0; j < NT; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f((s[j][e] - mnew[e >> 1]) * kLog2e);
+        const float pv = fast_ex2(fmaf(s[j][e], kLog2e, -mnew[e >> 1] * kLog2e));  // one FFMA + MUFU.EX2
         s[j][e] = pv;
         ls[e >> 1] += pv;
       }
@@ -193,7 +161,7 @@ attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, in
     l_run[hh] += __shfl_xor_sync(0xffffffffu, l_run[hh], 2);
   }
   const float inv_lo = 1.0f / l_run[0], inv_hi = 1.0f / l_run[1];
-  op16* obase = out + static_cast<long long>(b) * L * width + h * kHeadDim;
+  op16* obase = out_base;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = 8 * j + 2 * t;
@@ -204,6 +172,115 @@ attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, in
       *reinterpret_cast<uint32_t*>(obase + static_cast<long long>(row_hi) * width + col) =
           pack16(o[j][2] * inv_hi, o[j][3] * inv_hi);
   }
+}
+
+template <int QPAD, int KVPAD>
+__device__ __forceinline__ void stage_item(const op16* __restrict__ base, long long pitch, int width, int L, op16* sq,
+                                           op16* sk, op16* sv, bool async) {
+  // stage the Q, K, V head slices of one (batch, head) item; rows >= L are zero
+  for (int i = threadIdx.x; i < (QPAD + 2 * KVPAD) * 8; i += blockDim.x) {
+    const int c = i & 7;
+    int row = i >> 3;
+    int which = 0;
+    if (row >= QPAD) {
+      row -= QPAD;
+      which = 1;
+      if (row >= KVPAD) {
+        row -= KVPAD;
+        which = 2;
+      }
+    }
+    op16* dst = (which == 0 ? sq : (which == 1 ? sk : sv)) + row * kLds + c * 8;
+    const op16* src = base + row * pitch + which * width + c * 8;
+    if (async) {
+      const bool ok = row < L;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(ok ? src : base),
+                   "r"(ok ? 16u : 0u)
+                   : "memory");
+    } else {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (row < L) v = *reinterpret_cast<const uint4*>(src);
+      *reinterpret_cast<uint4*>(dst) = v;
+    }
+  }
+}
+
+// one CTA per (batch, head): used for L = 197, where two staging buffers would not fit next to each other
+template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
+__global__ void __launch_bounds__(QPAD * 2)
+attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, int heads) {
+  constexpr int KVPAD = KC * NCHUNK;
+  static_assert(QPAD % 16 == 0 && KC % 16 == 0 && KVPAD >= QPAD, "tile shapes");
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  op16* sq = reinterpret_cast<op16*>(att_smem);
+  op16* sk = sq + QPAD * kLds;
+  op16* sv = sk + KVPAD * kLds;
+  const int b = blockIdx.x / heads;
+  const int h = blockIdx.x % heads;
+  const int width = heads * kHeadDim;
+  const long long pitch = 3ll * width;
+  stage_item<QPAD, KVPAD>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, sq, sk, sv, false);
+  __syncthreads();
+  attention_compute<QPAD, KC, NCHUNK, CAUSAL>(sq, sk, sv, out + static_cast<long long>(b) * L * width + h * kHeadDim, L, width);
+}
+
+// persistent variant for the short sequences (L <= 80): every CTA walks over (batch, head) items and prefetches
+// the next item's Q/K/V with cp.async into the second staging buffer while the current item is computed, so the
+// HBM stream never waits for the tensor-core / softmax phase
+template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
+__global__ void __launch_bounds__(QPAD * 2)
+attention_persistent_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, int heads, int items) {
+  constexpr int KVPAD = KC * NCHUNK;
+  constexpr int kBuf = (QPAD + 2 * KVPAD) * kLds;
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  op16* buf = reinterpret_cast<op16*>(att_smem);
+  const int width = heads * kHeadDim;
+  const long long pitch = 3ll * width;
+  int item = blockIdx.x;
+  if (item >= items) return;
+  {
+    const int b = item / heads, h = item % heads;
+    stage_item<QPAD, KVPAD>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, buf, buf + QPAD * kLds,
+                            buf + (QPAD + KVPAD) * kLds, true);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int it = 0; item < items; item += gridDim.x, ++it) {
+    op16* cur = buf + (it & 1) * kBuf;
+    op16* nxt = buf + ((it + 1) & 1) * kBuf;
+    const int next_item = item + gridDim.x;
+    if (next_item < items) {
+      const int b = next_item / heads, h = next_item % heads;
+      stage_item<QPAD, KVPAD>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, nxt,
+                              nxt + QPAD * kLds, nxt + (QPAD + KVPAD) * kLds, true);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the prefetch just issued has landed
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int b = item / heads, h = item % heads;
+    attention_compute<QPAD, KC, NCHUNK, CAUSAL>(cur, cur + QPAD * kLds, cur + (QPAD + KVPAD) * kLds,
+                                                 out + static_cast<long long>(b) * L * width + h * kHeadDim, L, width);
+    __syncthreads();  // all warps are done with `cur` before the next iteration prefetches into it
+  }
+}
+
+template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
+int launch_persistent(const op16* qkv, op16* out, int batch, int L, int heads, cudaStream_t stream) {
+  constexpr int smem = 2 * (QPAD + 2 * KC * NCHUNK) * kLds * 2;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(attention_persistent_kernel<QPAD, KC, NCHUNK, CAUSAL>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MSCLIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &ctas_per_sm, attention_persistent_kernel<QPAD, KC, NCHUNK, CAUSAL>, QPAD * 2, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const int items = batch * heads;
+  const int grid = items < num_sms() * ctas_per_sm ? items : num_sms() * ctas_per_sm;
+  attention_persistent_kernel<QPAD, KC, NCHUNK, CAUSAL><<<grid, QPAD * 2, smem, stream>>>(qkv, out, L, heads, items);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
@@ -227,11 +304,11 @@ int launch_attention(const op16* qkv, op16* out, int batch, int L, int heads, in
   MSCLIP_REQUIRE(L >= 1 && L <= 208, "attention: sequence length must be in [1, 208]");
   MSCLIP_REQUIRE(heads >= 1, "attention: heads must be positive");
   if (L <= 64)
-    return causal ? launch_variant<64, 64, 1, true>(qkv, out, batch, L, heads, stream)
-                  : launch_variant<64, 64, 1, false>(qkv, out, batch, L, heads, stream);
+    return causal ? launch_persistent<64, 64, 1, true>(qkv, out, batch, L, heads, stream)
+                  : launch_persistent<64, 64, 1, false>(qkv, out, batch, L, heads, stream);
   if (L <= 80)
-    return causal ? launch_variant<80, 80, 1, true>(qkv, out, batch, L, heads, stream)
-                  : launch_variant<80, 80, 1, false>(qkv, out, batch, L, heads, stream);
+    return causal ? launch_persistent<80, 80, 1, true>(qkv, out, batch, L, heads, stream)
+                  : launch_persistent<80, 80, 1, false>(qkv, out, batch, L, heads, stream);
   return causal ? launch_variant<208, 112, 2, true>(qkv, out, batch, L, heads, stream)
                 : launch_variant<208, 112, 2, false>(qkv, out, batch, L, heads, stream);
 }
