@@ -253,3 +253,37 @@ def test_prefetched_images_equal_direct_transfer():
     l_direct = float(model.contrastive_loss(a, ttok))
     model.prefetch_images(a)
     assert float(model.contrastive_loss(a, ttok)) == l_direct
+
+
+def test_internal_chunk_boundaries():
+    """Batches that cross the library's internal chunking (1024 images per conv pass, 4096 sequences per tower
+    pass) give the same embeddings as the same samples encoded in small batches (bit-exact: every kernel is
+    batch-independent and deterministic)."""
+    cfg = MSCLIPConfig(layers=3)
+    model = build_model(cfg, synth.synth_state_dict(cfg, seed=6))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.randn(1030, 3, 224, 224, device="cuda", generator=g)
+    big = model.encode_image(img)
+    idx = [0, 511, 1023, 1024, 1029]
+    small = torch.cat([model.encode_image(img[i:i + 1]) for i in idx])
+    assert torch.equal(big[idx], small)
+    tok = torch.from_numpy(synth.synth_tokens(4100, 5, ragged=True)).cuda()
+    tbig = model.encode_text(tok)
+    tidx = [0, 4095, 4096, 4099]
+    tsmall = torch.cat([model.encode_text(tok[i:i + 1]) for i in tidx])
+    assert torch.equal(tbig[tidx], tsmall)
+    assert torch.isfinite(big).all() and torch.isfinite(tbig).all()
+
+
+def test_loss_matches_logits_path_at_odd_batch_sizes():
+    """Fused loss kernel vs cross-entropy of the materialised logits for batches that are not multiples of the
+    128-row / 128-column tiles (1, 3, 129, 257)."""
+    cfg = MSCLIPConfig(layers=2)
+    sd_np = synth.synth_state_dict(cfg, seed=8, logit_scale=math.log(20.0))
+    model = build_model(cfg, sd_np)
+    for b in (1, 3, 129, 257):
+        img = torch.from_numpy(synth.synth_images(b, 40 + b)).cuda()
+        tok = torch.from_numpy(synth.synth_tokens(b, 40 + b, ragged=True)).cuda()
+        fused = float(model.contrastive_loss(img, tok))
+        ref = loss_of(model(img, tok).cpu())
+        assert abs(fused - ref) <= 1e-3 * abs(ref) + 2e-4, (b, fused, ref)
