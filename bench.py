@@ -255,9 +255,41 @@ def run_ours(args, cfg, rank, world, local):
             step_host()
         e2e_steps = max(3, min(args.steps, 10))
         sec_h, _ = timed(step_host, e2e_steps)
+        loss_f32_host = float(out_host[2])
+        odt_img = _lib.torch_operand_dtype(args.precision)
         e2e = {"value": B * world * e2e_steps / sec_h, "unit": UNIT, "ms_per_step": sec_h / e2e_steps * 1e3,
                "h2d_bytes_per_step": int(img_host.numel() * 4 + tok_host.numel() * 8), "d2h_bytes_per_step": 12 if world == 1 else 8,
-               "steps": e2e_steps, "api": "msclip_stage_images (prefetch of the next step) + msclip_forward_loss, pinned host pointers"}
+               "steps": e2e_steps, "api": "msclip_stage_images (prefetch of the next step) + msclip_forward_loss, pinned host pointers",
+               "host_image_dtype": "f32"}
+        # what bounds it: the raw pinned host->device rate of this box
+        cp0, cp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cp0.record(stream)
+        img_dev.copy_(img_host, non_blocking=True)
+        cp1.record(stream)
+        torch.cuda.synchronize()
+        e2e["h2d_gb_per_s_measured"] = img_host.numel() * 4 / (cp0.elapsed_time(cp1) / 1e3) / 1e9
+        # secondary: the same call with the images already in the 16-bit operand type on the host (the reference
+        # casts with image.type(self.dtype) before the first conv, M.py:2980; the first kernel rounds fp32 pixels
+        # to this type anyway, so the result is bit-identical) - half the PCIe bytes
+        img_host16 = torch.empty(img_dev.shape, dtype=odt_img).pin_memory()
+        img_host16.copy_(img_dev)
+        code16 = _lib.F16 if args.precision == "fp16" else _lib.BF16
+
+        def step_host16():
+            _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host16.data_ptr()), code16, B, sp), "msclip_stage_images")
+            _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_host16.data_ptr()), code16, C.c_void_p(tok_host.data_ptr()), B,
+                                             C.c_void_p(out_host.data_ptr()),
+                                             C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
+                       "msclip_forward_loss(host, 16-bit images)")
+
+        _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host16.data_ptr()), code16, B, sp), "msclip_stage_images")
+        for _ in range(3):
+            step_host16()
+        sec_h16, _ = timed(step_host16, e2e_steps)
+        e2e["with_16bit_host_images"] = {"value": B * world * e2e_steps / sec_h16, "ms_per_step": sec_h16 / e2e_steps * 1e3,
+                                         "h2d_bytes_per_step": int(img_host16.numel() * 2 + tok_host.numel() * 8),
+                                         "loss_bit_identical_to_f32_images": bool(float(out_host[2]) == loss_f32_host) if world == 1 else None}
+        del img_host16
         del img_host
 
     # ---- roofline of the dominant kernel: the shared-block fc1 GEMM (+bias+QuickGELU) at the text-tower M

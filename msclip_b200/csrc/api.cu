@@ -186,7 +186,7 @@ int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m
 void msclip_op_set_gemm_pair_mode(int enable) { gemm_set_pair_mode(enable); }
 int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
                         void* stream) {
-  return launch_layernorm_bf16(x, row_stride, w, b, static_cast<op16*>(y_bf16), rows, as_stream(stream));
+  return launch_layernorm_op16(x, row_stride, w, b, static_cast<op16*>(y_bf16), rows, as_stream(stream));
 }
 int msclip_op_attention(const void* qkv_bf16, void* out_bf16, int batch, int seq_len, int heads, int causal,
                         void* stream) {

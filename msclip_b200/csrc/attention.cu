@@ -29,7 +29,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32." MSCLIP_MMA_OPERANDS ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
       "{%0, %1, %2, %3};"
@@ -85,8 +85,8 @@ __device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk
         for (int kk = 0; kk < 4; ++kk) {
           uint32_t kf[4];
           ldmatrix_x4(kf, smem_u32(sk + (kv0 + 16 * jp + r8 + 8 * (mi >> 1)) * kLds + kk * 16 + 8 * (mi & 1)));
-          mma_bf16_16816(s[2 * jp], qf[kk], kf[0], kf[1]);
-          mma_bf16_16816(s[2 * jp + 1], qf[kk], kf[2], kf[3]);
+          mma_16816(s[2 * jp], qf[kk], kf[0], kf[1]);
+          mma_16816(s[2 * jp + 1], qf[kk], kf[2], kf[3]);
         }
       }
     }
@@ -147,8 +147,8 @@ __device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t vf[4];
           ldmatrix_x4_trans(vf, smem_u32(sv + (kv0 + 16 * kk2 + r8 + 8 * (mi & 1)) * kLds + 16 * dp + 8 * (mi >> 1)));
-          mma_bf16_16816(o[2 * dp], pa, vf[0], vf[1]);
-          mma_bf16_16816(o[2 * dp + 1], pa, vf[2], vf[3]);
+          mma_16816(o[2 * dp], pa, vf[0], vf[1]);
+          mma_16816(o[2 * dp + 1], pa, vf[2], vf[3]);
         }
       }
     }

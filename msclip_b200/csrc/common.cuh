@@ -217,7 +217,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // 2-CTA MMA (M = 256 across the pair), issued by the leader CTA only
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -264,7 +264,7 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16/op16 operands with fp32 accumulate.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -322,7 +322,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // Instruction descriptor for kind::f16: D=fp32 (bits 4-5 = 1), A=B=op16 (bits 7-9, 10-12 = 1),
 // both operands K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int m, int n) {
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc(int m, int n) {
   return (1u << 4) | (kUmmaOperandFormat << 7) | (kUmmaOperandFormat << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
@@ -330,7 +330,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int m, int n) {
 // ------------------------------------------------------------------------------------ host: TMA maps
 // rows x cols op16 row-major (pitch ld elements), box = box_rows x 64 columns, 128-B swizzle,
 // out-of-bounds elements read as zero.
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+int make_tmap_op16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);
 
 }  // namespace msclip

@@ -198,7 +198,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, BN);
+      constexpr uint32_t idesc = umma_idesc_f32acc(kBM, BN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -214,7 +214,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
           const uint32_t b_addr = a_addr + Cfg::kStageA;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[s]);
           if (++s == Cfg::kStages) {
@@ -337,7 +337,7 @@ int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo,
   const bool vec_ok = ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                       (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   CUtensorMap tb;
-  MSCLIP_TRY(make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+  MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
                                static_cast<uint32_t>(bn)));
   const long long M = static_cast<long long>(batch) * Ho * Wo;
   MSCLIP_REQUIRE(M < (1ll << 31), "conv_gemm: too many output pixels for one launch");

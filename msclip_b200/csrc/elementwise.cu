@@ -63,7 +63,7 @@ __device__ __forceinline__ void store_row_f32(float* __restrict__ dst, int lane,
 }
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
-layernorm_bf16_kernel(const float* __restrict__ x, int row_stride, const float* __restrict__ w,
+layernorm_kernel(const float* __restrict__ x, int row_stride, const float* __restrict__ w,
                       const float* __restrict__ b, op16* __restrict__ y, int rows) {
   const int lane = threadIdx.x & 31;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
@@ -77,7 +77,7 @@ layernorm_bf16_kernel(const float* __restrict__ x, int row_stride, const float* 
 }
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
-eot_layernorm_bf16_kernel(const float* __restrict__ x, const int64_t* __restrict__ tok, int L,
+eot_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ tok, int L,
                           const float* __restrict__ w, const float* __restrict__ b, op16* __restrict__ y, int batch) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
@@ -254,18 +254,18 @@ inline int row_grid(long long rows) {
 
 }  // namespace
 
-int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
+int launch_layernorm_op16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
                           cudaStream_t stream) {
   if (rows <= 0) return 0;
-  layernorm_bf16_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, row_stride, w, b, y, rows);
+  layernorm_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, row_stride, w, b, y, rows);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_eot_layernorm_bf16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
+int launch_eot_layernorm_op16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
                               int batch, cudaStream_t stream) {
   if (batch <= 0) return 0;
-  eot_layernorm_bf16_kernel<<<(batch + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(
+  eot_layernorm_kernel<<<(batch + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(
       x, tok, L, w, b, y, batch);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -514,11 +514,11 @@ static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch,
                      op16* qkv, op16* attn, op16* fc1, cudaStream_t s) {
   const int w = h->cfg.width;
   const int M = batch * L;
-  MSCLIP_TRY(launch_layernorm_bf16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
+  MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
   MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, qkv, 3 * w, nullptr, 0, EPI_BF16, s));
   MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
   MSCLIP_TRY(launch_gemm(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, x, w, EPI_RESID_F32, s));
-  MSCLIP_TRY(launch_layernorm_bf16(x, 1, bw.ln2_w, bw.ln2_b, hbuf, M, s));
+  MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln2_w, bw.ln2_b, hbuf, M, s));
   MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
   MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, x, w, EPI_RESID_F32, s));
   count_launch(7);
@@ -700,7 +700,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
       MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, s));
     }
     // CLS -> ln_post -> proj -> L2 norm (M.py:2685-2690, 2982-2983)
-    MSCLIP_TRY(launch_layernorm_bf16(xc, L, h->ln_post_w, h->ln_post_b, pool_ln, nb, s));
+    MSCLIP_TRY(launch_layernorm_op16(xc, L, h->ln_post_w, h->ln_post_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->vproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));
     MSCLIP_TRY(launch_l2norm(feat_raw, out_dev + static_cast<size_t>(b0) * c.embed_dim,
@@ -730,7 +730,7 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_d
     MSCLIP_TRY(launch_text_embed(tk, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, s));
     count_launch(1);
     for (int idx = 0; idx < c.layers; ++idx) MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, s));
-    MSCLIP_TRY(launch_eot_layernorm_bf16(x, tk, L, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
+    MSCLIP_TRY(launch_eot_layernorm_op16(x, tk, L, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->tproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));
     MSCLIP_TRY(launch_l2norm(feat_raw, out_dev + static_cast<size_t>(b0) * c.embed_dim,
@@ -881,7 +881,7 @@ int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* o
 // split-op16 operands: [hi | hi | lo] . [hi | lo | hi]^T = hi.hi + hi.lo + lo.hi  (fp32-grade similarity
 // on the op16 tensor cores; the lo.lo term is below fp32 rounding)
 __global__ void __launch_bounds__(256)
-split_bf16_kernel(const float* __restrict__ x, op16* __restrict__ out, long long rows, int E, int role) {
+split_hi_lo_kernel(const float* __restrict__ x, op16* __restrict__ out, long long rows, int E, int role) {
   const long long total = rows * E;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
     const long long r = i / E;
@@ -925,8 +925,8 @@ int engine_similarity_logits(msclip_ctx* h, const float* img, int n_img, const f
     long long blocks = (total + 255) / 256;
     return static_cast<int>(std::min<long long>(blocks, 148 * 32));
   };
-  split_bf16_kernel<<<grid_for(static_cast<long long>(n_img) * E), 256, 0, s>>>(a, a3, n_img, E, 0);
-  split_bf16_kernel<<<grid_for(static_cast<long long>(n_txt) * E), 256, 0, s>>>(b, b3, n_txt, E, 1);
+  split_hi_lo_kernel<<<grid_for(static_cast<long long>(n_img) * E), 256, 0, s>>>(a, a3, n_img, E, 0);
+  split_hi_lo_kernel<<<grid_for(static_cast<long long>(n_txt) * E), 256, 0, s>>>(b, b3, n_txt, E, 1);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   MSCLIP_TRY(launch_gemm_scaled(a3, 3 * E, b3, 3 * E, n_img, n_txt, 3 * E, scale, nullptr, o, n_txt, nullptr, 0, EPI_F32, s));
   count_launch(3);

@@ -140,7 +140,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM * CG, BN);
+      constexpr uint32_t idesc = umma_idesc_f32acc(kBM * CG, BN);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -157,8 +157,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * 32), db = umma_desc_sw128(b_addr + k * 32);
-            if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_f16_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs) once these MMAs have read it
           if (CG == 2) umma_commit_pair(&empty_bar[s], static_cast<uint16_t>((1u << (2 * NP)) - 1u));
@@ -319,9 +319,9 @@ int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, i
   int np = 1;
   if (cg == 2 && g_pair_mode >= 2) np = (g_pair_mode == 4 && M >= 4096) ? 4 : (M >= 1024 ? 2 : 1);
   CUtensorMap ta, tb;
-  MSCLIP_TRY(make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
+  MSCLIP_TRY(make_tmap_op16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda),
                                kBM));
-  MSCLIP_TRY(make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+  MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
                                static_cast<uint32_t>(bn / cg / np)));
   GemmParams p;
   p.M = M;

@@ -64,10 +64,10 @@ int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, i
 
 // ---- LayerNorm family, D = 768 (elementwise.cu) ----------------------------------------------
 // y[r] = LN(x[r * row_stride]) ; out op16 (GEMM operand).  row_stride = L picks the CLS rows.
-int launch_layernorm_bf16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
+int launch_layernorm_op16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
                           cudaStream_t stream);
 // text pooling: row b <- LN(x[b*L + argmax_j tok[b,j]])  (M.py:3057-3060, 3072)
-int launch_eot_layernorm_bf16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
+int launch_eot_layernorm_op16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
                               int batch, cudaStream_t stream);
 // x[b*L+l] = tok_emb[tok[b,l]] + pos[l]   (M.py:3047-3048)
 int launch_text_embed(const int64_t* tok, const float* tok_emb, const float* pos, float* x, int batch, int L,
@@ -118,10 +118,6 @@ int launch_contrastive_loss_ex(const op16* img_local, const op16* txt_local, con
                                int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
                                cudaStream_t stream);
 size_t contrastive_loss_workspace_bytes(int world, int b_local);
-// plain logits (eval path / parity): out[i,j] = scale * <a_i, b_j>, f32 [Ma, Mb]
-int launch_similarity_logits(const op16* a, const op16* b, int Ma, int Mb, int E, float scale, float* out,
-                             cudaStream_t stream);
-
 // ---- weight packing (pack.cu) -------------------------------------------------------------------
 // dst[n, k] (op16, pitch ldd) = src[n*sn + k*sk] * (row_scale ? row_scale[n] : 1)
 int launch_pack_op16(const float* src, int64_t sn, int64_t sk, const float* row_scale, op16* dst, int64_t ldd, int N,

@@ -135,7 +135,7 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kLossBN);
+      constexpr uint32_t idesc = umma_idesc_f32acc(128, kLossBN);
       const uint32_t b_base = smem_u32(sB);
       int s = 0;
       uint32_t ph = 0;
@@ -152,7 +152,7 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
           const uint32_t b_addr = b_base + kb * (kLossBN * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[s]);
           if (++s == kLossStages) {
@@ -294,8 +294,8 @@ int launch_contrastive_loss_ex(const op16* img_local, const op16* txt_local, con
   p.diag = reinterpret_cast<float*>(p.ws + 2ll * p.n_col_tiles * p.b_pad);
   float* row_loss = p.diag + 2 * p.b_pad;
   CUtensorMap ti, tt;
-  MSCLIP_TRY(make_tmap_bf16_2d(&ti, img_local, b_local, kLossE, kLossE, 128));
-  MSCLIP_TRY(make_tmap_bf16_2d(&tt, txt_local, b_local, kLossE, kLossE, 128));
+  MSCLIP_TRY(make_tmap_op16_2d(&ti, img_local, b_local, kLossE, kLossE, 128));
+  MSCLIP_TRY(make_tmap_op16_2d(&tt, txt_local, b_local, kLossE, kLossE, 128));
   contrastive_lse_kernel<<<dim3(p.n_col_tiles, 2), kLossThreads, kLossSmem, stream>>>(ti, tt, p);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   lse_combine_kernel<<<(2 * b_local + 255) / 256, 256, 0, stream>>>(p.ws, p.diag, b_local, p.b_pad, p.n_col_tiles,
@@ -304,11 +304,6 @@ int launch_contrastive_loss_ex(const op16* img_local, const op16* txt_local, con
   loss_reduce_kernel<<<2, 1024, 0, stream>>>(row_loss, b_local, loss_parts);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
-}
-
-int launch_similarity_logits(const op16* a, const op16* b, int Ma, int Mb, int E, float scale, float* out,
-                             cudaStream_t stream) {
-  return launch_gemm_scaled(a, E, b, E, Ma, Mb, E, scale, nullptr, out, Mb, nullptr, 0, EPI_F32, stream);
 }
 
 }  // namespace msclip
