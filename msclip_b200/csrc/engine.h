@@ -121,5 +121,6 @@ int comm_import(msclip_ctx* h, const void* handles);
 int64_t launch_count();
 void count_launch(int n);
 bool is_device_pointer(const void* p);
+const void* pinned_device_alias(const void* p);
 
 }  // namespace msclip
