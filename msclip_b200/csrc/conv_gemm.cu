@@ -357,6 +357,7 @@ int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo,
   p.ldr = 0;
   p.alpha = 1.0f;
   p.vec_ok = vec_ok ? 1 : 0;
+  p.split_stride = 0;
   switch (bn) {
     case 192: return launch_conv_bn<192>(tb, cp, epi, stream);
     case 128: return launch_conv_bn<128>(tb, cp, epi, stream);

@@ -596,15 +596,18 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   for (int b0 = 0; b0 < batch; b0 += kConvChunk) {
     const int nb = std::min(kConvChunk, batch - b0);
     const uint8_t* img_c = static_cast<const uint8_t*>(img) + static_cast<size_t>(b0) * 3 * R * R * esz;
-    // first convs (stem conv1+bn1+ReLU, M.py:1993 | branch stage 0, M.py:2260-2273): one GEMM, N = 48 + 48
+    // first convs (stem conv1+bn1+ReLU, M.py:1993 | branch stage 0, M.py:2260-2273): one GEMM, N = 48 + 48, whose
+    // two column tiles land in two dense NHWC tensors (consumers of one half never touch the other half's bytes)
     MSCLIP_TRY(launch_im2col_first(img_c, dtype, col0, nb, R, R, s));
-    MSCLIP_TRY(launch_gemm(col0, 32, h->first.w, 32, static_cast<int>(nb * px1), 2 * c0, 32, h->first.b, a1, 2 * c0,
-                           nullptr, 0, EPI_RELU_BF16, s));
+    MSCLIP_TRY(launch_gemm_split(col0, 32, h->first.w, 32, static_cast<int>(nb * px1), 2 * c0, 32, h->first.b, a1, c0,
+                                 EPI_RELU_BF16, s));
+    const op16* a1_stem = a1;
+    const op16* a1_branch = a1 + static_cast<size_t>(nb) * px1 * c0;
     count_launch(2);
     // ---- stem: 4 residual stride blocks, then the 1x1 last_conv (M.py:1995-2000)
     {
-      const op16* cur = a1;
-      int cpix = 2 * c0, ch = c0, Hc = H1;
+      const op16* cur = a1_stem;
+      int cpix = c0, ch = c0, Hc = H1;
       op16* outs[2] = {actA, actB};
       for (int i = 0; i < 4; ++i) {
         const int st = c.early_strides[i], Ho = Hc / st;
@@ -633,8 +636,8 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     }
     // ---- parallel branch (M.py:2436-2442) -> only the patch-pooled features the adapters need are kept
     if (n_active > 0) {
-      const op16* p = a1;
-      int cpix = 2 * c0, coff = c0, Hc = H1;
+      const op16* p = a1_branch;
+      int cpix = c0, coff = 0, Hc = H1;
       MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, coff, dims[0], h->adapters[0].k, h->adapters[0].dw_w,
                                    h->adapters[0].dw_b, pooled[0] + static_cast<size_t>(b0) * g * g * dims[0], s));
       count_launch(1);

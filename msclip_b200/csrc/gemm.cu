@@ -203,10 +203,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const int row = m0 + q * 32 + lane;
+      GemmParams pt = p;  // per-tile view: with split outputs every column tile owns its own [M, BN] matrix
+      if (p.split_stride != 0) {
+        const long long shift = static_cast<long long>(tile % p.tiles_n) * p.split_stride - n0;
+        pt.out = (EPI == EPI_RESID_F32 || EPI == EPI_F32) ? static_cast<void*>(reinterpret_cast<float*>(p.out) + shift)
+                                                          : static_cast<void*>(reinterpret_cast<op16*>(p.out) + shift);
+      }
       // software pipeline: the TMEM load of chunk c+1 and the global operands of chunk c are in flight while
       // chunk c is converted and stored (tcgen05.wait::ld waits for every outstanding load, so the next load
       // is issued right after the wait)
-      const bool row_ok = row < p.M;
       uint32_t acc[2][Cfg::kChunk];
       tmem_ld_chunk<Cfg::kChunk>(taddr + c_begin * Cfg::kChunk, acc[0]);
 #pragma unroll
@@ -216,10 +221,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int col0 = n0 + c * Cfg::kChunk;
           const bool fast = p.vec_ok && (col0 + Cfg::kChunk <= p.N);
           EpiOperands<EPI, Cfg::kChunk> ops;
-          epilogue_prefetch<EPI, Cfg::kChunk>(ops, p, row, col0, fast);
+          epilogue_prefetch<EPI, Cfg::kChunk>(ops, pt, row, col0, fast);
           tmem_ld_wait();
           if (c + 1 < c_end) tmem_ld_chunk<Cfg::kChunk>(taddr + (c + 1) * Cfg::kChunk, acc[(i + 1) & 1]);
-          epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, p, row, col0, fast);
+          epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, pt, row, col0, fast);
         }
       }
       tc_fence_before();
@@ -303,19 +308,40 @@ int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, i
   return launch_gemm_scaled(A, lda, W, ldw, M, N, K, 1.0f, bias, out, ldo, resid, ldr, epi, stream);
 }
 
+static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
+                            const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
+                            int split_cols, cudaStream_t stream);
+
 int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
                        cudaStream_t stream) {
+  return launch_gemm_impl(A, lda, W, ldw, M, N, K, alpha, bias, out, ldo, resid, ldr, epi, 0, stream);
+}
+
+// Column tile j (split_cols wide) is written as its own dense [M, split_cols] matrix at out + j * M * split_cols:
+// one GEMM producing several tensors (the shared first convolution of the stem and of the parallel branch).
+int launch_gemm_split(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
+                      void* out, int split_cols, int epi, cudaStream_t stream) {
+  MSCLIP_REQUIRE(split_cols == 48 || split_cols == 64 || split_cols == 96 || split_cols == 128 || split_cols == 192 ||
+                     split_cols == 256,
+                 "launch_gemm_split: split width must be a supported tile width");
+  MSCLIP_REQUIRE(N % split_cols == 0 && epi != EPI_RESID_F32, "launch_gemm_split: N must be a multiple of the split width");
+  return launch_gemm_impl(A, lda, W, ldw, M, N, K, 1.0f, bias, out, split_cols, nullptr, 0, epi, split_cols, stream);
+}
+
+static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
+                            const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
+                            int split_cols, cudaStream_t stream) {
   MSCLIP_REQUIRE(M > 0 && N > 0 && K > 0, "launch_gemm: empty problem");
   MSCLIP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "launch_gemm: K and operand pitches must be multiples of 8");
-  const int bn = gemm_pick_bn(N);
+  const int bn = split_cols ? split_cols : gemm_pick_bn(N);
   const bool f32_out = (epi == EPI_RESID_F32 || epi == EPI_F32);
   if (epi == EPI_RESID_F32) MSCLIP_REQUIRE(resid != nullptr, "launch_gemm: residual operand missing");
   bool vec_ok = ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                 (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   if (epi == EPI_RESID_F32) vec_ok = vec_ok && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0;
   // CTA pairs for the large transformer GEMMs (N a multiple of 256, at least one full pair tile of rows)
-  const int cg = (g_pair_mode >= 1 && bn == 256 && N % 256 == 0 && M >= 256) ? 2 : 1;
+  const int cg = (g_pair_mode >= 1 && bn == 256 && N % 256 == 0 && M >= 256 && split_cols == 0) ? 2 : 1;
   int np = 1;
   if (cg == 2 && g_pair_mode >= 2) np = (g_pair_mode == 4 && M >= 4096) ? 4 : (M >= 1024 ? 2 : 1);
   CUtensorMap ta, tb;
@@ -330,6 +356,7 @@ int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, i
   p.tiles_n = (N + bn - 1) / bn;
   p.alpha = alpha;
   p.vec_ok = vec_ok ? 1 : 0;
+  p.split_stride = split_cols ? static_cast<long long>(M) * split_cols : 0;
   p.total_tiles = ((M + kBM * cg * np - 1) / (kBM * cg * np)) * p.tiles_n;
   p.bias = bias;
   p.out = out;

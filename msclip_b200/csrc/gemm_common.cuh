@@ -23,6 +23,7 @@ struct GemmParams {
   long long ldo, ldr;
   float alpha;  // acc is scaled by alpha before the bias (similarity logits: exp(logit_scale))
   int vec_ok;   // rows of out / resid keep 16-byte alignment -> vector stores
+  long long split_stride;  // != 0: column tile j writes a separate [M, BN] matrix at out + j * split_stride (elements)
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {

@@ -57,6 +57,8 @@ enum GemmEpilogue {
 int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
                 void* out, int64_t ldo, const float* resid, int64_t ldr, int epi, cudaStream_t stream);
 
+int launch_gemm_split(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
+                      void* out, int split_cols, int epi, cudaStream_t stream);
 void gemm_set_pair_mode(int mode);  // 0: 1 CTA per tile, 1: CTA pairs, 2|4: multicast clusters of 2|4 pairs
 int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
