@@ -11,6 +11,8 @@
  *   msclip_op_im2col_nhwc     gather for the later convs            M.py:1920-1936, 1842-1861
  *   msclip_op_conv_gemm       conv3x3 / strided conv1x1 (+BN+ReLU)  M.py:1920-1936, 1842-1861 (implicit GEMM)
  *   msclip_op_patch_pool      Lateral_Adapter.top2bottom_dw_conv    M.py:1756
+ *   msclip_op_front_conv      first convs of stem + branch, branch   M.py:1993, 2260-2273, 1842-1846, 1857, 1756
+ *                             bottleneck entry, adapter-0 pooling (one fused pass over the image)
  *   msclip_op_adapter_fuse_ln Lateral_Adapter tail                  M.py:1760-1777
  *   msclip_op_contrastive_lse similarity + symmetric CE partials    M.py:3141 + north-star loss
  *   msclip_num_keys / msclip_key_info   the state-dict contract     SURVEY.md section 8c
@@ -57,6 +59,13 @@ int msclip_op_conv_gemm(const void* in0, int h0, int w0, int cpix0, int coff0, i
                         void* stream);
 int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                          int k, const float* w, const float* bias, void* out_bf16, void* stream);
+/* Fused 112x112 stage: NCHW image (dtype code as msclip_encode_image) -> stem = relu(conv3x3_s2 . w0[0:48]),
+ * p0 = relu(conv3x3_s2 . w0[48:96]) (kept on chip), y1 = relu(w1 . p0 + b1), p0s = p0[:, ::2, ::2],
+ * pooled = depth-wise k x k / stride k pooling of p0 (+ pool_b).  w0 bf16 [96][32] (k = c*9 + ky*3 + kx, zero padded),
+ * w1 bf16 [48][48], pool_w f32 [k*k][48]; outputs NHWC bf16; height, width multiples of 32; k = 8 or 16. */
+int msclip_op_front_conv(const void* img, int dtype, int batch, int height, int width, const void* w0_bf16, const float* b0,
+                         const void* w1_bf16, const float* b1, const float* pool_w, const float* pool_b, int k,
+                         void* stem_bf16, void* y1_bf16, void* p0s_bf16, void* pooled_bf16, void* stream);
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                               const float* b, float* x_out, int batch, int grid, void* stream);
 /* parts2[0] = sum_i (lse_j s_ij - s_ii), parts2[1] = sum_j (lse_i s_ij - s_jj), s = scale * img . txt^T */

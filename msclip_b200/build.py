@@ -18,7 +18,7 @@ OBJ_DIR = os.path.join(CSRC, "build")
 # two builds of the same sources: MMA operands in bf16 (default) or IEEE fp16 (-DMSCLIP_FP16)
 LIB_PATHS = {"bf16": os.path.join(HERE, "libmsclip_b200.so"), "fp16": os.path.join(HERE, "libmsclip_b200_fp16.so")}
 LIB_PATH = LIB_PATHS["bf16"]
-SOURCES = ["runtime.cu", "gemm.cu", "conv_gemm.cu", "elementwise.cu", "conv.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
+SOURCES = ["runtime.cu", "gemm.cu", "conv_gemm.cu", "elementwise.cu", "conv.cu", "front.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
 HEADERS = ["common.cuh", "gemm_common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
            os.path.join("..", "..", "include", "msclip_b200_ops.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

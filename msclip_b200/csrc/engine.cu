@@ -540,8 +540,20 @@ static const bool g_conv_im2col = [] {
   const char* e = getenv("MSCLIP_CONV_IM2COL");
   return e != nullptr && e[0] == '1';
 }();
+// MSCLIP_FRONT_FUSED=0 falls back to im2col + GEMMs + patch pooling for the 112 x 112 stage (A/B timing)
+static const bool g_front_fused = [] {
+  const char* e = getenv("MSCLIP_FRONT_FUSED");
+  return e == nullptr || e[0] != '0';
+}();
+static int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  if (e == nullptr || e[0] == 0) return dflt;
+  const int v = atoi(e);
+  return (v < lo || v > hi) ? dflt : v;
+}
 static const int kLateral[5] = {2, 4, 6, 8, 10};  // PARALLEL_LATERAL_LAYER, b32-yfcc-msclips.yaml:18
-static const int kConvChunk = 1024;                // images per pass through the conv stages
+// images per pass through the conv stages (MSCLIP_CONV_CHUNK overrides, for tuning)
+static const int kConvChunk = env_int("MSCLIP_CONV_CHUNK", 1024, 1, 1 << 16);
 static const int kTowerChunk = 4096;               // sequences per pass through the transformer
 
 // image tower for `batch` images already on the device; feat_bf16 (optional) receives the op16 copy of
@@ -559,7 +571,13 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   const int nbmax = std::min(batch, kConvChunk);
   const size_t px1 = static_cast<size_t>(H1) * H1;  // pixels after the first conv
 
-  WS(col0, op16, "col0", nbmax * px1 * 32);
+  // the whole 112 x 112 stage in one kernel when the branch is live: first convs, the branch's first bottleneck
+  // 1x1 (-> actC), the even pixels of p_0 for its strided shortcut (-> the branch half of a1) and adapter 0's
+  // patch pooling (front.cu); p_0 itself never reaches HBM
+  const bool fused = g_front_fused && !g_conv_im2col && n_active > 0 && c.parallel_strides[1] == 2 &&
+                     front_conv_supported(R, R, c0, h->adapters[0].k);
+  op16* col0 = nullptr;
+  if (!fused) MSCLIP_TRY(ws_get(h, "col0", nbmax * px1 * 32 * sizeof(op16), reinterpret_cast<void**>(&col0)));
   WS(a1, op16, "a1", nbmax * px1 * 2 * c0);
   // largest im2col matrix and activation of the later stages (stage 0 of the stem dominates)
   size_t col_max = 0, act_max = 0;
@@ -598,12 +616,19 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     const uint8_t* img_c = static_cast<const uint8_t*>(img) + static_cast<size_t>(b0) * 3 * R * R * esz;
     // first convs (stem conv1+bn1+ReLU, M.py:1993 | branch stage 0, M.py:2260-2273): one GEMM, N = 48 + 48, whose
     // two column tiles land in two dense NHWC tensors (consumers of one half never touch the other half's bytes)
-    MSCLIP_TRY(launch_im2col_first(img_c, dtype, col0, nb, R, R, s));
-    MSCLIP_TRY(launch_gemm_split(col0, 32, h->first.w, 32, static_cast<int>(nb * px1), 2 * c0, 32, h->first.b, a1, c0,
-                                 EPI_RELU_BF16, s));
     const op16* a1_stem = a1;
     const op16* a1_branch = a1 + static_cast<size_t>(nb) * px1 * c0;
-    count_launch(2);
+    if (fused) {
+      MSCLIP_TRY(launch_front_conv(img_c, dtype, nb, R, R, h->first.w, h->first.b, h->br1[1].w, h->br1[1].b,
+                                   h->adapters[0].dw_w, h->adapters[0].dw_b, h->adapters[0].k, a1, actC, a1 + static_cast<size_t>(nb) * px1 * c0,
+                                   pooled[0] + static_cast<size_t>(b0) * g * g * dims[0], s));
+      count_launch(1);
+    } else {
+      MSCLIP_TRY(launch_im2col_first(img_c, dtype, col0, nb, R, R, s));
+      MSCLIP_TRY(launch_gemm_split(col0, 32, h->first.w, 32, static_cast<int>(nb * px1), 2 * c0, 32, h->first.b, a1, c0,
+                                   EPI_RELU_BF16, s));
+      count_launch(2);
+    }
     // ---- stem: 4 residual stride blocks, then the 1x1 last_conv (M.py:1995-2000)
     {
       const op16* cur = a1_stem;
@@ -638,15 +663,19 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     if (n_active > 0) {
       const op16* p = a1_branch;
       int cpix = c0, coff = 0, Hc = H1;
-      MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, coff, dims[0], h->adapters[0].k, h->adapters[0].dw_w,
-                                   h->adapters[0].dw_b, pooled[0] + static_cast<size_t>(b0) * g * g * dims[0], s));
-      count_launch(1);
+      if (!fused) {
+        MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, coff, dims[0], h->adapters[0].k, h->adapters[0].dw_w,
+                                     h->adapters[0].dw_b, pooled[0] + static_cast<size_t>(b0) * g * g * dims[0], s));
+        count_launch(1);
+      }
       op16* pbuf[2] = {actA, actB};
       for (int j = 1; j < n_active; ++j) {
         const int cin = dims[j - 1], st = c.parallel_strides[j], Ho = Hc / st;
+        const bool from_front = fused && j == 1;  // y1 and the strided p_0 were produced by the front kernel
         // y1 = relu(bn1(conv1x1(p)))
-        MSCLIP_TRY(launch_gemm(p + coff, cpix, h->br1[j].w, cin, nb * Hc * Hc, cin, cin, h->br1[j].b, actC, cin, nullptr,
-                               0, EPI_RELU_BF16, s));
+        if (!from_front)
+          MSCLIP_TRY(launch_gemm(p + coff, cpix, h->br1[j].w, cin, nb * Hc * Hc, cin, cin, h->br1[j].b, actC, cin, nullptr,
+                                 0, EPI_RELU_BF16, s));
         op16* pn = pbuf[j & 1];
         if (g_conv_im2col) {
           // y2 = relu(bn2(conv3x3_s(y1)))  -> columns [0, cin) of the concatenated operand
@@ -666,7 +695,11 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
           const ConvSource s2 = {actC, Hc, Hc, cin, 0, cin, 3, st, 1};
           MSCLIP_TRY(launch_conv_gemm(&s2, 1, nb, Ho, Ho, h->br2[j].w, 9 * cin, cin, h->br2[j].b, y2, cin, EPI_RELU_BF16, s));
           // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p))): one GEMM over K = [y2 | strided p]
-          const ConvSource s3[2] = {{y2, Ho, Ho, cin, 0, cin, 1, 1, 0}, {p, Hc, Hc, cpix, coff, cin, 1, st, 0}};
+          ConvSource s3[2] = {{y2, Ho, Ho, cin, 0, cin, 1, 1, 0}, {p, Hc, Hc, cpix, coff, cin, 1, st, 0}};
+          if (from_front) {  // p already holds only the pixels the strided shortcut reads
+            s3[1].H = s3[1].W = Ho;
+            s3[1].stride = 1;
+          }
           MSCLIP_TRY(launch_conv_gemm(s3, 2, nb, Ho, Ho, h->br3[j].w, 2 * cin, 2 * cin, h->br3[j].b, pn, 2 * cin,
                                       EPI_RELU_BF16, s));
         }
@@ -676,7 +709,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         Hc = Ho;
         MSCLIP_TRY(launch_patch_pool(p, nb, Hc, Hc, cpix, 0, dims[j], h->adapters[j].k, h->adapters[j].dw_w,
                                      h->adapters[j].dw_b, pooled[j] + static_cast<size_t>(b0) * g * g * dims[j], s));
-        count_launch(4);
+        count_launch(from_front ? 3 : 4);
       }
     }
   }

@@ -3,7 +3,7 @@
 # CUDA context of the others.  Logs land in gpurun_out/.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for k in test_gemm test_conv_gemm test_layernorm test_attention test_im2col test_patch_pool test_adapter test_contrastive; do
+for k in test_gemm test_conv_gemm test_layernorm test_attention test_im2col test_patch_pool test_front_conv test_adapter test_contrastive; do
   timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q --timeout 200 -k "$k" > gpurun_out/ops_$k.log 2>&1
   echo "== $k: exit $? : $(tail -1 gpurun_out/ops_$k.log)"
 done

@@ -315,6 +315,56 @@ def test_patch_pool(H, cpix, coff, Cc, k):
     assert r < tol16()
 
 
+@pytest.mark.parametrize("B,H,W,k,img16", [(3, 224, 224, 16, False), (2, 224, 224, 8, False), (2, 64, 96, 16, False),
+                                           (1, 96, 64, 8, True), (700, 32, 32, 16, False)])
+def test_front_conv_matches_unfused_reference(B, H, W, k, img16):
+    """Fused 112x112 stage (front.cu) against conv2d / 1x1 / depth-wise pooling on the same rounded operands:
+    stem and branch first convs (M.py:1993, 2260-2273), bottleneck entry (M.py:1842-1846), strided copy of p0
+    (M.py:1857) and adapter-0 patch pooling (M.py:1756)."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    dt = op_dtype()
+    img = torch.randn(B, 3, H, W, device="cuda", generator=g)
+    code = _lib.F32
+    if img16:
+        img = img.to(dt)
+        code = _lib.F16 if PREC == "fp16" else _lib.BF16
+    w0 = (torch.randn(96, 3, 3, 3, device="cuda", generator=g) / math.sqrt(27)).to(dt)
+    b0 = 0.3 * torch.randn(96, device="cuda", generator=g)
+    w1 = (torch.randn(48, 48, device="cuda", generator=g) / math.sqrt(48)).to(dt)
+    b1 = 0.3 * torch.randn(48, device="cuda", generator=g)
+    pw = torch.randn(48, 1, k, k, device="cuda", generator=g) / k
+    pb = torch.randn(48, device="cuda", generator=g)
+    w0p = torch.zeros(96, 32, device="cuda", dtype=dt)
+    w0p[:, :27] = w0.reshape(96, 27)                                   # k = c*9 + ky*3 + kx
+    pwp = pw.view(48, k * k).t().contiguous()                          # [k*k][C]
+    Ho, Wo = H // 2, W // 2
+    stem = torch.full((B, Ho, Wo, 48), 7.0, device="cuda", dtype=dt)
+    y1 = torch.full((B, Ho, Wo, 48), 7.0, device="cuda", dtype=dt)
+    p0s = torch.full((B, Ho // 2, Wo // 2, 48), 7.0, device="cuda", dtype=dt)
+    pooled = torch.full((B * (Ho // k) * (Wo // k), 48), 7.0, device="cuda", dtype=dt)
+    check(LIB.msclip_op_front_conv(ptr(img), code, B, H, W, ptr(w0p), ptr(b0), ptr(w1), ptr(b1), ptr(pwp), ptr(pb), k,
+                                   ptr(stem), ptr(y1), ptr(p0s), ptr(pooled), stream()))
+    a = torch.relu(F.conv2d(img.to(dt).float(), w0.float(), b0, stride=2, padding=1))    # operands rounded as the kernel does
+    p0 = a[:, 48:]
+    p0r = p0.to(dt).float()
+    refs = {
+        "stem": a[:, :48].permute(0, 2, 3, 1),
+        "y1": torch.relu(F.conv2d(p0r, w1.float()[:, :, None, None], b1)).permute(0, 2, 3, 1),
+        "p0s": p0r[:, :, ::2, ::2].permute(0, 2, 3, 1),
+        "pooled": (F.conv2d(p0, pw, stride=k, groups=48) + pb[None, :, None, None]).permute(0, 2, 3, 1).reshape(-1, 48),
+    }
+    outs = {"stem": stem, "y1": y1, "p0s": p0s, "pooled": pooled}
+    res = {}
+    for name, ref in refs.items():
+        res[name] = rel(outs[name].float().reshape(ref.shape), ref)
+    _record(f"front_conv/B{B}_{H}x{W}_k{k}_{'i16' if img16 else 'f32'}", res)
+    for name, r in res.items():
+        assert r < tol16(), (name, r)
+    # the strided copy is the rounded p0 itself: bit-equal wherever the fp32 accumulation order does not flip a rounding
+    same = (p0s.float() == refs["p0s"].to(dt).float()).float().mean().item()
+    assert same > 0.98, same
+
+
 @pytest.mark.parametrize("g", [7, 14])
 def test_adapter_tail_matches_oracle(g):
     """Lateral adapter (M.py:1752-1778) through the oracle: BN folded by hand here, exactly as the engine does."""

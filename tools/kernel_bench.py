@@ -118,6 +118,37 @@ def main():
         print(f"conv/{name:28s} implicit {ms_i:7.3f} ms ({fl / ms_i / 1e9:6.1f} TF/s, {algo / ms_i / 1e6:6.0f} GB/s algorithmic) | "
               f"im2col {ms_c:7.3f} + gemm {ms_g:7.3f} ms", flush=True)
         del x, w, o, col
+    # fused 112 x 112 stage (front.cu) against the kernels it replaces, one chunk of 256 images
+    if args.only in "front/fused":
+        R, kk = 224, 16
+        img = torch.randn(nbc, 3, R, R, device="cuda")
+        w0 = (torch.randn(96, 32, device="cuda") / 5).to(torch.bfloat16)
+        w0[:, 27:] = 0
+        w1 = (torch.randn(48, 48, device="cuda") / 7).to(torch.bfloat16)
+        b0, b1 = torch.randn(96, device="cuda"), torch.randn(48, device="cuda")
+        pw, pb = torch.randn(kk * kk, 48, device="cuda") / kk, torch.randn(48, device="cuda")
+        px = nbc * 112 * 112
+        stem = torch.empty(px, 48, device="cuda", dtype=torch.bfloat16)
+        y1 = torch.empty(px, 48, device="cuda", dtype=torch.bfloat16)
+        p0s = torch.empty(px // 4, 48, device="cuda", dtype=torch.bfloat16)
+        pooled = torch.empty(nbc * 49, 48, device="cuda", dtype=torch.bfloat16)
+        ms_f = time_ms(lambda: _lib.check(L.msclip_op_front_conv(ptr(img), _lib.F32, nbc, R, R, ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(pw),
+                                                                  ptr(pb), kk, ptr(stem), ptr(y1), ptr(p0s), ptr(pooled), sp)), args.reps)
+        col0 = torch.empty(px, 32, device="cuda", dtype=torch.bfloat16)
+        a1 = torch.empty(px, 96, device="cuda", dtype=torch.bfloat16)
+        ms_u = time_ms(lambda: (_lib.check(L.msclip_op_im2col_first(ptr(img), _lib.F32, ptr(col0), nbc, R, R, sp)),
+                                _lib.check(L.msclip_op_gemm(ptr(col0), 32, ptr(w0), 32, px, 96, 32, 1.0, ptr(b0), ptr(a1), 96, None, 0,
+                                                            _lib.EPI_RELU_BF16, sp)),
+                                _lib.check(L.msclip_op_gemm(ptr(a1[:, 48:]), 96, ptr(w1), 48, px, 48, 48, 1.0, ptr(b1), ptr(y1), 48, None, 0,
+                                                            _lib.EPI_RELU_BF16, sp)),
+                                _lib.check(L.msclip_op_patch_pool(ptr(a1), nbc, 112, 112, 96, 48, 48, kk, ptr(pw), ptr(pb), ptr(pooled), sp))),
+                       args.reps)
+        algo = img.numel() * 4 + (stem.numel() + y1.numel() + p0s.numel() + pooled.numel()) * 2
+        out["other"].append({"name": "front/fused", "ms": ms_f, "ms_unfused": ms_u, "GBps": algo / ms_f / 1e6,
+                             "frac_hbm": algo / ms_f / 1e6 / peaks["hbm"]})
+        print(f"front/fused {ms_f:7.3f} ms ({algo / ms_f / 1e6:6.0f} GB/s algorithmic, {100 * algo / ms_f / 1e6 / peaks['hbm']:.1f}% of HBM) | "
+              f"im2col + GEMM(96) + GEMM(48) + pool {ms_u:7.3f} ms", flush=True)
+        del img, stem, y1, p0s, col0, a1
     # LayerNorm (HBM-bound): M x 768 fp32 in, bf16 out
     for tower, Lseq in (("text", 77), ("image", 50)):
         if args.only not in f"{tower}/layernorm":
