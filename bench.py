@@ -40,6 +40,11 @@ from msclip_b200.config import MSCLIPConfig
 METRIC = "image-text pairs/sec (forward + contrastive loss), MS-CLIP-S ViT-B/32"
 UNIT = "pairs/s"
 GF_PER_PAIR = {32: 23.549e9, 16: 49.617e9}        # BASELINE.md section 3 (2*m*n*k of every GEMM/bmm/conv)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+# `ncu --set full` capture (never measured inside a bench run): fc1 at the text-tower shape read 0.4907 GB and
+# wrote 1.8835 GB = its algorithmic bytes (A + W read once, bf16 output written once)
+NCU_DRAM_BYTES_PER_LAUNCH = {(4096 * 77, 3072, 768): 2374214000}
+NCU_TRAFFIC_SOURCE = "profiles/r01_gemm_ncu.md (ncu --set full, fc1 M=315392 N=3072 K=768, CTA pair)"
 
 
 def peaks():
@@ -319,7 +324,9 @@ def run_ours(args, cfg, rank, world, local):
     step_tf = value / world * GF_PER_PAIR[cfg.patch_size] / 1e12
     roofline = {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel<256, QGELU> fc1 M={M} N={N} K={K}",
                 "achieved": gemm_tf, "peak": pk["burst"], "unit": "TFLOP/s", "frac": gemm_tf / pk["burst"],
-                "traffic": None, "peak_source": pk["source"] + ", burst (kernel timed alone)",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((M, N, K)), "traffic_source": NCU_TRAFFIC_SOURCE,
+                "algorithmic_bytes": (M * K + N * K + M * N) * 2,
+                "peak_source": pk["source"] + ", burst (kernel timed alone)",
                 "us_per_launch": gemm_s * 1e6,
                 "whole_step": {"achieved": step_tf, "peak": pk["sustained"], "frac": step_tf / pk["sustained"],
                                "note": "per-GPU pairs/s x 23.549 GFLOP/pair against the sustained cuBLAS peak"}}

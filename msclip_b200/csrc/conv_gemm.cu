@@ -49,10 +49,13 @@ struct ConvCfg {
   static constexpr int kSmemBytes = kStages * kStage + kTableBytes + 256 + 1024;
   static constexpr int kChunk = (BN % 32 == 0) ? 32 : 16;
   static constexpr int kNumChunks = BN / kChunk;
-  // cp.async groups a gather thread keeps in flight: as deep as the ring allows (the small-N convolutions are
-  // latency-bound on the A gather, bytes in flight are what buys bandwidth)
-  static constexpr int kLag = kStages - 1;
-  static_assert(kStages >= 2, "ring too shallow");
+  // cp.async groups a gather thread keeps in flight before it hands the oldest one to the MMA warp.  The ring is
+  // split between bytes in flight (LAG stages landing) and slack (stages already handed over that the MMA warp can
+  // run through while the gather threads sleep on a free-slot barrier): with LAG = kStages - 1 every k-block paid
+  // the full MMA-done -> gather-wakes -> issue -> arrive -> MMA-wakes round trip (profiles/r01d_conv_ncu.md)
+  static constexpr int kLagHalf = kStages / 2;
+  static constexpr int kLagDeep = kStages - 2 > 0 ? kStages - 2 : 1;
+  static_assert(kStages >= 3, "ring too shallow");
 };
 
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* src, uint32_t src_bytes) {
@@ -64,7 +67,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int LAG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp) {
   using Cfg = ConvCfg<BN>;
@@ -155,6 +158,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
         const int sidx = (e.y >> 16) & 1;
         const int kx = e.y & 0xFF, ky = (e.y >> 8) & 0xFF;
         const ConvSeg& sg = cp.seg[sidx];
+        if (it >= LAG) {
+          // hand over the block issued LAG iterations ago BEFORE sleeping on a free slot: the MMA warp must never
+          // wait for data that has already landed
+          cp_async_wait<LAG - 1>();
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+          mbar_arrive(&full_bar[(it - LAG) % Cfg::kStages]);
+        }
         mbar_wait(&empty_bar[s], ph ^ 1u, 21);
         const uint32_t dst_base = smem_u32(smem + s * Cfg::kStage) + static_cast<uint32_t>(warp * 32 + rsub) * 128u;
 #pragma unroll
@@ -169,16 +179,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
                             src, ok ? 16u : 0u);
         }
         cp_async_commit();
-        if (it >= Cfg::kLag) {
-          cp_async_wait<Cfg::kLag>();  // the group issued kLag iterations ago has landed
-          fence_proxy_async_smem();    // generic-proxy writes -> visible to the tensor core's async proxy
-          mbar_arrive(&full_bar[(it - Cfg::kLag) % Cfg::kStages]);
-        }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    for (int d = (it < Cfg::kLag ? it : Cfg::kLag); d > 0; --d) mbar_arrive(&full_bar[(it - d) % Cfg::kStages]);
+    for (int d = (it < LAG ? it : LAG); d > 0; --d) mbar_arrive(&full_bar[(it - d) % Cfg::kStages]);
   } else if (warp == 4) {
     if (lane == 0) {
       int s = 0;
@@ -272,19 +277,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
   if (warp == 6) tmem_dealloc(tmem_base, 512);
 }
 
-template <int BN, int EPI>
-int launch_conv_variant(const CUtensorMap& tb, const ConvParams& cp, cudaStream_t stream) {
+template <int BN, int EPI, int LAG>
+int launch_conv_lag(const CUtensorMap& tb, const ConvParams& cp, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::kSmemBytes));
     configured = true;
   }
   const int grid = cp.g.total_tiles < num_sms() ? cp.g.total_tiles : num_sms();
-  conv_gemm_kernel<BN, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tb, cp);
+  conv_gemm_kernel<BN, EPI, LAG><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(tb, cp);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// MSCLIP_CONV_LAG=deep keeps kStages - 2 gather groups in flight instead of kStages / 2 (A/B timing)
+static const bool g_lag_deep = [] {
+  const char* e = getenv("MSCLIP_CONV_LAG");
+  return e != nullptr && e[0] == 'd';
+}();
+
+template <int BN, int EPI>
+int launch_conv_variant(const CUtensorMap& tb, const ConvParams& cp, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  if (g_lag_deep && Cfg::kLagDeep != Cfg::kLagHalf) return launch_conv_lag<BN, EPI, Cfg::kLagDeep>(tb, cp, stream);
+  return launch_conv_lag<BN, EPI, Cfg::kLagHalf>(tb, cp, stream);
 }
 
 template <int BN>

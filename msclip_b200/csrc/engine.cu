@@ -553,7 +553,7 @@ static int env_int(const char* name, int dflt, int lo, int hi) {
 }
 static const int kLateral[5] = {2, 4, 6, 8, 10};  // PARALLEL_LATERAL_LAYER, b32-yfcc-msclips.yaml:18
 // images per pass through the conv stages (MSCLIP_CONV_CHUNK overrides, for tuning)
-static const int kConvChunk = env_int("MSCLIP_CONV_CHUNK", 1024, 1, 1 << 16);
+static const int kConvChunk = env_int("MSCLIP_CONV_CHUNK", 512, 1, 1 << 16);
 static const int kTowerChunk = 4096;               // sequences per pass through the transformer
 
 // image tower for `batch` images already on the device; feat_bf16 (optional) receives the op16 copy of
