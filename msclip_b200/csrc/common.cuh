@@ -124,9 +124,15 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
-  const uint64_t t0 = global_timer_ns();
+  // try_wait suspends the thread for a hardware-defined interval by itself; the timer is only consulted every 64
+  // failed polls so that a waiter notices the phase flip as soon as the hardware wakes it
+  uint64_t t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > 4000000000ull) {
+    if ((++polls & 63u) != 0) continue;
+    const uint64_t now = global_timer_ns();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > 4000000000ull) {
       printf("msclip: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();

@@ -10,9 +10,13 @@
 // buffering and the fused epilogue are those of gemm.cu.
 //
 // Warp roles (512 threads, 1 CTA / SM, persistent):
-//   warps 0-3  : A gather, thread t owns tile row t     warp 4 : W TMA producer (one lane)
-//   warp 5     : MMA issuer (one lane)                   warp 6 : TMEM allocator
-//   warps 8-15 : epilogue
+//   warps 0-7  : A gather (8 lanes per tile row, 4 rows per lane and k-block)
+//   warp 8     : W TMA producer (one lane)      warp 9 : MMA issuer (one lane)     warp 10 : TMEM allocator
+//   warps 12-15: epilogue (one per TMEM lane quarter; the tiles are at most 192 columns wide)
+// The gather warps are the critical resource (profiles/r01d_conv_ncu.md: they were busy ~80 % of the time on
+// address arithmetic while every other unit idled), so their inner loop is stripped to a table lookup, a bit
+// test and the copy: per tile row the thread keeps the patch origin as an element offset plus a bit mask of the
+// taps that fall inside the image, per k-chunk a table gives the tap's offset and bit.
 #include "gemm_common.cuh"
 
 namespace msclip {
@@ -22,7 +26,12 @@ namespace {
 using namespace gemm_detail;
 
 constexpr int kConvThreads = 512;
-constexpr int kGatherThreads = 128;
+constexpr int kGatherWarps = 8;
+constexpr int kGatherThreads = 32 * kGatherWarps;
+constexpr int kRowsPerLane = kBM / (4 * kGatherWarps);  // 4
+constexpr int kTmaWarp = kGatherWarps, kMmaWarp = kGatherWarps + 1, kAllocWarp = kGatherWarps + 2;
+constexpr int kFirstEpiWarp = 12;
+constexpr int kConvEpiWarps = 4;
 constexpr int kMaxKChunks = 512;  // K <= 4096
 
 struct ConvSeg {
@@ -86,7 +95,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
   const int num_kb = (p.K + kBK - 1) / kBK;
 
   // K-chunk table: chunk q (K indices 8q .. 8q+7) -> x: element offset of the tap inside the source
-  // ((ky*W + kx)*cpix + c), y: kx | ky << 8 | source << 16; y = 0xFFFFFFFF marks chunks beyond K (zero filled)
+  // ((ky*W + kx)*cpix + c), y: tap index ky*ksize + kx | source << 16; y = -1 marks chunks beyond K (zero filled)
   for (int q = threadIdx.x; q < num_kb * 8; q += kConvThreads) {
     const int k = q * 8;
     int2 e = make_int2(0, -1);
@@ -97,23 +106,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
       const int tap = kk / sg.C, c = kk - tap * sg.C;
       const int ky = tap / sg.ksize, kx = tap - ky * sg.ksize;
       e.x = (ky * sg.W + kx) * sg.cpix + c;
-      e.y = kx | (ky << 8) | (sidx << 16);
+      e.y = tap | (sidx << 16);
     }
     ktab[q] = e;
   }
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_b);
-  if (warp == 5 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) tma_prefetch_desc(&tmap_b);
+  if (warp == kMmaWarp && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
-      mbar_init(&full_bar[i], kGatherThreads + 1);  // 128 gather threads + the W producer's expect_tx arrive
+      mbar_init(&full_bar[i], kGatherThreads + 1);  // every gather thread + the W producer's expect_tx arrive
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kNumEpilogueWarps);
+      mbar_init(&tempty_bar[i], kConvEpiWarps);
     }
     fence_mbar_init();
   }
-  if (warp == 6) {
+  if (warp == kAllocWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -122,42 +131,75 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kGatherWarps) {
     // ------------------------------------------------------------------ A gather
-    // Lane l of warp w copies chunk j = l & 7 of rows w*32 + 4*i + (l >> 3), i = 0..7: the eight lanes that share
-    // a row fetch its 128 contiguous-in-K bytes (one or two contiguous NHWC segments) and write one full,
+    // Lane l of warp w copies chunk j = l & 7 of tile rows w*16 + 4*i + (l >> 3), i = 0..3: the eight lanes that
+    // share a row fetch its 128 contiguous-in-K bytes (one or two contiguous NHWC segments) and write one full,
     // conflict-free swizzled smem row, so each warp-wide cp.async touches 4 rows instead of 32.
     const int j = lane & 7;
     const int rsub = lane >> 3;
+    const int row0 = warp * (4 * kRowsPerLane) + rsub;
+    const op16* const in0 = cp.seg[0].in;
+    const op16* const in1 = cp.seg[1].in;
+    const int hw = cp.Ho * cp.Wo;
+    uint32_t dst_off[kRowsPerLane];
+#pragma unroll
+    for (int i = 0; i < kRowsPerLane; ++i) {
+      const uint32_t row = static_cast<uint32_t>(row0 + 4 * i);
+      dst_off[i] = row * 128u + ((static_cast<uint32_t>(j) ^ (row & 7u)) << 4);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int m_base = (tile / p.tiles_n) * kBM + warp * 32 + rsub;
-      const int hw = cp.Ho * cp.Wo;
-      // per row: element offset of the patch origin in each source and the origin coordinates (for the bounds test)
-      int pix_off[2][8];
-      int org[2][8];  // (iy0 + 64) | (ix0 + 64) << 16 ; -1 = row beyond M
+      // per row: element offset of the patch origin in each source and the bit mask of the taps inside the image
+      int pix_off[2][kRowsPerLane];
+      uint32_t tapmask[2][kRowsPerLane];
+      {
+        const int m0 = (tile / p.tiles_n) * kBM + row0;
+        int b = m0 / hw;
+        const int rem = m0 - b * hw;
+        int oy = rem / cp.Wo, ox = rem - oy * cp.Wo;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m_base + 4 * i;
-        const bool row_ok = m < p.M;
-        const int b = row_ok ? m / hw : 0;
-        const int rem = row_ok ? m - b * hw : 0;
-        const int oy = rem / cp.Wo, ox = rem - oy * cp.Wo;
+        for (int i = 0; i < kRowsPerLane; ++i) {
+          const bool row_ok = m0 + 4 * i < p.M;
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const ConvSeg& sg = cp.seg[s2];
-          const int iy0 = oy * sg.stride - sg.pad, ix0 = ox * sg.stride - sg.pad;
-          pix_off[s2][i] = ((b * sg.H + iy0) * sg.W + ix0) * sg.cpix + sg.c_off;
-          org[s2][i] = row_ok ? ((iy0 + 64) | ((ix0 + 64) << 16)) : -1;
+          for (int s2 = 0; s2 < 2; ++s2) {
+            if (s2 >= cp.nseg) {  // single source: the second slot is never selected
+              pix_off[s2][i] = 0;
+              tapmask[s2][i] = 0;
+              continue;
+            }
+            const ConvSeg& sg = cp.seg[s2];
+            const int iy0 = oy * sg.stride - sg.pad, ix0 = ox * sg.stride - sg.pad;
+            pix_off[s2][i] = ((b * sg.H + iy0) * sg.W + ix0) * sg.cpix + sg.c_off;
+            // taps ky in [ky_lo, ky_hi] and kx in [kx_lo, kx_hi] read inside the image
+            const int ky_lo = iy0 < 0 ? -iy0 : 0, kx_lo = ix0 < 0 ? -ix0 : 0;
+            const int ky_hi = min(sg.ksize - 1, sg.H - 1 - iy0), kx_hi = min(sg.ksize - 1, sg.W - 1 - ix0);
+            uint32_t mk = 0;
+            if (row_ok && kx_hi >= kx_lo) {
+              const uint32_t cols = ((2u << kx_hi) - 1u) & ~((1u << kx_lo) - 1u);
+              for (int ky = ky_lo; ky <= ky_hi; ++ky) mk |= cols << (ky * sg.ksize);
+            }
+            tapmask[s2][i] = mk;
+          }
+          ox += 4;
+          while (ox >= cp.Wo) {
+            ox -= cp.Wo;
+            ++oy;
+          }
+          while (oy >= cp.Ho) {
+            oy -= cp.Ho;
+            ++b;
+          }
         }
       }
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % Cfg::kStages;
         const uint32_t ph = static_cast<uint32_t>(it / Cfg::kStages) & 1u;
         const int2 e = ktab[kb * 8 + j];
-        const int sidx = (e.y >> 16) & 1;
-        const int kx = e.y & 0xFF, ky = (e.y >> 8) & 0xFF;
-        const ConvSeg& sg = cp.seg[sidx];
+        const bool second = ((e.y >> 16) & 1) != 0;
+        const uint32_t tap = static_cast<uint32_t>(e.y) & 0xFFu;
+        const bool chunk_ok = e.y != -1;
+        const op16* const base = second ? in1 : in0;
         if (it >= LAG) {
           // hand over the block issued LAG iterations ago BEFORE sleeping on a free slot: the MMA warp must never
           // wait for data that has already landed
@@ -166,17 +208,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
           mbar_arrive(&full_bar[(it - LAG) % Cfg::kStages]);
         }
         mbar_wait(&empty_bar[s], ph ^ 1u, 21);
-        const uint32_t dst_base = smem_u32(smem + s * Cfg::kStage) + static_cast<uint32_t>(warp * 32 + rsub) * 128u;
+        const uint32_t stage_base = smem_u32(smem + s * Cfg::kStage);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int o = sidx ? org[1][i] : org[0][i];
-          const int iy = (o & 0xFFFF) - 64 + ky, ix = ((o >> 16) & 0xFFFF) - 64 + kx;
-          const bool ok = e.y != -1 && o != -1 && iy >= 0 && iy < sg.H && ix >= 0 && ix < sg.W;
-          const int off = (sidx ? pix_off[1][i] : pix_off[0][i]) + e.x;
-          const op16* src = ok ? sg.in + off : cp.seg[0].in;
-          const uint32_t row = static_cast<uint32_t>(warp * 32 + rsub + 4 * i);
-          cp_async_16_zfill(dst_base + static_cast<uint32_t>(4 * i) * 128u + ((static_cast<uint32_t>(j) ^ (row & 7u)) << 4),
-                            src, ok ? 16u : 0u);
+        for (int i = 0; i < kRowsPerLane; ++i) {
+          const uint32_t mk = second ? tapmask[1][i] : tapmask[0][i];
+          const bool ok = chunk_ok && ((mk >> tap) & 1u) != 0;
+          const int off = (second ? pix_off[1][i] : pix_off[0][i]) + e.x;
+          cp_async_16_zfill(stage_base + dst_off[i], ok ? base + off : in0, ok ? 16u : 0u);
         }
         cp_async_commit();
       }
@@ -184,7 +222,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
     cp_async_wait<0>();
     fence_proxy_async_smem();
     for (int d = (it < LAG ? it : LAG); d > 0; --d) mbar_arrive(&full_bar[(it - d) % Cfg::kStages]);
-  } else if (warp == 4) {
+  } else if (warp == kTmaWarp) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
@@ -201,7 +239,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f32acc(kBM, BN);
       int s = 0;
@@ -232,12 +270,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
         if (as == 0) aph ^= 1;
       }
     }
-  } else if (warp >= 8) {
-    const int q = warp & 3;
-    const int half = (warp - 8) >> 2;
-    constexpr int kPerHalf = (Cfg::kNumChunks + 1) / 2;
-    const int c_begin = half * kPerHalf;
-    const int c_end = (c_begin + kPerHalf < Cfg::kNumChunks) ? c_begin + kPerHalf : Cfg::kNumChunks;
+  } else if (warp >= kFirstEpiWarp) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    constexpr int kPerHalf = Cfg::kNumChunks;
+    constexpr int c_begin = 0, c_end = Cfg::kNumChunks;
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -247,7 +283,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
       if (c_begin < c_end) {
         uint32_t acc[2][Cfg::kChunk];
         tmem_ld_chunk<Cfg::kChunk>(taddr + c_begin * Cfg::kChunk, acc[0]);
@@ -274,7 +309,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) tmem_dealloc(tmem_base, 512);
+  if (warp == kAllocWarp) tmem_dealloc(tmem_base, 512);
 }
 
 template <int BN, int EPI, int LAG>
@@ -340,7 +375,7 @@ int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo,
   for (int i = 0; i < nsrc; ++i) {
     const ConvSource& s = src[i];
     MSCLIP_REQUIRE(s.C % 8 == 0 && s.cpix % 8 == 0 && s.c_off % 8 == 0, "conv_gemm: channels must be multiples of 8");
-    MSCLIP_REQUIRE(s.ksize >= 1 && s.ksize <= 15 && s.stride >= 1, "conv_gemm: bad kernel geometry");
+    MSCLIP_REQUIRE(s.ksize >= 1 && s.ksize <= 5 && s.stride >= 1, "conv_gemm: kernel size must be in [1, 5]");
     MSCLIP_REQUIRE((s.H + 2 * s.pad - s.ksize) / s.stride + 1 == Ho && (s.W + 2 * s.pad - s.ksize) / s.stride + 1 == Wo,
                    "conv_gemm: source geometry does not produce the output grid");
     MSCLIP_REQUIRE((reinterpret_cast<uintptr_t>(s.in) & 15) == 0, "conv_gemm: input must be 16-byte aligned");

@@ -20,5 +20,8 @@ run half1024 MSCLIP_CONV_LAG=half MSCLIP_CONV_CHUNK=1024
 run half256 MSCLIP_CONV_LAG=half MSCLIP_CONV_CHUNK=256
 timeout 300 python tools/kernel_bench.py --only conv/ --reps 10 > gpurun_out/kb_conv.log 2>&1; tail -7 gpurun_out/kb_conv.log
 MSCLIP_CONV_LAG=deep timeout 300 python tools/kernel_bench.py --only conv/ --reps 10 > gpurun_out/kb_conv_deep.log 2>&1; tail -7 gpurun_out/kb_conv_deep.log
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r01d.csv python bench.py --steps 1 --warmup 1 --min-warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launch.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r01e.csv python bench.py --steps 1 --warmup 1 --min-warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launch.log 2>&1
 echo "== launches: exit $? [$(( $(date +%s) - t0 ))s]"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"conv_gemm_kernel" -c 6 -f -o gpurun_out/prof_conv_r01e \
+  python tools/kernel_bench.py --only conv/ --reps 1 --warm 0 > gpurun_out/ncu_conv.log 2>&1
+echo "== ncu conv: exit $? [$(( $(date +%s) - t0 ))s]"
