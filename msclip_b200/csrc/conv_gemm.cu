@@ -44,8 +44,26 @@ struct ConvParams {
   ConvSeg seg[2];
   int nseg;
   int Ho, Wo;
+  uint32_t hw_mul, hw_shr, wo_mul, wo_shr;  // n / (Ho*Wo) and n / Wo as multiply-high + shift (n < 2^31)
   GemmParams g;
 };
+
+// q = n / d for 0 <= n < 2^31 as umulhi(n, mul) >> shr (d == 1: mul = 0 selects the identity)
+inline void find_divisor(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  if (d == 1) {
+    *mul = 0;
+    *shr = 0;
+    return;
+  }
+  uint32_t lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  const uint32_t p = 31 + lg;
+  *mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+  *shr = p - 32;
+}
+__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr) {
+  return mul != 0 ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr) : n;
+}
 
 template <int BN>
 struct ConvCfg {
@@ -155,9 +173,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
       uint32_t tapmask[2][kRowsPerLane];
       {
         const int m0 = (tile / p.tiles_n) * kBM + row0;
-        int b = m0 / hw;
+        int b = fast_div(m0, cp.hw_mul, cp.hw_shr);
         const int rem = m0 - b * hw;
-        int oy = rem / cp.Wo, ox = rem - oy * cp.Wo;
+        int oy = fast_div(rem, cp.wo_mul, cp.wo_shr), ox = rem - oy * cp.Wo;
 #pragma unroll
         for (int i = 0; i < kRowsPerLane; ++i) {
           const bool row_ok = m0 + 4 * i < p.M;
@@ -171,13 +189,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvParams cp
             const ConvSeg& sg = cp.seg[s2];
             const int iy0 = oy * sg.stride - sg.pad, ix0 = ox * sg.stride - sg.pad;
             pix_off[s2][i] = ((b * sg.H + iy0) * sg.W + ix0) * sg.cpix + sg.c_off;
-            // taps ky in [ky_lo, ky_hi] and kx in [kx_lo, kx_hi] read inside the image
-            const int ky_lo = iy0 < 0 ? -iy0 : 0, kx_lo = ix0 < 0 ? -ix0 : 0;
-            const int ky_hi = min(sg.ksize - 1, sg.H - 1 - iy0), kx_hi = min(sg.ksize - 1, sg.W - 1 - ix0);
             uint32_t mk = 0;
-            if (row_ok && kx_hi >= kx_lo) {
-              const uint32_t cols = ((2u << kx_hi) - 1u) & ~((1u << kx_lo) - 1u);
-              for (int ky = ky_lo; ky <= ky_hi; ++ky) mk |= cols << (ky * sg.ksize);
+            if (row_ok) {
+              if (iy0 >= 0 && ix0 >= 0 && iy0 + sg.ksize <= sg.H && ix0 + sg.ksize <= sg.W) {
+                mk = (2u << (sg.ksize * sg.ksize - 1)) - 1u;  // interior pixel: every tap reads inside the image
+              } else {
+                // taps ky in [ky_lo, ky_hi] and kx in [kx_lo, kx_hi] read inside the image
+                const int ky_lo = iy0 < 0 ? -iy0 : 0, kx_lo = ix0 < 0 ? -ix0 : 0;
+                const int ky_hi = min(sg.ksize - 1, sg.H - 1 - iy0), kx_hi = min(sg.ksize - 1, sg.W - 1 - ix0);
+                if (kx_hi >= kx_lo) {
+                  const uint32_t cols = ((2u << kx_hi) - 1u) & ~((1u << kx_lo) - 1u);
+                  for (int ky = ky_lo; ky <= ky_hi; ++ky) mk |= cols << (ky * sg.ksize);
+                }
+              }
             }
             tapmask[s2][i] = mk;
           }
@@ -383,6 +407,8 @@ int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo,
     K += s.ksize * s.ksize * s.C;
   }
   if (nsrc == 1) cp.seg[1] = cp.seg[0];
+  find_divisor(static_cast<uint32_t>(Ho) * static_cast<uint32_t>(Wo), &cp.hw_mul, &cp.hw_shr);
+  find_divisor(static_cast<uint32_t>(Wo), &cp.wo_mul, &cp.wo_shr);
   MSCLIP_REQUIRE(K <= kMaxKChunks * 8, "conv_gemm: K too large");
   MSCLIP_REQUIRE(ldw % 8 == 0 && ldw >= K, "conv_gemm: weight pitch");
   const int bn = conv_pick_bn(N);

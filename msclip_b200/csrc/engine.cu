@@ -579,13 +579,13 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   op16* col0 = nullptr;
   if (!fused) MSCLIP_TRY(ws_get(h, "col0", nbmax * px1 * 32 * sizeof(op16), reinterpret_cast<void**>(&col0)));
   WS(a1, op16, "a1", nbmax * px1 * 2 * c0);
-  // largest im2col matrix and activation of the later stages (stage 0 of the stem dominates)
+  // scratch of the later stages: `col` = patch matrix (explicit formulation) or y2, act* = activations
   size_t col_max = 0, act_max = 0;
   {
     int Hc = H1, ch = c0;
     for (int i = 0; i < 4; ++i) {
       const int Ho = Hc / c.early_strides[i];
-      col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * 9 * ch);
+      if (g_conv_im2col) col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * 9 * ch);
       act_max = std::max(act_max, static_cast<size_t>(Ho) * Ho * 2 * ch);
       Hc = Ho;
       ch *= 2;
@@ -594,7 +594,8 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     for (int j = 1; j < 5; ++j) {
       const int cin = dims[j - 1];
       const int Ho = Hc / c.parallel_strides[j];
-      col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * 9 * cin);
+      // explicit formulation: the patch matrix; implicit: only y2 [Ho, Ho, cin] lives in `col`
+      col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * (g_conv_im2col ? 9 : 1) * cin);
       act_max = std::max(act_max, static_cast<size_t>(Hc) * Hc * cin);       // y1
       act_max = std::max(act_max, static_cast<size_t>(Ho) * Ho * 2 * cin);   // cat / p_j
       Hc = Ho;
@@ -637,9 +638,9 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
       for (int i = 0; i < 4; ++i) {
         const int st = c.early_strides[i], Ho = Hc / st;
         op16* o = outs[i & 1];
-        // the gather-fed kernel wins while the MMA work per gathered byte is small (N <= 384); the widest stage
-        // is better served by the TMA-fed GEMM on an explicit patch matrix (profiles/r01_kernel_bench.md)
-        if (g_conv_im2col || 2 * ch >= 768) {
+        // the gather-fed kernel beats im2col + TMA-fed GEMM at every stage since its gather warps were slimmed
+        // down (profiles/r01_kernel_bench.md); MSCLIP_CONV_IM2COL=1 keeps the explicit formulation for A/B timing
+        if (g_conv_im2col) {
           MSCLIP_TRY(launch_im2col_nhwc(cur, nb, Hc, Hc, cpix, 0, ch, 3, st, 1, col, 9 * ch, 0, s));
           MSCLIP_TRY(launch_gemm(col, 9 * ch, h->stem[i].w, 9 * ch, nb * Ho * Ho, 2 * ch, 9 * ch, h->stem[i].b, o, 2 * ch,
                                  nullptr, 0, EPI_RELU_BF16, s));
@@ -648,7 +649,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
           MSCLIP_TRY(launch_conv_gemm(&src, 1, nb, Ho, Ho, h->stem[i].w, 9 * ch, 2 * ch, h->stem[i].b, o, 2 * ch,
                                       EPI_RELU_BF16, s));
         }
-        count_launch((g_conv_im2col || 2 * ch >= 768) ? 2 : 1);
+        count_launch(g_conv_im2col ? 2 : 1);
         cur = o;
         cpix = 2 * ch;
         ch *= 2;

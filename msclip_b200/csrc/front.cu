@@ -30,6 +30,7 @@ constexpr int kC = 48;               // channels of each first conv and of the b
 constexpr int kW0Pitch = 40;         // op16 per staged row of w0 [96][32]  (80 B: conflict-free ldmatrix)
 constexpr int kW1Pitch = 56;         // op16 per staged row of w1 [48][48]  (112 B)
 constexpr int kStagePitch = 56;      // op16 per staged output pixel        (112 B)
+constexpr int kPoolPitch = 56;       // f32 per staged pooling tap [k*k][48] (224 B: conflict-free 8-byte loads)
 
 constexpr int kOffIn = 0;
 constexpr int kOffW0 = kOffIn + 3 * kInRows * kInPitch * 4;    // 14256
@@ -78,16 +79,16 @@ __device__ __forceinline__ float px_to_float(uint16_t v, int dtype) {
   return dtype == 1 ? __uint_as_float(static_cast<uint32_t>(v) << 16) : __half2float(__ushort_as_half(v));
 }
 
-// relu(acc + bias) of one 16-pixel row (6 n-tiles = 48 channels) -> staged -> 1536 contiguous bytes at gdst
-__device__ __forceinline__ void store_row(const float (&acc)[6][4], const float* bias, op16* stage, op16* gdst, int lane) {
+// relu(acc) of one 16-pixel row (6 n-tiles = 48 channels; the bias is already in the accumulator) -> staged ->
+// 1536 contiguous bytes at gdst
+__device__ __forceinline__ void store_row(const float (&acc)[6][4], op16* stage, op16* gdst, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    const float2 bb = *reinterpret_cast<const float2*>(bias + 8 * j + 2 * t);
     *reinterpret_cast<uint32_t*>(stage + g * kStagePitch + 8 * j + 2 * t) =
-        pack16(fmaxf(acc[j][0] + bb.x, 0.f), fmaxf(acc[j][1] + bb.y, 0.f));
+        pack16(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f));
     *reinterpret_cast<uint32_t*>(stage + (g + 8) * kStagePitch + 8 * j + 2 * t) =
-        pack16(fmaxf(acc[j][2] + bb.x, 0.f), fmaxf(acc[j][3] + bb.y, 0.f));
+        pack16(fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f));
   }
   __syncwarp();
 #pragma unroll
@@ -151,10 +152,21 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
     const int row = i / 6, pc = i - row * 6;
     *reinterpret_cast<uint4*>(w1_s + row * kW1Pitch + pc * 8) = reinterpret_cast<const uint4*>(p.w1)[i];
   }
+  __syncthreads();  // w0 rows are in place before their bias columns are patched
+  // the first convs' biases ride in the two spare K columns of w0 (A supplies 1.0 there): hi + lo split keeps them
+  // exact to 2^-17; columns 29..31 stay zero
+  for (int i = tid; i < 2 * kC; i += kFrontThreads) {
+    const float bv = p.b0[i];
+    const op16 hi = to_op16(bv);
+    w0_s[i * kW0Pitch + 27] = hi;
+    w0_s[i * kW0Pitch + 28] = to_op16(bv - op16_to_float(hi));
+  }
   for (int i = tid; i < 4 * kC; i += kFrontThreads)
     bias_s[i] = i < 2 * kC ? p.b0[i] : (i < 3 * kC ? p.b1[i - 2 * kC] : p.pool_b[i - 3 * kC]);
-  for (int i = tid; i < k * k * kC / 4; i += kFrontThreads)
-    reinterpret_cast<float4*>(poolw_s)[i] = reinterpret_cast<const float4*>(p.pool_w)[i];
+  for (int i = tid; i < k * k * kC / 4; i += kFrontThreads) {
+    const int tapi = i / (kC / 4), c4 = i - tapi * (kC / 4);
+    *reinterpret_cast<float4*>(poolw_s + tapi * kPoolPitch + c4 * 4) = reinterpret_cast<const float4*>(p.pool_w)[i];
+  }
 
   // window offsets of the 8 im2col columns this thread feeds: k = 16*kt + 8*hf + 2*t + e, k = c*9 + ky*3 + kx;
   // columns 27..31 meet zero weights, any finite value will do
@@ -194,9 +206,14 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
 #pragma unroll
         for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
-            a[r][kt][hf * 2 + rh] = pack16(px_to_float(bp[koff[kt][hf][0]], p.img_dtype),
-                                           px_to_float(bp[koff[kt][hf][1]], p.img_dtype));
+          for (int hf = 0; hf < 2; ++hf) {
+            float lo = px_to_float(bp[koff[kt][hf][0]], p.img_dtype), hi = px_to_float(bp[koff[kt][hf][1]], p.img_dtype);
+            if (kt == 1 && hf == 1) {  // k = 24 + 2t + e: columns 27 (t = 1, e = 1) and 28 (t = 2, e = 0) carry the bias
+              if (t == 1) hi = 1.0f;
+              if (t == 2) lo = 1.0f;
+            }
+            a[r][kt][hf * 2 + rh] = pack16(lo, hi);
+          }
       }
     __syncthreads();  // the window is consumed: the next tile's copy may overwrite it while this tile computes
     if (tile + static_cast<int>(gridDim.x) < p.total_tiles) issue_load(tile + gridDim.x);
@@ -220,7 +237,7 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
       }
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) store_row(acc[r], bias_s, stage, p.stem + (pix0 + static_cast<long long>(r) * p.Wo) * kC, lane);
+    for (int r = 0; r < 2; ++r) store_row(acc[r], stage, p.stem + (pix0 + static_cast<long long>(r) * p.Wo) * kC, lane);
 
     // ---- branch half (output channels 48..95): p0 stays in registers
 #pragma unroll
@@ -245,16 +262,15 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
     for (int r = 0; r < 2; ++r) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
-        const float2 bb = *reinterpret_cast<const float2*>(bias_s + kC + 8 * j + 2 * t);
-        acc[r][j][0] = fmaxf(acc[r][j][0] + bb.x, 0.f);
-        acc[r][j][1] = fmaxf(acc[r][j][1] + bb.y, 0.f);
-        acc[r][j][2] = fmaxf(acc[r][j][2] + bb.x, 0.f);
-        acc[r][j][3] = fmaxf(acc[r][j][3] + bb.y, 0.f);
+        acc[r][j][0] = fmaxf(acc[r][j][0], 0.f);
+        acc[r][j][1] = fmaxf(acc[r][j][1], 0.f);
+        acc[r][j][2] = fmaxf(acc[r][j][2], 0.f);
+        acc[r][j][3] = fmaxf(acc[r][j][3], 0.f);
       }
       const int ky = (2 * warp + r) & (k - 1);
 #pragma unroll
       for (int rh = 0; rh < 2; ++rh) {
-        const float* wp = poolw_s + (ky * k + ((g + 8 * rh) & (k - 1))) * kC + 2 * t;
+        const float* wp = poolw_s + (ky * k + ((g + 8 * rh) & (k - 1))) * kPoolPitch + 2 * t;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
           const float2 wv = *reinterpret_cast<const float2*>(wp + 8 * j);
@@ -290,11 +306,16 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
     }
     __syncwarp();
 
-    // ---- y1 = relu(bn1(conv1x1(p0))): K = 48 from the registers above
+    // ---- y1 = relu(bn1(conv1x1(p0))): K = 48 from the registers above, accumulators start at the bias
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int j = 0; j < 6; ++j) {
+      const float2 bb = *reinterpret_cast<const float2*>(bias_s + 2 * kC + 8 * j + 2 * t);
 #pragma unroll
-      for (int j = 0; j < 6; ++j) acc[r][j][0] = acc[r][j][1] = acc[r][j][2] = acc[r][j][3] = 0.f;
+      for (int r = 0; r < 2; ++r) {
+        acc[r][j][0] = acc[r][j][2] = bb.x;
+        acc[r][j][1] = acc[r][j][3] = bb.y;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       uint32_t bf[4], bg[4];
@@ -309,7 +330,7 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r)
-      store_row(acc[r], bias_s + 2 * kC, stage, p.y1 + (pix0 + static_cast<long long>(r) * p.Wo) * kC, lane);
+      store_row(acc[r], stage, p.y1 + (pix0 + static_cast<long long>(r) * p.Wo) * kC, lane);
 
     // ---- patch pooling: reduce over the 8 pixel columns held by the lanes of equal t, then over warps (fixed order)
     if (k == 16) {
@@ -399,7 +420,7 @@ int launch_front_conv(const void* img, int img_dtype, int batch, int H, int W, c
   p.y1 = y1;
   p.p0s = p0s;
   p.pooled = pooled;
-  const int smem = kOffPoolW + k * k * kC * 4;
+  const int smem = kOffPoolW + k * k * kPoolPitch * 4;
   const int grid = p.total_tiles < 2 * num_sms() ? p.total_tiles : 2 * num_sms();
   if (img_dtype == 0) {
     static int configured = 0;
