@@ -179,36 +179,39 @@ adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t,
         v[i].w += v[i].w;
       }
     } else {
+      // depth-wise 3x3 over the token grid + t, one third of the channels at a time with all nine neighbour rows
+      // in flight (the serial tap loop paid one L2 round trip per tap); out-of-grid taps load zeros
       const int gy = (l - 1) / g, gx = (l - 1) % g;
-      load_row(dw_bias, lane, v);
-#pragma unroll 1
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = gy + dy;
-        if (yy < 0 || yy >= g) continue;
-#pragma unroll 1
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int xx = gx + dx;
-          if (xx < 0 || xx >= g) continue;
-          float4 a[kVec], k[kVec];
-          load_row(x + (bi * L + 1 + yy * g + xx) * kD, lane, a);
-          load_row(dw_w9 + ((dy + 1) * 3 + (dx + 1)) * kD, lane, k);
+      const float4* xg = reinterpret_cast<const float4*>(x + (bi * L + 1) * kD);
+      const float4* t4 = reinterpret_cast<const float4*>(t + (bi * (L - 1) + (l - 1)) * kD);
+      const float4* w4 = reinterpret_cast<const float4*>(dw_w9);
+      const float4* b4 = reinterpret_cast<const float4*>(dw_bias);
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      static_assert(kVec % 2 == 0, "channel thirds are pairs of float4");
 #pragma unroll
-          for (int i = 0; i < kVec; ++i) {
-            v[i].x = fmaf(a[i].x, k[i].x, v[i].x);
-            v[i].y = fmaf(a[i].y, k[i].y, v[i].y);
-            v[i].z = fmaf(a[i].z, k[i].z, v[i].z);
-            v[i].w = fmaf(a[i].w, k[i].w, v[i].w);
-          }
+      for (int part = 0; part < kVec / 2; ++part) {
+        const int c0 = lane + 64 * part, c1 = c0 + 32;
+        float4 a[9][2];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int yy = gy + tap / 3 - 1, xx = gx + tap % 3 - 1;
+          const bool ok = yy >= 0 && yy < g && xx >= 0 && xx < g;
+          const float4* src = xg + static_cast<long long>(ok ? yy * g + xx : 0) * (kD / 4);
+          a[tap][0] = ok ? src[c0] : zero;
+          a[tap][1] = ok ? src[c1] : zero;
         }
-      }
-      float4 tt[kVec];
-      load_row(t + (bi * (L - 1) + (l - 1)) * kD, lane, tt);
+        const float4 tt0 = t4[c0], tt1 = t4[c1];
+        float4 acc0 = b4[c0], acc1 = b4[c1];
 #pragma unroll
-      for (int i = 0; i < kVec; ++i) {
-        v[i].x += tt[i].x;
-        v[i].y += tt[i].y;
-        v[i].z += tt[i].z;
-        v[i].w += tt[i].w;
+        for (int tap = 0; tap < 9; ++tap) {
+          const float4 k0 = w4[tap * (kD / 4) + c0], k1 = w4[tap * (kD / 4) + c1];
+          acc0.x = fmaf(a[tap][0].x, k0.x, acc0.x); acc0.y = fmaf(a[tap][0].y, k0.y, acc0.y);
+          acc0.z = fmaf(a[tap][0].z, k0.z, acc0.z); acc0.w = fmaf(a[tap][0].w, k0.w, acc0.w);
+          acc1.x = fmaf(a[tap][1].x, k1.x, acc1.x); acc1.y = fmaf(a[tap][1].y, k1.y, acc1.y);
+          acc1.z = fmaf(a[tap][1].z, k1.z, acc1.z); acc1.w = fmaf(a[tap][1].w, k1.w, acc1.w);
+        }
+        v[2 * part] = make_float4(acc0.x + tt0.x, acc0.y + tt0.y, acc0.z + tt0.z, acc0.w + tt0.w);
+        v[2 * part + 1] = make_float4(acc1.x + tt1.x, acc1.y + tt1.y, acc1.z + tt1.z, acc1.w + tt1.w);
       }
     }
     layer_norm_row(v, w, b, lane);

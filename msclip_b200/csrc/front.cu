@@ -29,7 +29,7 @@ constexpr int kInPitch = 36;         // staged input columns: ix = 2*ox0 - 4 .. 
 constexpr int kC = 48;               // channels of each first conv and of the bottleneck entry (width / 16)
 constexpr int kW0Pitch = 40;         // op16 per staged row of w0 [96][32]  (80 B: conflict-free ldmatrix)
 constexpr int kW1Pitch = 56;         // op16 per staged row of w1 [48][48]  (112 B)
-constexpr int kStagePitch = 56;      // op16 per staged output pixel        (112 B)
+constexpr int kStagePitch = 48;      // op16 per staged output pixel (dense; 16-byte chunk c of pixel p sits at c ^ ((p >> 2) & 1))
 constexpr int kPoolPitch = 56;       // f32 per staged pooling tap [k*k][48] (224 B: conflict-free 8-byte loads)
 
 constexpr int kOffIn = 0;
@@ -83,19 +83,22 @@ __device__ __forceinline__ float px_to_float(uint16_t v, int dtype) {
 // 1536 contiguous bytes at gdst
 __device__ __forceinline__ void store_row(const float (&acc)[6][4], op16* stage, op16* gdst, int lane) {
   const int g = lane >> 2, t = lane & 3;
+  const int sw = (g >> 2) & 1;  // same for pixels g and g + 8
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    *reinterpret_cast<uint32_t*>(stage + g * kStagePitch + 8 * j + 2 * t) =
+    // dense 96-byte pixels would put pixels g and g + 4 on the same banks; swapping the chunk pairs of every
+    // second group of four pixels keeps both the 4-byte stores and the 16-byte read-back conflict-free
+    *reinterpret_cast<uint32_t*>(stage + g * kStagePitch + 8 * (j ^ sw) + 2 * t) =
         pack16(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f));
-    *reinterpret_cast<uint32_t*>(stage + (g + 8) * kStagePitch + 8 * j + 2 * t) =
+    *reinterpret_cast<uint32_t*>(stage + (g + 8) * kStagePitch + 8 * (j ^ sw) + 2 * t) =
         pack16(fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f));
   }
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const int idx = lane + 32 * i;  // 16 pixels x 6 vectors of 8 channels
+    const int idx = lane + 32 * i;  // 16 pixels x 6 vectors of 8 channels, physical order
     const int px = idx / 6, pc = idx - px * 6;
-    *reinterpret_cast<uint4*>(gdst + idx * 8) = *reinterpret_cast<const uint4*>(stage + px * kStagePitch + pc * 8);
+    *reinterpret_cast<uint4*>(gdst + (px * 6 + (pc ^ ((px >> 2) & 1))) * 8) = *reinterpret_cast<const uint4*>(stage + idx * 8);
   }
   __syncwarp();
 }
@@ -288,12 +291,13 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
     }
     // even pixels of the even row (r = 0) feed the strided shortcut: 8 pixels x 48 channels, contiguous in p0s
     if ((g & 1) == 0) {
+      // staged pixels g/2 (chunks as they are) and g/2 + 4 (chunk pairs swapped, see store_row)
 #pragma unroll
       for (int kk = 0; kk < 3; ++kk) {
         *reinterpret_cast<uint32_t*>(stage + (g >> 1) * kStagePitch + 16 * kk + 2 * t) = a2[0][kk][0];
-        *reinterpret_cast<uint32_t*>(stage + ((g >> 1) + 4) * kStagePitch + 16 * kk + 2 * t) = a2[0][kk][1];
+        *reinterpret_cast<uint32_t*>(stage + ((g >> 1) + 4) * kStagePitch + 16 * kk + 8 + 2 * t) = a2[0][kk][1];
         *reinterpret_cast<uint32_t*>(stage + (g >> 1) * kStagePitch + 16 * kk + 8 + 2 * t) = a2[0][kk][2];
-        *reinterpret_cast<uint32_t*>(stage + ((g >> 1) + 4) * kStagePitch + 16 * kk + 8 + 2 * t) = a2[0][kk][3];
+        *reinterpret_cast<uint32_t*>(stage + ((g >> 1) + 4) * kStagePitch + 16 * kk + 2 * t) = a2[0][kk][3];
       }
     }
     __syncwarp();
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
       op16* gdst = p.p0s + ((static_cast<long long>(b) * (p.Ho / 2) + (oy0 / 2 + warp)) * (p.Wo / 2) + ox0 / 2) * kC;
       for (int idx = lane; idx < 48; idx += 32) {
         const int px = idx / 6, pc = idx - px * 6;
-        *reinterpret_cast<uint4*>(gdst + idx * 8) = *reinterpret_cast<const uint4*>(stage + px * kStagePitch + pc * 8);
+        *reinterpret_cast<uint4*>(gdst + (px * 6 + (pc ^ ((px >> 2) & 1))) * 8) = *reinterpret_cast<const uint4*>(stage + idx * 8);
       }
     }
     __syncwarp();
