@@ -90,15 +90,17 @@ __device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk
         }
       }
     }
-    // mask + chunk max
+    // mask + chunk max.  Key column c = kv0 + 8j + 2t + (e & 1) is live for a row iff c <= min(L - 1, row) (causal) or
+    // c <= L - 1; columns of key groups beyond `ng` lie past that bound as well, so one compare per score suffices:
+    // 8j + (e & 1) <= lim - kv0 - 2t, with the left side a compile-time constant.
+    const int lim_lo = (CAUSAL ? min(L - 1, row_lo) : L - 1) - kv0 - 2 * t;
+    const int lim_hi = (CAUSAL ? min(L - 1, row_hi) : L - 1) - kv0 - 2 * t;
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int col = kv0 + 8 * j + 2 * t + (e & 1);
-        const int row = (e < 2) ? row_lo : row_hi;
-        const bool ok = (j < 2 * ng) && col < L && (!CAUSAL || col <= row);
+        const bool ok = 8 * j + (e & 1) <= ((e < 2) ? lim_lo : lim_hi);
         if (!ok) s[j][e] = -INFINITY;
         mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
       }
@@ -205,6 +207,32 @@ __device__ __forceinline__ void stage_item(const op16* __restrict__ base, long l
   }
 }
 
+// cp.async staging for the persistent kernels: thread -> fixed 16-byte column c = tid & 7, rows tid / 8 + k * (threads / 8);
+// pointers advance by constants, one bounds compare per copy (stage_item spends ~15 index instructions per copy)
+template <int QPAD, int KVPAD, int THREADS>
+__device__ __forceinline__ void stage_item_async(const op16* __restrict__ base, long long pitch, int width, int L, op16* sq,
+                                                 op16* sk, op16* sv) {
+  constexpr int kRowsPerPass = THREADS / 8;
+  static_assert(QPAD % kRowsPerPass == 0 && KVPAD % kRowsPerPass == 0, "row passes must tile the staging buffers");
+  const int c = threadIdx.x & 7;
+  const int r0 = threadIdx.x >> 3;
+  const op16* src = base + r0 * pitch + c * 8;
+  const uint32_t dq = smem_u32(sq + r0 * kLds + c * 8);
+  const uint32_t dk = smem_u32(sk + r0 * kLds + c * 8);
+  const uint32_t dv = smem_u32(sv + r0 * kLds + c * 8);
+#pragma unroll
+  for (int k = 0; k < KVPAD / kRowsPerPass; ++k) {
+    const bool ok = r0 + k * kRowsPerPass < L;
+    const op16* sp = ok ? src + static_cast<long long>(k * kRowsPerPass) * pitch : base;
+    const uint32_t n = ok ? 16u : 0u;
+    const uint32_t off = static_cast<uint32_t>(k * kRowsPerPass * kLds * 2);
+    if (k < QPAD / kRowsPerPass)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dq + off), "l"(sp), "r"(n) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk + off), "l"(sp + width), "r"(n) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv + off), "l"(sp + 2 * width), "r"(n) : "memory");
+  }
+}
+
 // one CTA per (batch, head): used for L = 197, where two staging buffers would not fit next to each other
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
 __global__ void __launch_bounds__(QPAD * 2)
@@ -240,8 +268,8 @@ attention_persistent_kernel(const op16* __restrict__ qkv, op16* __restrict__ out
   if (item >= items) return;
   {
     const int b = item / heads, h = item % heads;
-    stage_item<QPAD, KVPAD>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, buf, buf + QPAD * kLds,
-                            buf + (QPAD + KVPAD) * kLds, true);
+    stage_item_async<QPAD, KVPAD, QPAD * 2>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, buf,
+                                            buf + QPAD * kLds, buf + (QPAD + KVPAD) * kLds);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int it = 0; item < items; item += gridDim.x, ++it) {
@@ -250,8 +278,8 @@ attention_persistent_kernel(const op16* __restrict__ qkv, op16* __restrict__ out
     const int next_item = item + gridDim.x;
     if (next_item < items) {
       const int b = next_item / heads, h = next_item % heads;
-      stage_item<QPAD, KVPAD>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, nxt,
-                              nxt + QPAD * kLds, nxt + (QPAD + KVPAD) * kLds, true);
+      stage_item_async<QPAD, KVPAD, QPAD * 2>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, nxt,
+                                              nxt + QPAD * kLds, nxt + (QPAD + KVPAD) * kLds);
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the prefetch just issued has landed
     } else {
