@@ -6,6 +6,8 @@
  *
  *   msclip_op_gemm            F.linear + fused epilogue             M.py:612, 747, 794-798, 2690, 3074
  *   msclip_op_layernorm       LayerNorm.forward                     M.py:204-219
+ *   msclip_op_gemm_ln         LayerNorm folded into QKV / fc1 and    M.py:204-219 + 612, 747, 794-798
+ *                             emitted by out-proj / fc2
  *   msclip_op_attention       Attention_CUST.forward core           M.py:707-738
  *   msclip_op_im2col_first    gather for the 3x3/s2 first convs     M.py:1952, 2154 (EarlyconvRes / branch)
  *   msclip_op_im2col_nhwc     gather for the later convs            M.py:1920-1936, 1842-1861
@@ -42,6 +44,19 @@ int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m
 /* Tiling of the large GEMMs (N % 256 == 0): 0 = one CTA per 128x256 tile, 1 = CTA pairs (cta_group::2, 256x256),
  * 2 / 4 = clusters of 2 / 4 pairs that share the weight tile by TMA multicast; any other value = library default. */
 void msclip_op_set_gemm_pair_mode(int mode);
+/* LayerNorm (M.py:204-219) folded into the GEMMs around it: LN(x) . W^T + b = rstd * (xc . W'^T - mean_c * colsum) + b'
+ * with xc = x - shift, W' = W diag(gamma), b' = b + W . beta.
+ * Row record = 16 floats: [0] shift, [4 + 2s] / [5 + 2s] = sum / sum of squares of the centred row over 128-column slice s.
+ *   ln_mode 1 (epilogue BF16 or QGELU_BF16): a = bf16(x - shift) [m,k], w = W', bias = b', colsum[n]; records ln_in.
+ *   ln_mode 2 (epilogue RESID_F32, n = 768): out = resid + a . w^T + bias as msclip_op_gemm, and additionally
+ *     out16 = bf16(out - shift') with shift' = row mean of resid (from ln_in), records of out -> ln_out (!= ln_in). */
+int msclip_op_gemm_ln(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, const float* bias, void* out,
+                      int64_t ldo, const float* resid, int64_t ldr, int epilogue, int ln_mode, const float* ln_in,
+                      float* ln_out, void* out16, int64_t ldo16, const float* colsum, void* stream);
+/* w_out[n,k] = bf16(w[n,k] * row_scale[n] * gamma[k]); colsum[n] = sum_k w_out[n,k]; bias_out[n] = row_scale[n] *
+ * (bias[n] + sum_k w[n,k] * beta[k]); row_scale / bias may be NULL. */
+int msclip_op_pack_ln_fold(const float* w, const float* row_scale, const float* gamma, const float* beta, const float* bias,
+                           void* w_out_bf16, float* colsum, float* bias_out, int n, int k, void* stream);
 /* y[r,:] (bf16) = LN(x[r*row_stride,:]) over 768 columns, eps 1e-12 inside the sqrt. */
 int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
                         void* stream);

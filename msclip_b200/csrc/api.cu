@@ -184,6 +184,17 @@ int msclip_op_gemm(const void* a, int64_t lda, const void* w, int64_t ldw, int m
                             out, ldo, resid, ldr, epilogue, as_stream(stream));
 }
 void msclip_op_set_gemm_pair_mode(int enable) { gemm_set_pair_mode(enable); }
+int msclip_op_gemm_ln(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, const float* bias, void* out,
+                      int64_t ldo, const float* resid, int64_t ldr, int epilogue, int ln_mode, const float* ln_in,
+                      float* ln_out, void* out16, int64_t ldo16, const float* colsum, void* stream) {
+  return launch_gemm_ln(static_cast<const op16*>(a), lda, static_cast<const op16*>(w), ldw, m, n, k, bias, out, ldo, resid, ldr,
+                        epilogue, ln_mode, ln_in, ln_out, static_cast<op16*>(out16), ldo16, colsum, as_stream(stream));
+}
+int msclip_op_pack_ln_fold(const float* w, const float* row_scale, const float* gamma, const float* beta, const float* bias,
+                           void* w_out_bf16, float* colsum, float* bias_out, int n, int k, void* stream) {
+  return launch_pack_ln_fold(w, row_scale, gamma, beta, bias, static_cast<op16*>(w_out_bf16), colsum, bias_out, n, k,
+                             as_stream(stream));
+}
 int msclip_op_layernorm(const float* x, int row_stride, const float* w, const float* b, void* y_bf16, int rows,
                         void* stream) {
   return launch_layernorm_op16(x, row_stride, w, b, static_cast<op16*>(y_bf16), rows, as_stream(stream));
@@ -224,7 +235,7 @@ int msclip_op_front_conv(const void* img, int dtype, int batch, int height, int 
 }
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                               const float* b, float* x_out, int batch, int grid, void* stream) {
-  return launch_adapter_fuse_ln(x, t, dw_w9, dw_bias, w, b, x_out, batch, grid, as_stream(stream));
+  return launch_adapter_fuse_ln(x, t, dw_w9, dw_bias, w, b, x_out, batch, grid, nullptr, nullptr, as_stream(stream));
 }
 int msclip_op_contrastive_lse(const void* img_bf16, const void* txt_bf16, int b, float scale, void* workspace,
                               float* parts2, void* stream) {

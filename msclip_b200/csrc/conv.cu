@@ -127,6 +127,32 @@ pack_op16_kernel(const float* __restrict__ src, long long sn, long long sk, cons
   }
 }
 
+// LN fold: one warp per weight row n.  dst[n][k] = op16(src[n][k] * rs[n] * gamma[k]); colsum[n] = sum_k dst[n][k] (of
+// the rounded values, which is what the MMA will see); bias_out[n] = rs[n] * (bias[n] + sum_k src[n][k] * beta[k])
+__global__ void __launch_bounds__(256)
+pack_ln_fold_kernel(const float* __restrict__ src, const float* __restrict__ row_scale, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ bias, op16* __restrict__ dst,
+                    float* __restrict__ colsum, float* __restrict__ bias_out, int N, int K) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float rs = row_scale ? row_scale[n] : 1.0f;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = src[static_cast<long long>(n) * K + k];
+    const op16 q = to_op16(w * rs * gamma[k]);
+    dst[static_cast<long long>(n) * K + k] = q;
+    cs += op16_to_float(q);
+    bb = fmaf(w, beta[k], bb);
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_out[n] = rs * ((bias ? bias[n] : 0.f) + bb);
+  }
+}
+
 inline int flat_grid(long long total) {
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 32;
@@ -165,6 +191,14 @@ int launch_patch_pool(const op16* in, int batch, int H, int W, int cpix, int c_o
   MSCLIP_REQUIRE(H % k == 0 && W % k == 0, "patch_pool: kernel must tile the feature map");
   const long long total = static_cast<long long>(batch) * (H / k) * (W / k) * (C / 8);
   patch_pool_kernel<<<flat_grid(total), 256, 0, stream>>>(in, H, W, cpix, c_off, C, k, w, bias, out, total);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_ln_fold(const float* src, const float* row_scale, const float* gamma, const float* beta, const float* bias,
+                        op16* dst, float* colsum, float* bias_out, int N, int K, cudaStream_t stream) {
+  if (N <= 0 || K <= 0) return 0;
+  pack_ln_fold_kernel<<<(N + 7) / 8, 256, 0, stream>>>(src, row_scale, gamma, beta, bias, dst, colsum, bias_out, N, K);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -62,6 +62,28 @@ __device__ __forceinline__ void store_row_f32(float* __restrict__ dst, int lane,
   for (int i = 0; i < kVec; ++i) d4[lane + 32 * i] = v[i];
 }
 
+// LN fold (gemm_common.cuh): centred 16-bit copy of a freshly produced residual row and its record -
+// shift = exact row mean, slice 0 = (sum, sum of squares) of the centred row, slices 1..5 empty
+__device__ __forceinline__ void emit_centred_row(const float4 (&v)[kVec], int lane, op16* __restrict__ xc,
+                                                 float* __restrict__ rec) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float4 c[kVec];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    c[i] = make_float4(v[i].x - mean, v[i].y - mean, v[i].z - mean, v[i].w - mean);
+    s1 += (c[i].x + c[i].y) + (c[i].z + c[i].w);
+    s2 += (c[i].x * c[i].x + c[i].y * c[i].y) + (c[i].z * c[i].z + c[i].w * c[i].w);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  store_row_bf16(xc, lane, c);
+  if (lane < kLnRecordFloats) rec[lane] = lane == 0 ? mean : (lane == 4 ? s1 : (lane == 5 ? s2 : 0.f));
+}
+
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 layernorm_kernel(const float* __restrict__ x, int row_stride, const float* __restrict__ w,
                       const float* __restrict__ b, op16* __restrict__ y, int rows) {
@@ -109,7 +131,8 @@ eot_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ to
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 text_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb, const float* __restrict__ pos,
-                  float* __restrict__ x, long long rows, int L, int vocab, int* __restrict__ err) {
+                  float* __restrict__ x, long long rows, int L, int vocab, int* __restrict__ err, op16* __restrict__ xc,
+                  float* __restrict__ rec) {
   const int lane = threadIdx.x & 31;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
        r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
@@ -130,13 +153,14 @@ text_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb
       v[i].w += p[i].w;
     }
     store_row_f32(x + r * kD, lane, v);
+    if (xc != nullptr) emit_centred_row(v, lane, xc + r * kD, rec + r * kLnRecordFloats);
   }
 }
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 image_embed_ln_pre_kernel(const float* __restrict__ grid, const float* __restrict__ cls, const float* __restrict__ pos,
                           const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ x,
-                          long long rows, int L) {
+                          long long rows, int L, op16* __restrict__ xc, float* __restrict__ rec) {
   const int lane = threadIdx.x & 31;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
        r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
@@ -154,6 +178,7 @@ image_embed_ln_pre_kernel(const float* __restrict__ grid, const float* __restric
     }
     layer_norm_row(v, w, b, lane);
     store_row_f32(x + r * kD, lane, v);
+    if (xc != nullptr) emit_centred_row(v, lane, xc + r * kD, rec + r * kLnRecordFloats);
   }
 }
 
@@ -161,7 +186,7 @@ image_embed_ln_pre_kernel(const float* __restrict__ grid, const float* __restric
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ dw_w9,
                        const float* __restrict__ dw_bias, const float* __restrict__ w, const float* __restrict__ b,
-                       float* __restrict__ x_out, long long rows, int g) {
+                       float* __restrict__ x_out, long long rows, int g, op16* __restrict__ xc, float* __restrict__ rec) {
   const int lane = threadIdx.x & 31;
   const int L = g * g + 1;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
@@ -216,6 +241,7 @@ adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t,
     }
     layer_norm_row(v, w, b, lane);
     store_row_f32(x_out + r * kD, lane, v);
+    if (xc != nullptr) emit_centred_row(v, lane, xc + r * kD, rec + r * kLnRecordFloats);
   }
 }
 
@@ -284,12 +310,13 @@ static int* token_error_flag() {
 }
 
 int launch_text_embed(const int64_t* tok, const float* tok_emb, const float* pos, float* x, int batch, int L,
-                      int vocab, cudaStream_t stream) {
+                      int vocab, op16* xc, float* rec, cudaStream_t stream) {
   if (batch <= 0) return 0;
   int* flag = token_error_flag();
   MSCLIP_REQUIRE(flag != nullptr, "cudaMalloc of the token error flag failed");
   const long long rows = static_cast<long long>(batch) * L;
-  text_embed_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(tok, tok_emb, pos, x, rows, L, vocab, flag);
+  text_embed_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(tok, tok_emb, pos, x, rows, L, vocab, flag, xc,
+                                                                       xc ? rec : nullptr);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -309,20 +336,21 @@ int check_token_error(cudaStream_t stream) {
 }
 
 int launch_image_embed_ln_pre(const float* grid, const float* cls, const float* pos, const float* w, const float* b,
-                              float* x, int batch, int L, cudaStream_t stream) {
+                              float* x, int batch, int L, op16* xc, float* rec, cudaStream_t stream) {
   if (batch <= 0) return 0;
   const long long rows = static_cast<long long>(batch) * L;
-  image_embed_ln_pre_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(grid, cls, pos, w, b, x, rows, L);
+  image_embed_ln_pre_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(grid, cls, pos, w, b, x, rows, L, xc, rec);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
-                           const float* b, float* x_out, int batch, int g, cudaStream_t stream) {
+                           const float* b, float* x_out, int batch, int g, op16* xc, float* rec, cudaStream_t stream) {
   if (batch <= 0) return 0;
   MSCLIP_REQUIRE(x != x_out, "adapter tail cannot run in place (3x3 neighbourhood reads)");
   const long long rows = static_cast<long long>(batch) * (g * g + 1);
-  adapter_fuse_ln_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, t, dw_w9, dw_bias, w, b, x_out, rows, g);
+  adapter_fuse_ln_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, t, dw_w9, dw_bias, w, b, x_out, rows, g, xc,
+                                                                            rec);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

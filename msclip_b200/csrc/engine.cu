@@ -193,6 +193,19 @@ struct Packer {
     if (d && launch_pack_op16(t.dev, 1, N, nullptr, d, K, N, K, stream)) rc = 1;
     return d;
   }
+  // W [N,K] with LayerNorm `ln` in front of it -> W * diag(gamma) (op16), its column sums, bias + W . beta
+  void ln_fold(const std::string& wk, const std::string& bk, const float* row_scale, const std::string& ln, op16** w_out,
+               float** cs_out, float** b_out) {
+    const RawTensor& t = raw(wk);
+    const int N = static_cast<int>(t.shape[0]), K = static_cast<int>(t.shape[1]);
+    *w_out = static_cast<op16*>(dalloc(static_cast<size_t>(N) * K * 2));
+    *cs_out = static_cast<float*>(dalloc(static_cast<size_t>(N) * 4));
+    *b_out = static_cast<float*>(dalloc(static_cast<size_t>(N) * 4));
+    if (*w_out && *cs_out && *b_out &&
+        launch_pack_ln_fold(t.dev, row_scale, raw(ln + ".weight").dev, raw(ln + ".bias").dev, raw(bk).dev, *w_out, *cs_out,
+                            *b_out, N, K, stream))
+      rc = 1;
+  }
   // eval-mode BatchNorm as per-channel scale / shift
   void bn(const std::string& p, float eps, std::vector<float>& scale, std::vector<float>& shift) {
     const std::vector<float> g = host(p + ".weight"), b = host(p + ".bias"), m = host(p + ".running_mean"),
@@ -241,6 +254,10 @@ static void pack_block(Packer& P, const std::string& p, BlockWeights& bw, const 
   bw.ln1_b = P.keep_f32(p + ".ln_1.bias");
   bw.ln2_w = P.keep_f32(p + ".ln_2.weight");
   bw.ln2_b = P.keep_f32(p + ".ln_2.bias");
+  // LN fold: this tower's gamma / beta folded into its own copies of the QKV and fc1 weights
+  P.ln_fold(p + ".attn.in_proj_weight", p + ".attn.in_proj_bias", qscale_dev, p + ".ln_1", &bw.w_qkv_ln, &bw.cs_qkv,
+            &bw.b_qkv_ln);
+  P.ln_fold(p + ".mlp.c_fc.weight", p + ".mlp.c_fc.bias", nullptr, p + ".ln_2", &bw.w_fc1_ln, &bw.cs_fc1, &bw.b_fc1_ln);
 }
 
 int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
@@ -520,10 +537,32 @@ static int ensure_xchg(msclip_ctx* h, int batch) {
 }
 
 // ------------------------------------------------------------------------------------ shared block
+// MSCLIP_LN_FOLD=1 folds the LayerNorms in front of QKV / fc1 into the GEMM epilogues (gemm_common.cuh).  Correct and
+// parity-tested, but the GEMMs of this path are epilogue-bound: the extra epilogue work costs more (QKV +15 %,
+// fc1 +17 %, out-proj +43 %, fc2 +24 %) than the 47 LayerNorm launches it removes (8.2 ms), so it stays off.
+static const bool g_ln_fold = [] {
+  const char* e = getenv("MSCLIP_LN_FOLD");
+  return e != nullptr && e[0] == '1';
+}();
+
+// rec: the two row-record buffers of the LN fold; rec[0] describes x on entry and on return (hbuf = centred copy of x)
 static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, op16* hbuf,
-                     op16* qkv, op16* attn, op16* fc1, cudaStream_t s) {
+                     op16* qkv, op16* attn, op16* fc1, float** rec, cudaStream_t s) {
   const int w = h->cfg.width;
   const int M = batch * L;
+  if (g_ln_fold) {
+    MSCLIP_TRY(launch_gemm_ln(hbuf, w, bw.w_qkv_ln, w, M, 3 * w, w, bw.b_qkv_ln, qkv, 3 * w, nullptr, 0, EPI_BF16, 1, rec[0],
+                              nullptr, nullptr, 0, bw.cs_qkv, s));
+    MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
+    MSCLIP_TRY(launch_gemm_ln(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, x, w, EPI_RESID_F32, 2, rec[0], rec[1], hbuf, w,
+                              nullptr, s));
+    MSCLIP_TRY(launch_gemm_ln(hbuf, w, bw.w_fc1_ln, w, M, 4 * w, w, bw.b_fc1_ln, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, 1,
+                              rec[1], nullptr, nullptr, 0, bw.cs_fc1, s));
+    MSCLIP_TRY(launch_gemm_ln(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, x, w, EPI_RESID_F32, 2, rec[1], rec[0],
+                              hbuf, w, nullptr, s));
+    count_launch(5);
+    return 0;
+  }
   MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
   MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, qkv, 3 * w, nullptr, 0, EPI_BF16, s));
   MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
@@ -726,12 +765,16 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   WS(fc1, op16, "fc1", Mmax * 4 * w);
   WS(pool_ln, op16, "pool_ln", static_cast<size_t>(tb) * w);
   WS(feat_raw, float, "feat_raw", static_cast<size_t>(tb) * c.embed_dim);
+  WS(rec0, float, "ln_rec0", Mmax * kLnRecordFloats);
+  WS(rec1, float, "ln_rec1", Mmax * kLnRecordFloats);
+  float* rec[2] = {rec0, rec1};
+  op16* const xcen = g_ln_fold ? hbuf : nullptr;  // centred 16-bit copy of x for the LN fold
   for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
     const int nb = std::min(kTowerChunk, batch - b0);
     float* xc = x;
     float* xo = x2;
     float* gt = gridtmp + static_cast<size_t>(b0) * g * g * w;
-    MSCLIP_TRY(launch_image_embed_ln_pre(gt, h->cls, h->vpos, h->ln_pre_w, h->ln_pre_b, xc, nb, L, s));
+    MSCLIP_TRY(launch_image_embed_ln_pre(gt, h->cls, h->vpos, h->ln_pre_w, h->ln_pre_b, xc, nb, L, xcen, rec[0], s));
     count_launch(1);
     for (int idx = 1; idx < c.layers; ++idx) {
       for (int j = 0; j < n_active; ++j) {
@@ -740,11 +783,11 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         // t = pw_conv(BN(dw_conv(top)))  (M.py:1756-1759); the stem output in gridtmp is dead by now
         MSCLIP_TRY(launch_gemm(pooled[j] + static_cast<size_t>(b0) * g * g * a.C, a.C, a.pw, a.C, nb * g * g, w, a.C,
                                nullptr, gt, w, nullptr, 0, EPI_F32, s));
-        MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, s));
+        MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, xcen, rec[0], s));
         count_launch(2);
         std::swap(xc, xo);
       }
-      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, s));
+      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, rec, s));
     }
     // CLS -> ln_post -> proj -> L2 norm (M.py:2685-2690, 2982-2983)
     MSCLIP_TRY(launch_layernorm_op16(xc, L, h->ln_post_w, h->ln_post_b, pool_ln, nb, s));
@@ -771,12 +814,16 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_d
   WS(fc1, op16, "fc1", Mmax * 4 * w);
   WS(pool_ln, op16, "pool_ln", static_cast<size_t>(tb) * w);
   WS(feat_raw, float, "feat_raw", static_cast<size_t>(tb) * c.embed_dim);
+  WS(rec0, float, "ln_rec0", Mmax * kLnRecordFloats);
+  WS(rec1, float, "ln_rec1", Mmax * kLnRecordFloats);
+  float* rec[2] = {rec0, rec1};
   for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
     const int nb = std::min(kTowerChunk, batch - b0);
     const int64_t* tk = tok + static_cast<size_t>(b0) * L;
-    MSCLIP_TRY(launch_text_embed(tk, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, s));
+    MSCLIP_TRY(launch_text_embed(tk, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0], s));
     count_launch(1);
-    for (int idx = 0; idx < c.layers; ++idx) MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, s));
+    for (int idx = 0; idx < c.layers; ++idx)
+      MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, rec, s));
     MSCLIP_TRY(launch_eot_layernorm_op16(x, tk, L, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->tproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));

@@ -30,6 +30,10 @@ struct BlockWeights {
   op16 *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
   float *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+  // LN fold (gemm_common.cuh): weights with ln_1 / ln_2 gamma folded in (per tower: the LayerNorms are not shared),
+  // their column sums and the biases with W . beta added
+  op16 *w_qkv_ln = nullptr, *w_fc1_ln = nullptr;
+  float *cs_qkv = nullptr, *cs_fc1 = nullptr, *b_qkv_ln = nullptr, *b_fc1_ln = nullptr;
 };
 
 struct ConvWeights {

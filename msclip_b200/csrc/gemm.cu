@@ -45,8 +45,11 @@ struct GemmCfg {
 // per CTA cuts the L2 -> SM operand traffic per flop by a third and deepens the smem ring from 4 to 6 stages.
 // NP > 1 (CG = 2 only): NP CTA pairs form one cluster and work on NP vertically adjacent 256-row tiles of the
 // same column tile; every W slice is fetched from L2 once and TMA-multicast to the NP CTAs that need it.
-template <int BN, int EPI, int CG, int NP>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// LN = 1 / 2: LayerNorm folding, see gemm_common.cuh (consume in the epilogue of QKV / fc1, emit from out-proj / fc2)
+// NE = number of epilogue warps (a multiple of 4: NE / 4 warps share each TMEM lane quarter and split the tile's column
+// chunks between them); 8 by default, 12 / 16 selectable for the CTA-pair tiles (see g_epi_warps below).
+template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8>
+__global__ void __launch_bounds__(128 + 32 * NE, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
   using Cfg = GemmCfg<BN, CG>;
@@ -80,7 +83,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kNumEpilogueWarps * CG);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&tempty_bar[i], NE * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
@@ -177,10 +180,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= 4) {
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;    // which half of the tile's column chunks this warp drains
-    constexpr int kPerHalf = (Cfg::kNumChunks + 1) / 2;
+    const int half = (warp - 4) >> 2;    // which share of the tile's column chunks this warp drains
+    constexpr int kParts = NE / 4;
+    // more epilogue warps run under a tighter register cap: they drain the tile in 16-column pieces
+    constexpr int kCh = (NE > 8 && Cfg::kChunk == 32) ? 16 : Cfg::kChunk;
+    constexpr int kNumCh = BN / kCh;
+    static_assert(NE % 4 == 0 && kParts >= 1 && (LN != 2 || kParts == 2), "LN emit slots assume two column halves per tile");
+    constexpr int kPerHalf = (kNumCh + kParts - 1) / kParts;
     const int c_begin = half * kPerHalf;
-    const int c_end = (c_begin + kPerHalf < Cfg::kNumChunks) ? c_begin + kPerHalf : Cfg::kNumChunks;
+    const int c_end = (c_begin + kPerHalf < kNumCh) ? c_begin + kPerHalf : kNumCh;
     int as = 0;
     uint32_t aph = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
@@ -192,17 +200,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // while the MMAs run, so the epilogue's loads see L2 latency instead of DRAM latency
         const int prow = m0 + q * 32 + lane;
         if (prow < p.M) {
-          const float* rp = p.resid + static_cast<long long>(prow) * p.ldr + n0 + c_begin * Cfg::kChunk;
+          const float* rp = p.resid + static_cast<long long>(prow) * p.ldr + n0 + c_begin * kCh;
 #pragma unroll
           for (int i = 0; i < kPerHalf; ++i)
-            if (c_begin + i < c_end && n0 + (c_begin + i + 1) * Cfg::kChunk <= p.N)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + i * Cfg::kChunk));
+            if (c_begin + i < c_end && n0 + (c_begin + i + 1) * kCh <= p.N)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + i * kCh));
+        }
+      }
+      const int row = m0 + q * 32 + lane;
+      // LN fold: the row records are fetched while the MMAs of this tile still run (an L2 round trip on the
+      // epilogue's critical path costs the short-K GEMMs ~15 %)
+      LnRow lnr = {0.f, 1.f};
+      LnEmit lne = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (LN == 1 && row < p.M) {
+        float sh;
+        ln_load_record(p.ln_in + static_cast<long long>(row) * kLnRec, 1.0f / static_cast<float>(p.K), sh, lnr.mean_c, lnr.rstd);
+      }
+      if (LN == 2) {
+        // new shift of a row = its mean before this update (from the record of the residual input)
+        const int row_e = row & ~1, row_o = row | 1;
+        float mc, rs;
+        if (row_e < p.M) {
+          ln_load_record(p.ln_in + static_cast<long long>(row_e) * kLnRec, 1.0f / static_cast<float>(p.N), lne.shift_e, mc, rs);
+          lne.shift_e += mc;
+        }
+        if (row_o < p.M) {
+          ln_load_record(p.ln_in + static_cast<long long>(row_o) * kLnRec, 1.0f / static_cast<float>(p.N), lne.shift_o, mc, rs);
+          lne.shift_o += mc;
         }
       }
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      const int row = m0 + q * 32 + lane;
       GemmParams pt = p;  // per-tile view: with split outputs every column tile owns its own [M, BN] matrix
       if (p.split_stride != 0) {
         const long long shift = static_cast<long long>(tile % p.tiles_n) * p.split_stride - n0;
@@ -212,19 +241,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // software pipeline: the TMEM load of chunk c+1 and the global operands of chunk c are in flight while
       // chunk c is converted and stored (tcgen05.wait::ld waits for every outstanding load, so the next load
       // is issued right after the wait)
-      uint32_t acc[2][Cfg::kChunk];
-      tmem_ld_chunk<Cfg::kChunk>(taddr + c_begin * Cfg::kChunk, acc[0]);
+      uint32_t acc[2][kCh];
+      tmem_ld_chunk<kCh>(taddr + c_begin * kCh, acc[0]);
 #pragma unroll
       for (int i = 0; i < kPerHalf; ++i) {
         const int c = c_begin + i;
         if (c < c_end) {
-          const int col0 = n0 + c * Cfg::kChunk;
-          const bool fast = p.vec_ok && (col0 + Cfg::kChunk <= p.N);
-          EpiOperands<EPI, Cfg::kChunk> ops;
-          epilogue_prefetch<EPI, Cfg::kChunk>(ops, pt, row, col0, fast);
+          const int col0 = n0 + c * kCh;
+          const bool fast = p.vec_ok && (col0 + kCh <= p.N);
+          EpiOperands<EPI, kCh, LN> ops;
+          epilogue_prefetch<EPI, kCh, LN>(ops, pt, row, col0, fast);
           tmem_ld_wait();
-          if (c + 1 < c_end) tmem_ld_chunk<Cfg::kChunk>(taddr + (c + 1) * Cfg::kChunk, acc[(i + 1) & 1]);
-          epilogue_store<EPI, Cfg::kChunk>(acc[i & 1], ops, pt, row, col0, fast);
+          if (c + 1 < c_end) tmem_ld_chunk<kCh>(taddr + (c + 1) * kCh, acc[(i + 1) & 1]);
+          epilogue_store<EPI, kCh, LN>(acc[i & 1], ops, pt, row, col0, fast, lnr, &lne);
+        }
+      }
+      if (LN == 2) {
+        // row sums of this 128-column slice: the two lanes of a pair hold complementary pieces of both rows
+        lne.s1e += __shfl_xor_sync(0xffffffffu, lne.s1e, 1);
+        lne.s2e += __shfl_xor_sync(0xffffffffu, lne.s2e, 1);
+        lne.s1o += __shfl_xor_sync(0xffffffffu, lne.s1o, 1);
+        lne.s2o += __shfl_xor_sync(0xffffffffu, lne.s2o, 1);
+        const bool odd = (lane & 1) != 0;
+        const int r = odd ? (row | 1) : (row & ~1);
+        if (r < p.M) {
+          const int slot = (tile % p.tiles_n) * 2 + half;
+          float* rec = p.ln_out + static_cast<long long>(r) * kLnRec;
+          *reinterpret_cast<float2*>(rec + 4 + 2 * slot) = odd ? make_float2(lne.s1o, lne.s2o) : make_float2(lne.s1e, lne.s2e);
+          if (slot == 0) rec[0] = odd ? lne.shift_o : lne.shift_e;
         }
       }
       tc_fence_before();
@@ -244,12 +288,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN, int EPI, int CG, int NP>
+template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG, NP>,
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG, NP, LN, NE>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
@@ -257,7 +301,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   const int n = p.total_tiles < units ? p.total_tiles : units;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n * CG * NP);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(128 + 32 * NE);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -267,12 +311,37 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG, NP>, ta, tb, p));
+  MSCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG, NP, LN, NE>, ta, tb, p));
   return 0;
 }
 
+// MSCLIP_GEMM_EPI_WARPS = 8 | 12 | 16: epilogue warps of the CTA-pair tiles (16 = 16 for the 16-bit epilogues and 12 for
+// the fp32 residual epilogue).  Measured on the text-tower shapes (profiles/r01_kernel_bench.md): 8 warps draining
+// 32-column pieces are as fast or faster (QKV 1330 / 1314 / 1292, fc1 1244 / 1224 / 1267, fc2 1365 / 1277 / 1278 TFLOP/s
+// with 8 / 12 / 16 warps), so 8 stays the default and the wider variants are kept for A/B runs only.
+static const int g_epi_warps = [] {
+  const char* e = getenv("MSCLIP_GEMM_EPI_WARPS");
+  const int v = e ? atoi(e) : 8;
+  return (v == 8 || v == 12 || v == 16) ? v : 8;
+}();
+
 template <int BN, int CG, int NP>
 int launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int epi, cudaStream_t stream) {
+  if constexpr (BN == 256 && CG == 2 && NP == 1) {
+    if (g_epi_warps == 16) {
+      switch (epi) {
+        case EPI_BF16: return launch_variant<BN, EPI_BF16, CG, NP, 0, 16>(ta, tb, p, stream);
+        case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16, CG, NP, 0, 16>(ta, tb, p, stream);
+        case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32, CG, NP, 0, 12>(ta, tb, p, stream);
+      }
+    } else if (g_epi_warps == 12) {
+      switch (epi) {
+        case EPI_BF16: return launch_variant<BN, EPI_BF16, CG, NP, 0, 12>(ta, tb, p, stream);
+        case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16, CG, NP, 0, 12>(ta, tb, p, stream);
+        case EPI_RESID_F32: return launch_variant<BN, EPI_RESID_F32, CG, NP, 0, 12>(ta, tb, p, stream);
+      }
+    }
+  }
   switch (epi) {
     case EPI_BF16: return launch_variant<BN, EPI_BF16, CG, NP>(ta, tb, p, stream);
     case EPI_QGELU_BF16: return launch_variant<BN, EPI_QGELU_BF16, CG, NP>(ta, tb, p, stream);
@@ -329,6 +398,58 @@ int launch_gemm_split(const op16* A, int64_t lda, const op16* W, int64_t ldw, in
   return launch_gemm_impl(A, lda, W, ldw, M, N, K, 1.0f, bias, out, split_cols, nullptr, 0, epi, split_cols, stream);
 }
 
+int launch_gemm_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, void* out,
+                   int64_t ldo, const float* resid, int64_t ldr, int epi, int ln_mode, const float* ln_in, float* ln_out,
+                   op16* out16, int64_t ldo16, const float* colsum, cudaStream_t stream) {
+  MSCLIP_REQUIRE(M > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "launch_gemm_ln: bad operand shapes");
+  MSCLIP_REQUIRE(ln_mode == 1 || ln_mode == 2, "launch_gemm_ln: mode must be 1 (consume) or 2 (emit)");
+  MSCLIP_REQUIRE(N % 256 == 0 && ln_in != nullptr && (reinterpret_cast<uintptr_t>(ln_in) & 15) == 0,
+                 "launch_gemm_ln: N must be a multiple of 256 and the row records 16-byte aligned");
+  const bool f32_out = epi == EPI_RESID_F32;
+  if (ln_mode == 1) {
+    MSCLIP_REQUIRE((epi == EPI_BF16 || epi == EPI_QGELU_BF16) && colsum != nullptr && (reinterpret_cast<uintptr_t>(colsum) & 15) == 0,
+                   "launch_gemm_ln: consume mode needs a 16-bit epilogue and the column sums of the folded weight");
+  } else {
+    MSCLIP_REQUIRE(epi == EPI_RESID_F32 && N == 128 * kLnSlots && resid != nullptr && ln_out != nullptr && out16 != nullptr &&
+                       ln_out != ln_in && ldr % 4 == 0 && ldo16 % 4 == 0 && (reinterpret_cast<uintptr_t>(resid) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(out16) & 7) == 0 && (reinterpret_cast<uintptr_t>(ln_out) & 15) == 0,
+                   "launch_gemm_ln: emit mode needs the residual epilogue, N = 768 and separate in / out row records");
+  }
+  MSCLIP_REQUIRE(ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                     (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+                 "launch_gemm_ln: output rows and bias must be 16-byte aligned");
+  const int cg = (g_pair_mode >= 1 && M >= 256) ? 2 : 1;
+  CUtensorMap ta, tb;
+  MSCLIP_TRY(make_tmap_op16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM));
+  MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+                               static_cast<uint32_t>(256 / cg)));
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.tiles_n = N / 256;
+  p.alpha = 1.0f;
+  p.vec_ok = 1;
+  p.split_stride = 0;
+  p.total_tiles = ((M + kBM * cg - 1) / (kBM * cg)) * p.tiles_n;
+  p.bias = bias;
+  p.out = out;
+  p.resid = resid;
+  p.ldo = ldo;
+  p.ldr = ldr;
+  p.ln_in = ln_in;
+  p.ln_out = ln_out;
+  p.out16 = out16;
+  p.ldo16 = ldo16;
+  p.colsum = colsum;
+  if (ln_mode == 2) return cg == 2 ? launch_variant<256, EPI_RESID_F32, 2, 1, 2>(ta, tb, p, stream)
+                                   : launch_variant<256, EPI_RESID_F32, 1, 1, 2>(ta, tb, p, stream);
+  if (epi == EPI_BF16) return cg == 2 ? launch_variant<256, EPI_BF16, 2, 1, 1>(ta, tb, p, stream)
+                                      : launch_variant<256, EPI_BF16, 1, 1, 1>(ta, tb, p, stream);
+  return cg == 2 ? launch_variant<256, EPI_QGELU_BF16, 2, 1, 1>(ta, tb, p, stream)
+                 : launch_variant<256, EPI_QGELU_BF16, 1, 1, 1>(ta, tb, p, stream);
+}
+
 static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                             const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
                             int split_cols, cudaStream_t stream) {
@@ -349,7 +470,7 @@ static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t l
                                kBM));
   MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
                                static_cast<uint32_t>(bn / cg / np)));
-  GemmParams p;
+  GemmParams p = {};
   p.M = M;
   p.N = N;
   p.K = K;

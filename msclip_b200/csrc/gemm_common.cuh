@@ -24,7 +24,44 @@ struct GemmParams {
   float alpha;  // acc is scaled by alpha before the bias (similarity logits: exp(logit_scale))
   int vec_ok;   // rows of out / resid keep 16-byte alignment -> vector stores
   long long split_stride;  // != 0: column tile j writes a separate [M, BN] matrix at out + j * split_stride (elements)
+  // LayerNorm folded into the GEMMs around it (kernel template parameter LN, see below)
+  const float* ln_in;    // LN = 1: row records of A's rows; LN = 2: records of the residual input (its mean = new shift)
+  float* ln_out;         // LN = 2: row records of the new residual stream
+  op16* out16;           // LN = 2: op16(x_new - shift), the next GEMM's A operand, pitch ldo16
+  const float* colsum;   // LN = 1: sum_k W'[n][k] of the packed (gamma-folded) weight
+  long long ldo16;
 };
+
+// ---- LayerNorm folding --------------------------------------------------------------------------------------
+// LN(x) . W^T + b  ==  rstd * (xc . W'^T - mean_c * colsum(W')) + b'   with  xc = x - shift (any per-row shift),
+// mean_c = mean(xc), rstd = 1 / sqrt(var(xc) + eps), W' = W * diag(gamma), b' = b + W . beta.
+// The GEMM that produces the residual stream (LN = 2: out-proj, fc2) therefore also emits op16(x - shift) and a
+// 64-byte record per row - the shift (mean of the row before this update, so the centred values stay small and
+// the 16-bit rounding error does not grow with a common-mode offset) and (sum, sum of squares) of the centred
+// values per 128-column slice - and the GEMM that consumes LN(x) (LN = 1: QKV, fc1) reads the centred rows as its A
+// operand and finishes the normalisation in its epilogue.  The separate LayerNorm pass over the fp32 stream
+// (6 bytes per element, 47 launches per step) disappears.
+constexpr int kLnRec = 16;    // floats per row record: [0] shift, [4 + 2*slot] sum, [5 + 2*slot] sum of squares
+constexpr int kLnSlots = 6;   // slot = 256-column tile * 2 + epilogue half (N = 768)
+constexpr float kLnEps = 1e-12f;  // inside the sqrt (M.py:217)
+
+struct LnRow {   // LN = 1: statistics of this thread's row
+  float mean_c, rstd;
+};
+struct LnEmit {  // LN = 2: running sums of the two rows of the lane pair (pieces held after the swap)
+  float shift_e, shift_o, s1e, s2e, s1o, s2o;
+};
+
+__device__ __forceinline__ void ln_load_record(const float* rec, float inv_width, float& shift, float& mean_c, float& rstd) {
+  const float4* r4 = reinterpret_cast<const float4*>(rec);
+  const float4 a = __ldg(r4), b = __ldg(r4 + 1), c = __ldg(r4 + 2), d = __ldg(r4 + 3);
+  shift = a.x;
+  const float s1 = (b.x + b.z) + (c.x + c.z) + (d.x + d.z);
+  const float s2 = (b.y + b.w) + (c.y + c.w) + (d.y + d.w);
+  mean_c = s1 * inv_width;
+  const float var = fmaxf(s2 * inv_width - mean_c * mean_c, 0.f);
+  rstd = 1.0f / sqrtf(var + kLnEps);
+}
 
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x)   (M.py:224)
@@ -41,17 +78,23 @@ __device__ __forceinline__ float quick_gelu(float x) {
 
 // Operands the epilogue needs from global memory for one chunk (bias slice, residual pieces in the swapped
 // layout); fetched before the accumulator chunk is waited for so their latency overlaps the TMEM load.
-template <int EPI, int CH>
+template <int EPI, int CH, int LN = 0>
 struct EpiOperands {
   float4 bias[CH / 4];
   float4 resid_even[(EPI == EPI_RESID_F32) ? CH / 8 : 1];  // even row of the lane pair, pieces 2j + (lane & 1)
   float4 resid_odd[(EPI == EPI_RESID_F32) ? CH / 8 : 1];   // odd row of the lane pair
+  float4 colsum[(LN == 1) ? CH / 4 : 1];
 };
 
-template <int EPI, int CH>
-__device__ __forceinline__ void epilogue_prefetch(EpiOperands<EPI, CH>& o, const GemmParams& p, int row, int col0,
+template <int EPI, int CH, int LN = 0>
+__device__ __forceinline__ void epilogue_prefetch(EpiOperands<EPI, CH, LN>& o, const GemmParams& p, int row, int col0,
                                                   bool fast) {
   if (!fast) return;
+  if (LN == 1) {
+    const float4* c4 = reinterpret_cast<const float4*>(p.colsum + col0);
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) o.colsum[j] = __ldg(c4 + j);
+  }
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
@@ -75,14 +118,16 @@ __device__ __forceinline__ void epilogue_prefetch(EpiOperands<EPI, CH>& o, const
 }
 
 // Must be called by all 32 lanes of the warp (it shuffles); rows >= M are masked inside.
-template <int EPI, int CH>
-__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const EpiOperands<EPI, CH>& o,
-                                               const GemmParams& p, int row, int col0, bool fast) {
+template <int EPI, int CH, int LN = 0>
+__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const EpiOperands<EPI, CH, LN>& o,
+                                               const GemmParams& p, int row, int col0, bool fast,
+                                               const LnRow& lnr = LnRow(), LnEmit* lne = nullptr) {
   float v[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
   if (!fast) {
-    // ragged edge (N not a multiple of the tile) or unaligned rows: scalar, bounds-checked
+    // ragged edge (N not a multiple of the tile) or unaligned rows: scalar, bounds-checked (never taken with LN != 0:
+    // the launcher requires aligned, tile-sized problems there)
     if (row >= p.M) return;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -99,6 +144,17 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
       }
     }
     return;
+  }
+  if (LN == 1) {
+    // finish the LayerNorm of this row: rstd * (xc . W'^T - mean_c * colsum)
+    const float nm = -lnr.mean_c;
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) {
+      v[4 * j + 0] = lnr.rstd * fmaf(nm, o.colsum[j].x, v[4 * j + 0]);
+      v[4 * j + 1] = lnr.rstd * fmaf(nm, o.colsum[j].y, v[4 * j + 1]);
+      v[4 * j + 2] = lnr.rstd * fmaf(nm, o.colsum[j].z, v[4 * j + 2]);
+      v[4 * j + 3] = lnr.rstd * fmaf(nm, o.colsum[j].w, v[4 * j + 3]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < CH / 4; ++j) {
@@ -138,6 +194,22 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
       }
       if (ok_e) oe[2 * j + par] = make_float4(e[0], e[1], e[2], e[3]);
       if (ok_o) oo[2 * j + par] = make_float4(d[0], d[1], d[2], d[3]);
+      if (LN == 2) {
+        // centred 16-bit copy for the next GEMM + this lane's share of the row sums
+        uint2* be = reinterpret_cast<uint2*>(p.out16 + static_cast<long long>(row_e) * p.ldo16 + col0);
+        uint2* bo = reinterpret_cast<uint2*>(p.out16 + static_cast<long long>(row_o) * p.ldo16 + col0);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          e[t] -= lne->shift_e;
+          d[t] -= lne->shift_o;
+          lne->s1e += e[t];
+          lne->s2e = fmaf(e[t], e[t], lne->s2e);
+          lne->s1o += d[t];
+          lne->s2o = fmaf(d[t], d[t], lne->s2o);
+        }
+        if (ok_e) be[2 * j + par] = make_uint2(pack16(e[0], e[1]), pack16(e[2], e[3]));
+        if (ok_o) bo[2 * j + par] = make_uint2(pack16(d[0], d[1]), pack16(d[2], d[3]));
+      }
     }
   } else {
     // pieces = uint4 (8 columns of 16-bit values)

@@ -64,6 +64,20 @@ int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, i
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
                        cudaStream_t stream);
 
+// LayerNorm folded into the GEMMs around it (gemm_common.cuh).  ln_mode 1 (QKV, fc1; epi EPI_BF16 / EPI_QGELU_BF16):
+// A = op16(x - shift), W = W * diag(gamma), bias = b + W . beta, colsum[n] = sum_k W'[n][k]; the epilogue applies
+// rstd * (acc - mean_c * colsum) from the row records ln_in.  ln_mode 2 (out-proj, fc2; EPI_RESID_F32, N = 768): also
+// writes out16 = op16(x_new - shift_new) and the records ln_out of x_new (shift_new = row mean of resid, from ln_in).
+// Row record: 16 floats, [0] shift, [4 + 2 s], [5 + 2 s] = sum / sum of squares of the centred row over 128-column slice s.
+constexpr int kLnRecordFloats = 16;
+int launch_gemm_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, void* out,
+                   int64_t ldo, const float* resid, int64_t ldr, int epi, int ln_mode, const float* ln_in, float* ln_out,
+                   op16* out16, int64_t ldo16, const float* colsum, cudaStream_t stream);
+// dst[n][k] = op16(src[n][k] * row_scale[n] * gamma[k]); colsum[n] = sum_k dst[n][k]; bias_out[n] = row_scale[n] *
+// (bias[n] + sum_k src[n][k] * beta[k])   (row_scale may be null)
+int launch_pack_ln_fold(const float* src, const float* row_scale, const float* gamma, const float* beta, const float* bias,
+                        op16* dst, float* colsum, float* bias_out, int N, int K, cudaStream_t stream);
+
 // ---- LayerNorm family, D = 768 (elementwise.cu) ----------------------------------------------
 // y[r] = LN(x[r * row_stride]) ; out op16 (GEMM operand).  row_stride = L picks the CLS rows.
 int launch_layernorm_op16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
@@ -72,14 +86,15 @@ int launch_layernorm_op16(const float* x, int row_stride, const float* w, const 
 int launch_eot_layernorm_op16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
                               int batch, cudaStream_t stream);
 // x[b*L+l] = tok_emb[tok[b,l]] + pos[l]   (M.py:3047-3048)
+// xc / rec (optional, all three producers of the residual stream): op16(x - mean) and the row record for the LN fold
 int launch_text_embed(const int64_t* tok, const float* tok_emb, const float* pos, float* x, int batch, int L,
-                      int vocab, cudaStream_t stream);
+                      int vocab, op16* xc, float* rec, cudaStream_t stream);
 // x[b*L+l] = ln_pre((l == 0 ? cls : grid[b*(L-1)+l-1]) + pos[l])   (M.py:2418-2426)
 int launch_image_embed_ln_pre(const float* grid, const float* cls, const float* pos, const float* w, const float* b,
-                              float* x, int batch, int L, cudaStream_t stream);
+                              float* x, int batch, int L, op16* xc, float* rec, cudaStream_t stream);
 // Lateral adapter tail (M.py:1760-1777): x_out = ln_adapt(concat(2*cls, BN(dw3x3(grid(x))) + t))
 int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
-                           const float* b, float* x_out, int batch, int g, cudaStream_t stream);
+                           const float* b, float* x_out, int batch, int g, op16* xc, float* rec, cudaStream_t stream);
 // out[r] = x[r] / ||x[r]|| (optional) as f32 and op16 copies; width E (<= 1024, multiple of 4)
 int check_token_error(cudaStream_t stream);  // synchronises; non-zero if an out-of-range token id was seen
 int launch_l2norm(const float* x, float* out_f32, op16* out_bf16, int rows, int E, int normalise, cudaStream_t stream);

@@ -177,6 +177,92 @@ def test_gemm_rejects_bad_arguments():
     assert rc != 0 and "multiples of 8" in _lib.last_error(PREC)
 
 
+def _ln_records(x):
+    """Row records of the LN fold as the elementwise producers write them: shift = row mean, slice 0 = sums."""
+    mean = x.mean(-1, keepdim=True)
+    c = x - mean
+    rec = torch.zeros(x.shape[0], 16, device=x.device)
+    rec[:, 0] = mean[:, 0]
+    rec[:, 4] = c.sum(-1)
+    rec[:, 5] = (c * c).sum(-1)
+    return rec, c
+
+
+@pytest.mark.parametrize("M,N,epi", [(4096 + 77, 2304, "bf16"), (1000, 3072, "qgelu"), (77, 2304, "bf16")])
+def test_gemm_ln_consume_matches_layernorm_linear(M, N, epi):
+    """QKV / fc1 with the LayerNorm folded in (gemm_common.cuh) against LN (M.py:204-219) + F.linear in fp32; the rows
+    carry a common-mode offset of several standard deviations, which the per-row shift has to absorb."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    K = 768
+    x = torch.randn(M, K, device="cuda", generator=g) * (1 + torch.rand(M, 1, device="cuda", generator=g)) \
+        + 5.0 * torch.randn(M, 1, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = 0.2 * torch.randn(N, device="cuda", generator=g)
+    gamma = 1.0 + 0.3 * torch.randn(K, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(K, device="cuda", generator=g)
+    rs = torch.ones(N, device="cuda")
+    rs[:768] = 0.125
+    wf = torch.empty(N, K, device="cuda", dtype=op_dtype())
+    cs, bf = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    check(LIB.msclip_op_pack_ln_fold(ptr(w), ptr(rs), ptr(gamma), ptr(beta), ptr(b), ptr(wf), ptr(cs), ptr(bf), N, K, stream()))
+    assert rel(wf.float(), w * rs[:, None] * gamma[None, :]) < tol16()
+    assert torch.allclose(cs, wf.float().sum(-1), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(bf, rs * (b + w @ beta), rtol=1e-4, atol=1e-4)
+    rec, c = _ln_records(x)
+    xc = c.to(op_dtype())
+    out = torch.zeros(M, N, device="cuda", dtype=op_dtype())
+    code = _lib.EPI_BF16 if epi == "bf16" else _lib.EPI_QGELU_BF16
+    check(LIB.msclip_op_gemm_ln(ptr(xc), K, ptr(wf), K, M, N, K, ptr(bf), ptr(out), N, None, 0, code, 1, ptr(rec), None, None, 0,
+                                ptr(cs), stream()))
+    ref = F.linear(O.layer_norm(x, gamma, beta), w, b) * rs
+    if epi == "qgelu":
+        ref = O.quick_gelu(ref)
+    r = rel(out.float(), ref)
+    _record(f"gemm_ln/consume_M{M}_N{N}_{epi}", {"rel": r})
+    assert r < 1.5 * tol16(), r          # operand rounding of x - shift and of W * gamma, then the output rounding
+
+
+@pytest.mark.parametrize("M,K", [(4096 + 77, 768), (600, 3072), (50, 768)])
+def test_gemm_ln_emit_matches_reference(M, K):
+    """out-proj / fc2 with the residual epilogue that also emits the centred 16-bit copy and the row records."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    N = 768
+    a = torch.randn(M, K, device="cuda", generator=g).to(op_dtype())
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(op_dtype())
+    b = 0.2 * torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g) * 2 + 3.0 * torch.randn(M, 1, device="cuda", generator=g)
+    rec_in, _ = _ln_records(x)
+    rec_in[:, 0] += 0.25                                   # a stale shift: mean of x = shift + s1 / 768 must still come out
+    rec_in[:, 4] -= 0.25 * N
+    rec_out = torch.full((M, 16), 9.0, device="cuda")
+    x_new = x.clone()
+    xc = torch.zeros(M, N, device="cuda", dtype=op_dtype())
+    check(LIB.msclip_op_gemm_ln(ptr(a), K, ptr(w), K, M, N, K, ptr(b), ptr(x_new), N, ptr(x_new), N, _lib.EPI_RESID_F32, 2,
+                                ptr(rec_in), ptr(rec_out), ptr(xc), N, None, stream()))
+    ref = x + a.float() @ w.float().t() + b
+    assert rel(x_new, ref) < 2e-5
+    shift = x.mean(-1)
+    assert torch.allclose(rec_out[:, 0], shift, rtol=1e-4, atol=1e-4)
+    cen = x_new - rec_out[:, :1]
+    assert rel(xc.float(), cen) < tol16()
+    s1 = rec_out[:, 4:16:2].sum(-1)
+    s2 = rec_out[:, 5:16:2].sum(-1)
+    assert torch.allclose(s1, cen.sum(-1), rtol=1e-3, atol=2e-2)
+    assert torch.allclose(s2, (cen * cen).sum(-1), rtol=1e-4)
+    # chained: the emitted copy + records reproduce LayerNorm(x_new) . W2^T through the consume epilogue
+    w2 = torch.randn(256, N, device="cuda", generator=g) / math.sqrt(N)
+    gamma, beta = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g), 0.1 * torch.randn(N, device="cuda", generator=g)
+    wf = torch.empty(256, N, device="cuda", dtype=op_dtype())
+    cs, bf = torch.empty(256, device="cuda"), torch.empty(256, device="cuda")
+    check(LIB.msclip_op_pack_ln_fold(ptr(w2), None, ptr(gamma), ptr(beta), None, ptr(wf), ptr(cs), ptr(bf), 256, N, stream()))
+    y = torch.zeros(M, 256, device="cuda", dtype=op_dtype())
+    check(LIB.msclip_op_gemm_ln(ptr(xc), N, ptr(wf), N, M, 256, N, ptr(bf), ptr(y), 256, None, 0, _lib.EPI_BF16, 1, ptr(rec_out),
+                                None, None, 0, ptr(cs), stream()))
+    r = rel(y.float(), F.linear(O.layer_norm(x_new, gamma, beta), w2))
+    _record(f"gemm_ln/emit_M{M}_K{K}", {"rel_chain": r})
+    assert r < 1.5 * tol16(), r
+
+
 @pytest.mark.parametrize("rows,stride", [(1, 1), (77, 1), (5000, 1), (64, 50)])
 def test_layernorm(rows, stride):
     x = torch.randn(rows * stride, 768, device="cuda") * 3 + 0.5
