@@ -256,7 +256,7 @@ def test_prefetched_images_equal_direct_transfer():
 
 
 def test_internal_chunk_boundaries():
-    """Batches that cross the library's internal chunking (1024 images per conv pass, 4096 sequences per tower
+    """Batches that cross the library's internal chunking (512 images per conv pass, 4096 sequences per tower
     pass) give the same embeddings as the same samples encoded in small batches (bit-exact: every kernel is
     batch-independent and deterministic)."""
     cfg = MSCLIPConfig(layers=3)
@@ -264,7 +264,7 @@ def test_internal_chunk_boundaries():
     g = torch.Generator(device="cuda").manual_seed(3)
     img = torch.randn(1030, 3, 224, 224, device="cuda", generator=g)
     big = model.encode_image(img)
-    idx = [0, 511, 1023, 1024, 1029]
+    idx = [0, 511, 512, 1023, 1024, 1029]
     small = torch.cat([model.encode_image(img[i:i + 1]) for i in idx])
     assert torch.equal(big[idx], small)
     tok = torch.from_numpy(synth.synth_tokens(4100, 5, ragged=True)).cuda()
