@@ -77,10 +77,11 @@ int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, 
 /* Fused 112x112 stage: NCHW image (dtype code as msclip_encode_image) -> stem = relu(conv3x3_s2 . w0[0:48]),
  * p0 = relu(conv3x3_s2 . w0[48:96]) (kept on chip), y1 = relu(w1 . p0 + b1), p0s = p0[:, ::2, ::2],
  * pooled = depth-wise k x k / stride k pooling of p0 (+ pool_b).  w0 bf16 [96][32] (k = c*9 + ky*3 + kx, zero padded),
- * w1 bf16 [48][48], pool_w f32 [k*k][48]; outputs NHWC bf16; height, width multiples of 32; k = 8 or 16. */
+ * w1 bf16 [48][48], pool_w f32 [k*k][48]; outputs NHWC bf16 (p0s with a pixel pitch of p0s_pitch >= 48 elements);
+ * height, width multiples of 32; k = 8 or 16. */
 int msclip_op_front_conv(const void* img, int dtype, int batch, int height, int width, const void* w0_bf16, const float* b0,
                          const void* w1_bf16, const float* b1, const float* pool_w, const float* pool_b, int k,
-                         void* stem_bf16, void* y1_bf16, void* p0s_bf16, void* pooled_bf16, void* stream);
+                         void* stem_bf16, void* y1_bf16, void* p0s_bf16, int p0s_pitch, void* pooled_bf16, void* stream);
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                               const float* b, float* x_out, int batch, int grid, void* stream);
 /* parts2[0] = sum_i (lse_j s_ij - s_ii), parts2[1] = sum_j (lse_i s_ij - s_jj), s = scale * img . txt^T */

@@ -77,7 +77,7 @@ _SIGNATURES = {
     "msclip_op_conv_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P,
                                 _P, _L, _I, _P]),
     "msclip_op_patch_pool": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "msclip_op_front_conv": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "msclip_op_front_conv": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P]),
     "msclip_op_adapter_fuse_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "msclip_op_contrastive_lse": (_I, [_P, _P, _I, _F, _P, _P, _P]),
     "msclip_op_contrastive_lse_workspace": (C.c_size_t, [_I]),

@@ -227,11 +227,11 @@ int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, 
 }
 int msclip_op_front_conv(const void* img, int dtype, int batch, int height, int width, const void* w0_bf16, const float* b0,
                          const void* w1_bf16, const float* b1, const float* pool_w, const float* pool_b, int k,
-                         void* stem_bf16, void* y1_bf16, void* p0s_bf16, void* pooled_bf16, void* stream) {
+                         void* stem_bf16, void* y1_bf16, void* p0s_bf16, int p0s_pitch, void* pooled_bf16, void* stream) {
   return launch_front_conv(img, dtype, batch, height, width, static_cast<const op16*>(w0_bf16), b0,
                            static_cast<const op16*>(w1_bf16), b1, pool_w, pool_b, k, static_cast<op16*>(stem_bf16),
-                           static_cast<op16*>(y1_bf16), static_cast<op16*>(p0s_bf16), static_cast<op16*>(pooled_bf16),
-                           as_stream(stream));
+                           static_cast<op16*>(y1_bf16), static_cast<op16*>(p0s_bf16), p0s_pitch,
+                           static_cast<op16*>(pooled_bf16), as_stream(stream));
 }
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                               const float* b, float* x_out, int batch, int grid, void* stream) {

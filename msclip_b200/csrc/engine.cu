@@ -633,8 +633,8 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     for (int j = 1; j < 5; ++j) {
       const int cin = dims[j - 1];
       const int Ho = Hc / c.parallel_strides[j];
-      // explicit formulation: the patch matrix; implicit: only y2 [Ho, Ho, cin] lives in `col`
-      col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * (g_conv_im2col ? 9 : 1) * cin);
+      // explicit formulation: the patch matrix; implicit: y2 [Ho, Ho, cin] (stage 1: [y2 | p0s], twice as wide)
+      col_max = std::max(col_max, static_cast<size_t>(Ho) * Ho * (g_conv_im2col ? 9 : 2) * cin);
       act_max = std::max(act_max, static_cast<size_t>(Hc) * Hc * cin);       // y1
       act_max = std::max(act_max, static_cast<size_t>(Ho) * Ho * 2 * cin);   // cat / p_j
       Hc = Ho;
@@ -659,8 +659,9 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     const op16* a1_stem = a1;
     const op16* a1_branch = a1 + static_cast<size_t>(nb) * px1 * c0;
     if (fused) {
+      // p0s goes straight into the right half of `col` = [y2 | p0s], the K-concatenated operand of the stage-1 tail
       MSCLIP_TRY(launch_front_conv(img_c, dtype, nb, R, R, h->first.w, h->first.b, h->br1[1].w, h->br1[1].b,
-                                   h->adapters[0].dw_w, h->adapters[0].dw_b, h->adapters[0].k, a1, actC, a1 + static_cast<size_t>(nb) * px1 * c0,
+                                   h->adapters[0].dw_w, h->adapters[0].dw_b, h->adapters[0].k, a1, actC, col + c0, 2 * c0,
                                    pooled[0] + static_cast<size_t>(b0) * g * g * dims[0], s));
       count_launch(1);
     } else {
@@ -732,16 +733,20 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         } else {
           // y2 = relu(bn2(conv3x3_s(y1))): implicit GEMM straight from y1
           op16* y2 = col;
+          const int y2_pitch = from_front ? 2 * cin : cin;  // stage 1: left half of [y2 | p0s]
           const ConvSource s2 = {actC, Hc, Hc, cin, 0, cin, 3, st, 1};
-          MSCLIP_TRY(launch_conv_gemm(&s2, 1, nb, Ho, Ho, h->br2[j].w, 9 * cin, cin, h->br2[j].b, y2, cin, EPI_RELU_BF16, s));
+          MSCLIP_TRY(launch_conv_gemm(&s2, 1, nb, Ho, Ho, h->br2[j].w, 9 * cin, cin, h->br2[j].b, y2, y2_pitch, EPI_RELU_BF16, s));
           // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p))): one GEMM over K = [y2 | strided p]
-          ConvSource s3[2] = {{y2, Ho, Ho, cin, 0, cin, 1, 1, 0}, {p, Hc, Hc, cpix, coff, cin, 1, st, 0}};
-          if (from_front) {  // p already holds only the pixels the strided shortcut reads
-            s3[1].H = s3[1].W = Ho;
-            s3[1].stride = 1;
+          if (from_front) {
+            // both halves are dense and adjacent (the front kernel wrote the strided pixels of p_0 next to y2):
+            // a plain TMA-fed GEMM, no gather
+            MSCLIP_TRY(launch_gemm(col, 2 * cin, h->br3[j].w, 2 * cin, nb * Ho * Ho, 2 * cin, 2 * cin, h->br3[j].b, pn, 2 * cin,
+                                   nullptr, 0, EPI_RELU_BF16, s));
+          } else {
+            const ConvSource s3[2] = {{y2, Ho, Ho, cin, 0, cin, 1, 1, 0}, {p, Hc, Hc, cpix, coff, cin, 1, st, 0}};
+            MSCLIP_TRY(launch_conv_gemm(s3, 2, nb, Ho, Ho, h->br3[j].w, 2 * cin, 2 * cin, h->br3[j].b, pn, 2 * cin,
+                                        EPI_RELU_BF16, s));
           }
-          MSCLIP_TRY(launch_conv_gemm(s3, 2, nb, Ho, Ho, h->br3[j].w, 2 * cin, 2 * cin, h->br3[j].b, pn, 2 * cin,
-                                      EPI_RELU_BF16, s));
         }
         p = pn;
         cpix = 2 * cin;

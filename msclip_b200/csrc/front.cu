@@ -58,6 +58,7 @@ struct FrontParams {
   op16* stem;
   op16* y1;
   op16* p0s;
+  int p0s_pitch;  // elements between consecutive p0s pixels (48 = dense; 96 when it is the second half of a [y2 | p0s] operand)
   op16* pooled;
 };
 
@@ -302,10 +303,11 @@ __global__ void __launch_bounds__(kFrontThreads, 2) front_conv_kernel(const Fron
     }
     __syncwarp();
     {
-      op16* gdst = p.p0s + ((static_cast<long long>(b) * (p.Ho / 2) + (oy0 / 2 + warp)) * (p.Wo / 2) + ox0 / 2) * kC;
+      op16* gdst = p.p0s + ((static_cast<long long>(b) * (p.Ho / 2) + (oy0 / 2 + warp)) * (p.Wo / 2) + ox0 / 2) * p.p0s_pitch;
       for (int idx = lane; idx < 48; idx += 32) {
         const int px = idx / 6, pc = idx - px * 6;
-        *reinterpret_cast<uint4*>(gdst + (px * 6 + (pc ^ ((px >> 2) & 1))) * 8) = *reinterpret_cast<const uint4*>(stage + idx * 8);
+        *reinterpret_cast<uint4*>(gdst + px * p.p0s_pitch + (pc ^ ((px >> 2) & 1)) * 8) =
+            *reinterpret_cast<const uint4*>(stage + idx * 8);
       }
     }
     __syncwarp();
@@ -393,7 +395,7 @@ bool front_conv_supported(int H, int W, int c0, int k) {
 
 int launch_front_conv(const void* img, int img_dtype, int batch, int H, int W, const op16* w0, const float* b0,
                       const op16* w1, const float* b1, const float* pool_w, const float* pool_b, int k, op16* stem,
-                      op16* y1, op16* p0s, op16* pooled, cudaStream_t stream) {
+                      op16* y1, op16* p0s, int p0s_pitch, op16* pooled, cudaStream_t stream) {
   if (batch <= 0) return 0;
   MSCLIP_REQUIRE(img_dtype >= 0 && img_dtype <= 2, "front_conv: image dtype must be 0 (f32), 1 (bf16) or 2 (f16)");
   MSCLIP_REQUIRE(front_conv_supported(H, W, kC, k), "front_conv: needs H, W multiples of 32 and a lateral kernel of 8 or 16");
@@ -401,6 +403,7 @@ int launch_front_conv(const void* img, int img_dtype, int batch, int H, int W, c
                        reinterpret_cast<uintptr_t>(pool_w) | reinterpret_cast<uintptr_t>(stem) |
                        reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(p0s);
   MSCLIP_REQUIRE((al & 15) == 0, "front_conv: image, weights and outputs must be 16-byte aligned");
+  MSCLIP_REQUIRE(p0s_pitch >= kC && p0s_pitch % 8 == 0, "front_conv: p0s pixel pitch must be a multiple of 8 and at least 48");
   FrontParams p;
   p.img = img;
   p.img_dtype = img_dtype;
@@ -423,6 +426,7 @@ int launch_front_conv(const void* img, int img_dtype, int batch, int H, int W, c
   p.stem = stem;
   p.y1 = y1;
   p.p0s = p0s;
+  p.p0s_pitch = p0s_pitch;
   p.pooled = pooled;
   const int smem = kOffPoolW + k * k * kPoolPitch * 4;
   const int grid = p.total_tiles < 2 * num_sms() ? p.total_tiles : 2 * num_sms();

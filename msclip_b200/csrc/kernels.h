@@ -114,12 +114,13 @@ int launch_patch_pool(const op16* in, int batch, int H, int W, int cpix, int c_o
 // ---- fused front end (front.cu): both 3x3 / stride-2 first convs (stem | parallel branch, w0 [96][32] with
 // k = c*9 + ky*3 + kx, BN folded), the branch's first bottleneck 1x1 (w1 [48][48]), the even-pixel copy of the
 // branch activation for its strided shortcut and the depth-wise k x k patch pooling of adapter 0, in one pass over
-// the image.  NCHW image (f32 / bf16 / f16) -> stem, y1 NHWC op16 [B, H/2, W/2, 48]; p0s [B, H/4, W/4, 48];
+// the image.  NCHW image (f32 / bf16 / f16) -> stem, y1 NHWC op16 [B, H/2, W/2, 48]; p0s [B, H/4, W/4, 48] with pixel
+// pitch p0s_pitch (96 lets it be the right half of the [y2 | p0s] operand of the ConvResBlock tail GEMM);
 // pooled [B * (H/2/k) * (W/2/k), 48].
 bool front_conv_supported(int H, int W, int c0, int k);
 int launch_front_conv(const void* img, int img_dtype, int batch, int H, int W, const op16* w0, const float* b0,
                       const op16* w1, const float* b1, const float* pool_w, const float* pool_b, int k, op16* stem,
-                      op16* y1, op16* p0s, op16* pooled, cudaStream_t stream);
+                      op16* y1, op16* p0s, int p0s_pitch, op16* pooled, cudaStream_t stream);
 
 // ---- implicit-GEMM convolution (conv_gemm.cu): out[B*Ho*Wo, N] = epi(patches . W^T + bias) ---------------
 // K is the concatenation of the sources' (ky, kx, c) patch vectors; every source must map onto the same

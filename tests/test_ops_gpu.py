@@ -426,10 +426,14 @@ def test_front_conv_matches_unfused_reference(B, H, W, k, img16):
     Ho, Wo = H // 2, W // 2
     stem = torch.full((B, Ho, Wo, 48), 7.0, device="cuda", dtype=dt)
     y1 = torch.full((B, Ho, Wo, 48), 7.0, device="cuda", dtype=dt)
-    p0s = torch.full((B, Ho // 2, Wo // 2, 48), 7.0, device="cuda", dtype=dt)
+    # p0s lands in the right half of a 96-wide [y2 | p0s] operand when W is the model's 224 (engine layout), dense otherwise
+    pitch = 96 if W == 224 else 48
+    cat = torch.full((B, Ho // 2, Wo // 2, pitch), 7.0, device="cuda", dtype=dt)
+    p0s = cat[..., pitch - 48:]
     pooled = torch.full((B * (Ho // k) * (Wo // k), 48), 7.0, device="cuda", dtype=dt)
     check(LIB.msclip_op_front_conv(ptr(img), code, B, H, W, ptr(w0p), ptr(b0), ptr(w1), ptr(b1), ptr(pwp), ptr(pb), k,
-                                   ptr(stem), ptr(y1), ptr(p0s), ptr(pooled), stream()))
+                                   ptr(stem), ptr(y1), C.c_void_p(cat.data_ptr() + 2 * (pitch - 48)), pitch, ptr(pooled), stream()))
+    assert pitch == 48 or torch.all(cat[..., :48] == 7.0)
     a = torch.relu(F.conv2d(img.to(dt).float(), w0.float(), b0, stride=2, padding=1))    # operands rounded as the kernel does
     p0 = a[:, 48:]
     p0r = p0.to(dt).float()

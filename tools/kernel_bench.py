@@ -133,7 +133,7 @@ def main():
         p0s = torch.empty(px // 4, 48, device="cuda", dtype=torch.bfloat16)
         pooled = torch.empty(nbc * 49, 48, device="cuda", dtype=torch.bfloat16)
         ms_f = time_ms(lambda: _lib.check(L.msclip_op_front_conv(ptr(img), _lib.F32, nbc, R, R, ptr(w0), ptr(b0), ptr(w1), ptr(b1), ptr(pw),
-                                                                  ptr(pb), kk, ptr(stem), ptr(y1), ptr(p0s), ptr(pooled), sp)), args.reps)
+                                                                  ptr(pb), kk, ptr(stem), ptr(y1), ptr(p0s), 48, ptr(pooled), sp)), args.reps)
         col0 = torch.empty(px, 32, device="cuda", dtype=torch.bfloat16)
         a1 = torch.empty(px, 96, device="cuda", dtype=torch.bfloat16)
         ms_u = time_ms(lambda: (_lib.check(L.msclip_op_im2col_first(ptr(img), _lib.F32, ptr(col0), nbc, R, R, sp)),
