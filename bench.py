@@ -152,7 +152,7 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cfg, world):
@@ -347,10 +347,29 @@ def run_ours(args, cfg, rank, world, local):
         "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary, "roofline": roofline, "cpu_baseline": cpu,
         "device_bytes": int(L.msclip_device_bytes(h)),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout: route everything else that writes to fd 1 (NCCL's version banner,
+    library chatter of the ranks) to stderr and keep a private handle on the real stdout for that line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
