@@ -80,8 +80,13 @@ int msclip_encode_image(msclip_handle h, const void* image, int image_dtype, int
  * of step i+1 overlaps the compute of step i.  Two slots (double buffering); the host buffer must stay unchanged
  * until it has been consumed. */
 int msclip_stage_images(msclip_handle h, const void* image_host, int image_dtype, int batch, void* stream);
-/* tokens: [batch, context_length] int64; out: [batch, embed_dim] f32.  Out-of-range ids are an error. */
+/* tokens: [batch, context_length] int64; out: [batch, embed_dim] f32.  Out-of-range ids are an error.
+ * The text tower is causal and pools the row at argmax(tokens) (M.py:2965-2971, 3057-3060), so positions after a
+ * sequence's EOT token cannot influence its output: by default the call runs the tower only over the longest live
+ * prefix of the batch (bit-identical results; costs one 4-byte device->host read per call).
+ * msclip_set_text_trim(h, 0) switches this off; msclip_forward / msclip_forward_loss never trim (no host sync). */
 int msclip_encode_text(msclip_handle h, const int64_t* tokens, int batch, float* out, int normalize, void* stream);
+int msclip_set_text_trim(msclip_handle h, int enable);
 /* logits[n_img, n_txt] = scale * img_feat . txt_feat^T (f32 in, f32 out; split-bf16 tensor-core product). */
 int msclip_similarity_logits(msclip_handle h, const float* img_feat, int n_img, const float* txt_feat, int n_txt,
                              float scale, float* logits, void* stream);

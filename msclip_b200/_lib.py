@@ -56,6 +56,7 @@ _SIGNATURES = {
     "msclip_encode_image": (_I, [_P, _P, _I, _I, _P, _I, _P]),
     "msclip_stage_images": (_I, [_P, _P, _I, _I, _P]),
     "msclip_encode_text": (_I, [_P, _P, _I, _P, _I, _P]),
+    "msclip_set_text_trim": (_I, [_P, _I]),
     "msclip_similarity_logits": (_I, [_P, _P, _I, _P, _I, _F, _P, _P]),
     "msclip_forward": (_I, [_P, _P, _I, _P, _I, _P, _P]),
     "msclip_comm_init": (_I, [_P, _I, _I, _I]),

@@ -135,6 +135,8 @@ int msclip_encode_text(msclip_handle h, const int64_t* tokens, int batch, float*
   return engine_encode_text(h, tokens, batch, out, normalize, as_stream(stream));
 }
 
+int msclip_set_text_trim(msclip_handle h, int enable) { return engine_set_text_trim(h, enable); }
+
 int msclip_similarity_logits(msclip_handle h, const float* img_feat, int n_img, const float* txt_feat, int n_txt,
                              float scale, float* logits, void* stream) {
   return engine_similarity_logits(h, img_feat, n_img, txt_feat, n_txt, scale, logits, as_stream(stream));

@@ -99,7 +99,7 @@ layernorm_kernel(const float* __restrict__ x, int row_stride, const float* __res
 }
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
-eot_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ tok, int L,
+eot_layernorm_kernel(const float* __restrict__ x, int Lx, const int64_t* __restrict__ tok, int L,
                           const float* __restrict__ w, const float* __restrict__ b, op16* __restrict__ y, int batch) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
@@ -124,19 +124,48 @@ eot_layernorm_kernel(const float* __restrict__ x, const int64_t* __restrict__ to
     }
   }
   float4 v[kVec];
-  load_row(x + (static_cast<long long>(r) * L + best_i) * kD, lane, v);
+  if (best_i >= Lx) best_i = Lx - 1;  // cannot happen when Lx covers the longest sequence; keeps the read in bounds
+  load_row(x + (static_cast<long long>(r) * Lx + best_i) * kD, lane, v);
   layer_norm_row(v, w, b, lane);
   store_row_bf16(y + static_cast<long long>(r) * kD, lane, v);
 }
 
+// longest live prefix of a batch: max over sequences of argmax_j tok[b, j] + 1 (everything after the EOT token cannot
+// influence the pooled output of a causal tower, M.py:2965-2971 + 3059)
+__global__ void __launch_bounds__(32 * kRowsPerBlock)
+text_max_len_kernel(const int64_t* __restrict__ tok, int L, int batch, int* __restrict__ out_max) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (r >= batch) return;
+  long long best = INT64_MIN;
+  int best_i = 0x7fffffff;
+  for (int j = lane; j < L; j += 32) {
+    const long long t = tok[static_cast<long long>(r) * L + j];
+    if (t > best) {
+      best = t;
+      best_i = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  if (lane == 0) atomicMax(out_max, best_i + 1);
+}
+
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 text_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb, const float* __restrict__ pos,
-                  float* __restrict__ x, long long rows, int L, int vocab, int* __restrict__ err, op16* __restrict__ xc,
-                  float* __restrict__ rec) {
+                  float* __restrict__ x, long long rows, int L, int Ltok, int vocab, int* __restrict__ err,
+                  op16* __restrict__ xc, float* __restrict__ rec) {
   const int lane = threadIdx.x & 31;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
        r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
-    long long t = tok[r];
+    long long t = tok[(r / L) * Ltok + (r % L)];  // rows: L live positions per sequence, tokens: pitch Ltok
     if (t < 0 || t >= vocab) {  // nn.Embedding raises; we flag and clamp so the kernel stays in bounds
       if (lane == 0) atomicExch(err, 1);
       t = 0;
@@ -291,11 +320,18 @@ int launch_layernorm_op16(const float* x, int row_stride, const float* w, const 
   return 0;
 }
 
-int launch_eot_layernorm_op16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
+int launch_eot_layernorm_op16(const float* x, int x_len, const int64_t* tok, int L, const float* w, const float* b, op16* y,
                               int batch, cudaStream_t stream) {
   if (batch <= 0) return 0;
   eot_layernorm_kernel<<<(batch + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(
-      x, tok, L, w, b, y, batch);
+      x, x_len, tok, L, w, b, y, batch);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_text_max_len(const int64_t* tok, int L, int batch, int* out_max, cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  text_max_len_kernel<<<(batch + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(tok, L, batch, out_max);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -309,14 +345,14 @@ static int* token_error_flag() {
   return flag;
 }
 
-int launch_text_embed(const int64_t* tok, const float* tok_emb, const float* pos, float* x, int batch, int L,
+int launch_text_embed(const int64_t* tok, int tok_pitch, const float* tok_emb, const float* pos, float* x, int batch, int L,
                       int vocab, op16* xc, float* rec, cudaStream_t stream) {
   if (batch <= 0) return 0;
   int* flag = token_error_flag();
   MSCLIP_REQUIRE(flag != nullptr, "cudaMalloc of the token error flag failed");
   const long long rows = static_cast<long long>(batch) * L;
-  text_embed_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(tok, tok_emb, pos, x, rows, L, vocab, flag, xc,
-                                                                       xc ? rec : nullptr);
+  text_embed_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(tok, tok_emb, pos, x, rows, L, tok_pitch, vocab, flag,
+                                                                       xc, xc ? rec : nullptr);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

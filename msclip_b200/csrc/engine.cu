@@ -806,12 +806,16 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
   return 0;
 }
 
-static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_dev, int normalize, op16* feat_bf16,
+// L = positions per sequence the tower runs over (context_length, or the longest live prefix of the batch: with the
+// causal mask nothing after a sequence's EOT token can reach the row that is pooled, M.py:2965-2971 + 3057-3060);
+// tokens keep their pitch of context_length
+static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float* out_dev, int normalize, op16* feat_bf16,
                       cudaStream_t s) {
   const msclip_config& c = h->cfg;
-  const int w = c.width, L = c.context_length;
+  const int w = c.width, Lt = c.context_length;
+  MSCLIP_REQUIRE(L >= 1 && L <= Lt, "text tower: live length out of range");
   const int tb = std::min(batch, kTowerChunk);
-  const size_t Mmax = static_cast<size_t>(tb) * std::max(h->l_img, L);
+  const size_t Mmax = static_cast<size_t>(tb) * std::max(h->l_img, Lt);
   WS(x, float, "x", Mmax * w);
   WS(hbuf, op16, "h", Mmax * w);
   WS(qkv, op16, "qkv", Mmax * 3 * w);
@@ -824,12 +828,12 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, float* out_d
   float* rec[2] = {rec0, rec1};
   for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
     const int nb = std::min(kTowerChunk, batch - b0);
-    const int64_t* tk = tok + static_cast<size_t>(b0) * L;
-    MSCLIP_TRY(launch_text_embed(tk, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0], s));
+    const int64_t* tk = tok + static_cast<size_t>(b0) * Lt;
+    MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0], s));
     count_launch(1);
     for (int idx = 0; idx < c.layers; ++idx)
       MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, rec, s));
-    MSCLIP_TRY(launch_eot_layernorm_op16(x, tk, L, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
+    MSCLIP_TRY(launch_eot_layernorm_op16(x, L, tk, Lt, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->tproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));
     MSCLIP_TRY(launch_l2norm(feat_raw, out_dev + static_cast<size_t>(b0) * c.embed_dim,
@@ -945,7 +949,21 @@ int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, 
   return 0;
 }
 
+int engine_set_text_trim(msclip_ctx* h, int enable) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  h->text_trim = enable != 0;
+  return 0;
+}
+
+static int encode_text_impl(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, bool allow_trim,
+                            cudaStream_t s);
+
 int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, cudaStream_t s) {
+  return encode_text_impl(h, tokens, batch, out, normalize, h != nullptr && h->text_trim, s);
+}
+
+static int encode_text_impl(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, bool allow_trim,
+                            cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));
   if (batch == 0) return 0;
   MSCLIP_REQUIRE(batch > 0 && tokens != nullptr && out != nullptr, "encode_text: bad arguments");
@@ -975,7 +993,19 @@ int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* o
     MSCLIP_TRY(ensure_xchg(h, batch));
     if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 1);
   }
-  MSCLIP_TRY(text_tower(h, tok_dev, batch, out_dev, normalize, fb, s));
+  int live = c.context_length;
+  if (allow_trim) {
+    // one tiny reduction + a 4-byte read-back: prompts are mostly far shorter than the 77-token context
+    WS(dmax, int, "txt_maxlen", 1);
+    MSCLIP_CHECK_CUDA(cudaMemsetAsync(dmax, 0, sizeof(int), s));
+    MSCLIP_TRY(launch_text_max_len(tok_dev, c.context_length, batch, dmax, s));
+    int hmax = 0;
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+    count_launch(1);
+    live = std::min(c.context_length, std::max(hmax, 16));
+  }
+  MSCLIP_TRY(text_tower(h, tok_dev, batch, live, out_dev, normalize, fb, s));
   h->last_txt_batch = fb ? batch : -1;
   if (!out_dev_ptr) {
     MSCLIP_CHECK_CUDA(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(batch) * c.embed_dim * 4, cudaMemcpyDeviceToHost, s));
@@ -1050,7 +1080,7 @@ int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* t
   const int E = h->cfg.embed_dim;
   WS(fi, float, "fwd_img", static_cast<size_t>(std::max(batch, 1)) * E);
   WS(ft, float, "fwd_txt", static_cast<size_t>(std::max(batch, 1)) * E);
-  MSCLIP_TRY(engine_encode_text(h, tokens, batch, ft, 1, s));
+  MSCLIP_TRY(encode_text_impl(h, tokens, batch, ft, 1, false, s));
   MSCLIP_TRY(engine_encode_image(h, image, dtype, batch, fi, 1, s));
   return engine_similarity_logits(h, fi, batch, ft, batch, std::exp(h->logit_scale), logits, s);
 }
@@ -1142,7 +1172,7 @@ int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64
     MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_copy, h->copy_stream));
     img_dev = stage;
   }
-  MSCLIP_TRY(engine_encode_text(h, tokens, b_local, ft, 1, s));
+  MSCLIP_TRY(encode_text_impl(h, tokens, b_local, ft, 1, false, s));
   if (img_dev != image) MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_copy, 0));
   MSCLIP_TRY(engine_encode_image(h, img_dev, dtype, b_local, fi, 1, s));
   return engine_contrastive_loss(h, b_local, std::exp(h->logit_scale), partial_out, loss_out, s);

@@ -58,6 +58,7 @@ struct msclip_ctx {
   std::map<std::string, std::vector<int64_t>> spec;  // expected state-dict keys -> shapes
   std::map<std::string, msclip::RawTensor> raw;      // copies made by msclip_set_weight (freed by finalize)
   bool finalized = false;
+  bool text_trim = true;  // encode_text runs the causal tower only over the longest live prefix (<= EOT) of the batch
   float logit_scale = 0.f;
 
   // packed weights
@@ -107,6 +108,7 @@ void build_spec(msclip_ctx* h);
 int engine_finalize(msclip_ctx* h, cudaStream_t stream);
 int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, float* out, int normalize,
                         cudaStream_t stream);
+int engine_set_text_trim(msclip_ctx* h, int enable);
 int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize,
                        cudaStream_t stream);
 int engine_similarity_logits(msclip_ctx* h, const float* img, int n_img, const float* txt, int n_txt, float scale,

@@ -83,11 +83,14 @@ int launch_pack_ln_fold(const float* src, const float* row_scale, const float* g
 int launch_layernorm_op16(const float* x, int row_stride, const float* w, const float* b, op16* y, int rows,
                           cudaStream_t stream);
 // text pooling: row b <- LN(x[b*L + argmax_j tok[b,j]])  (M.py:3057-3060, 3072)
-int launch_eot_layernorm_op16(const float* x, const int64_t* tok, int L, const float* w, const float* b, op16* y,
+// x holds x_len (<= L) live positions per sequence, tok has pitch L
+int launch_eot_layernorm_op16(const float* x, int x_len, const int64_t* tok, int L, const float* w, const float* b, op16* y,
                               int batch, cudaStream_t stream);
-// x[b*L+l] = tok_emb[tok[b,l]] + pos[l]   (M.py:3047-3048)
+// *out_max = max(*out_max, max_b argmax_j tok[b, j] + 1): the longest live prefix of the batch
+int launch_text_max_len(const int64_t* tok, int L, int batch, int* out_max, cudaStream_t stream);
+// x[b*L+l] = tok_emb[tok[b*tok_pitch + l]] + pos[l], l < L <= tok_pitch   (M.py:3047-3048)
 // xc / rec (optional, all three producers of the residual stream): op16(x - mean) and the row record for the LN fold
-int launch_text_embed(const int64_t* tok, const float* tok_emb, const float* pos, float* x, int batch, int L,
+int launch_text_embed(const int64_t* tok, int tok_pitch, const float* tok_emb, const float* pos, float* x, int batch, int L,
                       int vocab, op16* xc, float* rec, cudaStream_t stream);
 // x[b*L+l] = ln_pre((l == 0 ? cls : grid[b*(L-1)+l-1]) + pos[l])   (M.py:2418-2426)
 int launch_image_embed_ln_pre(const float* grid, const float* cls, const float* pos, const float* w, const float* b,

@@ -194,6 +194,12 @@ class CLIP(nn.Module):
                    "msclip_encode_text")
         return out
 
+    def set_text_trim(self, enable: bool) -> None:
+        """encode_text runs the causal tower only over the longest live prefix (up to the EOT token, M.py:3057-3060) of
+        the batch - bit-identical outputs, less work for short prompts.  On by default."""
+        self._ensure_handle()
+        self._check(self._library().msclip_set_text_trim(self._handle, int(bool(enable))), "msclip_set_text_trim")
+
     @torch.no_grad()
     def similarity_logits(self, image_features: torch.Tensor, text_features: torch.Tensor, scale: float) -> torch.Tensor:
         """scale * I @ T^T (M.py:3141/3146; tools/zero_shot.py:266 with scale = 100)."""

@@ -275,6 +275,29 @@ def test_internal_chunk_boundaries():
     assert torch.isfinite(big).all() and torch.isfinite(tbig).all()
 
 
+def test_text_trim_is_bit_identical():
+    """Positions after the EOT token cannot reach the pooled row of the causal text tower (M.py:2965-2971, 3057-3060):
+    running the tower over the longest live prefix of the batch gives bit-identical embeddings."""
+    cfg = MSCLIPConfig(layers=4)
+    model = build_model(cfg, synth.synth_state_dict(cfg, seed=9))
+    tok = synth.synth_tokens(96, 21, ragged=True)
+    short = tok.copy()
+    short[:, 20:] = 0                       # every prompt ends within 20 positions
+    short[:, 19] = np.where(tok.argmax(1) >= 19, 49407, short[:, 19])
+    full = tok.copy()
+    full[0, :] = np.maximum(full[0, :], 1)
+    full[0, 76] = 49407                     # one sequence uses the whole context
+    for name, t in (("ragged", tok), ("short", short), ("full", full)):
+        tt = torch.from_numpy(t).cuda()
+        model.set_text_trim(True)
+        a = model.encode_text(tt)
+        model.set_text_trim(False)
+        b = model.encode_text(tt)
+        assert torch.isfinite(a).all(), name
+        assert torch.equal(a, b), name
+    model.set_text_trim(True)
+
+
 def test_loss_matches_logits_path_at_odd_batch_sizes():
     """Fused loss kernel vs cross-entropy of the materialised logits for batches that are not multiples of the
     128-row / 128-column tiles (1, 3, 129, 257)."""
