@@ -33,7 +33,6 @@ struct GemmCfg {
   static constexpr int kBarrierBytes = 256;
   static constexpr int kSmemBytes = kStages * kStage + kBarrierBytes + 1024;  // + alignment slack
   static constexpr int kChunk = (BN % 32 == 0) ? 32 : 16;                     // columns per tcgen05.ld
-  static constexpr int kNumChunks = BN / kChunk;
   static_assert(kStageB % 1024 == 0, "B stage must keep 1024-byte alignment");
   static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint");
   static_assert(CG == 1 || BN % 32 == 0, "pair tiles split N in two halves");
