@@ -12,8 +12,9 @@
 // each warp builds the im2col fragments of its two pixel rows straight from that window, runs both first
 // convolutions (K = 27 -> 32, N = 48 + 48) and the 1x1 bottleneck entry (K = 48, N = 48, fed from the accumulator
 // registers of p0) on the tensor cores with mma.sync m16n8k16 - the work per byte is far too small for a 128-row
-// tcgen05 tile pipeline to pay off, the kernel is bound by its HBM writes - and accumulates the depth-wise patch
-// pooling of p0 in registers.  p0 itself never reaches HBM (only its even pixels do).  Outputs are staged per warp
+// tcgen05 tile pipeline to pay off; measured, the kernel moves exactly its algorithmic bytes at ~3.4 TB/s and is
+// bound by shared-memory wavefronts (weight fragments, output staging), profiles/r01_conv_front_ncu.md - and
+// accumulates the depth-wise patch pooling of p0 in registers.  p0 itself never reaches HBM (only its even pixels do).  Outputs are staged per warp
 // in shared memory and leave as full 16-byte vectors of contiguous NHWC rows.
 #include "common.cuh"
 #include "kernels.h"
@@ -37,7 +38,7 @@ constexpr int kOffW0 = kOffIn + 3 * kInRows * kInPitch * 4;    // 14256
 constexpr int kOffW1 = kOffW0 + 2 * kC * kW0Pitch * 2;         // + 7680
 constexpr int kOffBias = kOffW1 + kC * kW1Pitch * 2;           // + 5376
 constexpr int kOffStage = kOffBias + 4 * kC * 4;               // b0[96] | b1[48] | pool_b[48]
-constexpr int kOffPart = kOffStage + 8 * kT * kStagePitch * 2;  // + 14336
+constexpr int kOffPart = kOffStage + 8 * kT * kStagePitch * 2;  // + 12288
 constexpr int kOffPoolW = kOffPart + 8 * 2 * kC * 4;           // + 3072
 static_assert(kOffW0 % 16 == 0 && kOffW1 % 16 == 0 && kOffBias % 16 == 0 && kOffStage % 16 == 0 && kOffPart % 16 == 0 &&
                   kOffPoolW % 16 == 0,
