@@ -13,7 +13,10 @@ NVLink read of the peers' embeddings inside the fused loss kernel.
 JSON keys: see the contract in the task statement; `value` is device-resident throughput, `e2e` goes
 through the public API with pinned HOST buffers (H2D of images/tokens and D2H of the loss inside the
 timed region), `roofline` times the dominant kernel (the shared-block fc1 GEMM) alone with CUDA events,
-`cpu_baseline` times the CPU oracle (a port of the reference forward) on this box's host cores.
+`cpu_baseline` times the reference's own CLIP.forward (staged copy under baseline/_ref; the oracle port if it is
+absent) on this box's host cores, `comparators` holds the same reference forward run eagerly on this GPU
+(fp32 / TF32 / autocast bf16) and, at N > 1, NCCL all-gather + logits + CE against the fused loss stage.
+`--global-batch 32768` is BASELINE.json's metric configuration on any N (micro-batches, one loss).
 """
 from __future__ import annotations
 
@@ -136,26 +139,177 @@ def cpu_oracle_throughput(cfg, sd_np, sample: int, steps: int, warmup: int, seed
     return sample * len(times) / total, total / len(times), torch.get_num_threads()
 
 
+def reference_module_available() -> bool:
+    """The real reference (staged copy under baseline/_ref on the GPU box, tools/stage_reference.py)."""
+    try:
+        from oracle import ref_shim
+        return ref_shim.reference_available()
+    except Exception:
+        return False
+
+
+def cpu_reference_throughput(cfg, sd_np, sample: int, steps: int, warmup: int, seed: int = 1234):
+    """pairs/s of the REAL reference module - `CLIP.forward` (M.py:3126-3155), fp32, eval mode, all host threads -
+    plus the symmetric cross-entropy the north star adds on its logits."""
+    import torch.nn.functional as F
+    from oracle import ref_shim
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = ref_shim.build_reference_model(cfg, state_dict=sd_np)
+    img = torch.from_numpy(synth.synth_images(sample, seed, cfg.image_resolution))
+    tok = torch.from_numpy(synth.synth_tokens(sample, seed, cfg.context_length, cfg.vocab_size))
+    target = torch.arange(sample)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            logits = model(img, tok)
+            loss = float(0.5 * (F.cross_entropy(logits, target) + F.cross_entropy(logits.t(), target)))
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    assert math.isfinite(loss)
+    total = sum(times)
+    return sample * len(times) / total, total / len(times), torch.get_num_threads()
+
+
+def cpu_baseline(cfg, sd_np, sample, steps, warmup):
+    """(value, s/step, cores, kind, description): the real reference module when it is on the box, else the port."""
+    if reference_module_available():
+        v, sec, cores = cpu_reference_throughput(cfg, sd_np, sample, steps, warmup)
+        return v, sec, cores, "reference", (f"the reference's own CLIP.forward (lib/models/clip_openai_pe_res_v1.py, unmodified, "
+                                            f"staged under baseline/_ref) + symmetric CE, fp32, {sample} pairs x {steps} timed steps")
+    v, sec, cores = cpu_oracle_throughput(cfg, sd_np, sample, steps, warmup)
+    return v, sec, cores, "port", f"CPU oracle (torch fp32 port of the reference forward + loss), {sample} pairs x {steps} timed steps"
+
+
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
     sd_np = synth.synth_state_dict(cfg, seed=0)
     sample = args.cpu_sample
-    value, sec_per_step, cores = cpu_oracle_throughput(cfg, sd_np, sample, args.steps, args.warmup)
-    desc = f"{sample} pairs per step of the same synthetic workload, fp32, {cores} host threads"
+    value, sec_per_step, cores, kind, desc = cpu_baseline(cfg, sd_np, sample, max(args.steps, 3), max(args.warmup, 1))
+    desc += f", {cores} host threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, cfg, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------- comparators
+def eager_reference_on_gpu(cfg, sd_np, dev, batch: int, seed: int = 1234):
+    """the SAME reference PyTorch forward run eagerly on this B200 (cuBLAS / cuDNN / ATen),
+    in true fp32, with TF32 tensor cores, and under autocast(bf16); forward + symmetric CE, pairs/s by CUDA events."""
+    import torch.nn.functional as F
+    from oracle import ref_shim
+    model = ref_shim.build_reference_model(cfg, state_dict=sd_np).to(dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    out = {}
+    while batch >= 256:
+        try:
+            img = torch.randn(batch, 3, cfg.image_resolution, cfg.image_resolution, device=dev, generator=g)
+            tok = torch.from_numpy(synth.synth_tokens(batch, seed, cfg.context_length, cfg.vocab_size)).to(dev)
+            target = torch.arange(batch, device=dev)
+
+            def step():
+                logits = model(img, tok)
+                return 0.5 * (F.cross_entropy(logits.float(), target) + F.cross_entropy(logits.float().t(), target))
+
+            for name, tf32, amp in (("fp32", False, False), ("tf32", True, False), ("autocast_bf16", True, True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    step()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 2
+                    e0.record()
+                    for _ in range(reps):
+                        loss = step()
+                    e1.record()
+                    torch.cuda.synchronize()
+                sec = e0.elapsed_time(e1) / 1e3 / reps
+                out[name] = {"value": batch / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "loss": float(loss)}
+            out["batch"] = batch
+            out["what"] = ("the reference's unmodified CLIP.forward (baseline/_ref) + symmetric CE, PyTorch eager on this GPU, "
+                           "same synthetic weights; 1 warm-up + 2 timed steps per mode")
+            break
+        except torch.OutOfMemoryError:
+            out = {}
+            batch //= 2
+            torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def nccl_loss_comparator(model, L, h, dev, B, world, sp, scale):
+    """The reference's exchange (two NCCL all-gathers, lib/utils/comm.py:140-154) + logits (M.py:3141) + symmetric CE in
+    PyTorch, against the fused loss kernel with the in-kernel NVLink gather, on the same per-rank features.  Device
+    time, max over ranks."""
+    import torch.nn.functional as F
+    from msclip_b200 import _lib
+    from msclip_b200.comm import gather_tensors
+    g = torch.Generator(device=dev).manual_seed(99 + torch.distributed.get_rank())
+    fi = F.normalize(torch.randn(B, 512, device=dev, generator=g), dim=-1)
+    ft = F.normalize(fi + 0.3 * torch.randn(B, 512, device=dev, generator=g), dim=-1)
+    parts = torch.zeros(2, device=dev)
+    target = torch.arange(B * world, device=dev)
+
+    def ours():
+        _lib.check(L.msclip_contrastive_loss_features(h, C.c_void_p(fi.data_ptr()), C.c_void_p(ft.data_ptr()), B, scale,
+                                                      C.c_void_p(parts.data_ptr()), None, sp), "contrastive_loss_features")
+
+    def nccl(tf32):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        fa, ta = gather_tensors(fi), gather_tensors(ft)
+        logits = scale * fa @ ta.t()
+        return 0.5 * (F.cross_entropy(logits, target) + F.cross_entropy(logits.t(), target))
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms), r
+
+    ms_ours, _ = timed(ours)
+    p = parts.clone()
+    torch.distributed.all_reduce(p)
+    loss_ours = float(p.sum() / (2.0 * world * B))
+    ms_fp32, loss_fp32 = timed(lambda: nccl(False))
+    ms_tf32, _ = timed(lambda: nccl(True))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return {"fused_p2p_loss_ms": ms_ours, "nccl_allgather_matmul_ce_fp32_ms": ms_fp32, "nccl_allgather_matmul_ce_tf32_ms": ms_tf32,
+            "loss_fused": loss_ours, "loss_nccl_fp32": float(loss_fp32), "global_batch": B * world,
+            "what": "loss stage only, same per-rank features: ours = msclip_contrastive_loss_features (publish + in-kernel NVLink "
+                    "gather + fused similarity/CE); comparator = 2 x dist.all_gather + [G,G] logits + 2 x F.cross_entropy"}
+
+
 def workload_config(args, cfg, world):
+    if args.global_batch:
+        b_local = args.global_batch // world
+        name = (f"MS-CLIP-S ViT-B/{cfg.patch_size} full {cfg.layers}-layer shared encoder, global batch {args.global_batch} "
+                f"synthetic 224^2 + 77-token pairs: {b_local} per GPU in micro-batches of {min(args.batch, b_local)} "
+                f"(embeddings retained), one contrastive loss over all {args.global_batch}")
+        return {"workload": name, "per_gpu_batch": b_local, "micro_batch": min(args.batch, b_local), "global_batch": args.global_batch,
+                "image": "3x224x224 f32", "tokens": cfg.context_length, "parallelism": f"dp{world}",
+                "l2": "inputs (2.5 GB per micro-batch) exceed the 126 MB L2"}
     name = (f"MS-CLIP-S ViT-B/{cfg.patch_size} full {cfg.layers}-layer shared encoder, batch {args.batch} synthetic "
             f"224^2 + 77-token pairs per GPU")
     return {"workload": name, "per_gpu_batch": args.batch, "global_batch": args.batch * world, "image": "3x224x224 f32",
@@ -173,13 +327,25 @@ def run_ours(args, cfg, rank, world, local):
     dev = torch.device("cuda", local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    # weak scaling (default): B = --batch pairs per rank and step, one msclip_forward_loss.
+    # --global-batch G (strong scaling): every rank owns G / world pairs, encoded in micro-batches of --batch pairs
+    # whose embeddings are retained (msclip_encode_pairs), then ONE loss over all G.
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be divisible by the number of GPUs")
+        B = args.global_batch // world
+        micro = min(args.batch, B)
+        if B % micro:
+            raise SystemExit("--global-batch / gpus must be a multiple of --batch (the micro-batch)")
+    else:
+        B = micro = args.batch
+    n_micro = B // micro
     sd_np = synth.synth_state_dict(cfg, seed=0)
     model = CLIP(cfg, precision=args.precision)
     model.load_state_dict({k: torch.as_tensor(v) for k, v in sd_np.items()})
     model = model.to(dev).eval()
     model._sync_weights()
-    if world > 1:
+    if world > 1 or n_micro > 1:
         model.setup_data_parallel(B)
 
     # synthetic shard of this rank (rows rank*B .. rank*B+B of the global batch)
@@ -194,10 +360,23 @@ def run_ours(args, cfg, rank, world, local):
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
 
+    scale = C.c_float()
+    _lib.check(L.msclip_logit_scale_exp(h, C.byref(scale)), "msclip_logit_scale_exp")
+    img_micro_bytes = micro * 3 * cfg.image_resolution * cfg.image_resolution * 4
+    tok_micro_bytes = micro * cfg.context_length * 8
+
     def step_device():
-        _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_dev.data_ptr()), _lib.F32, C.c_void_p(tok_dev.data_ptr()), B,
-                                         C.c_void_p(parts.data_ptr()), C.c_void_p(loss_dev.data_ptr()) if world == 1 else None,
-                                         sp), "msclip_forward_loss")
+        if n_micro == 1:
+            _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_dev.data_ptr()), _lib.F32, C.c_void_p(tok_dev.data_ptr()), B,
+                                             C.c_void_p(parts.data_ptr()), C.c_void_p(loss_dev.data_ptr()) if world == 1 else None,
+                                             sp), "msclip_forward_loss")
+            return
+        for m in range(n_micro):
+            _lib.check(L.msclip_encode_pairs(h, C.c_void_p(img_dev.data_ptr() + m * img_micro_bytes), _lib.F32,
+                                             C.c_void_p(tok_dev.data_ptr() + m * tok_micro_bytes), micro, m * micro, sp),
+                       "msclip_encode_pairs")
+        _lib.check(L.msclip_contrastive_loss(h, B, scale.value, C.c_void_p(parts.data_ptr()),
+                                             C.c_void_p(loss_dev.data_ptr()) if world == 1 else None, sp), "msclip_contrastive_loss")
 
     def barrier():
         torch.cuda.synchronize()
@@ -237,23 +416,37 @@ def run_ours(args, cfg, rank, world, local):
     # ---- end to end through the public C ABI with pinned HOST buffers
     e2e = None
     if not args.no_e2e:
-        img_host = torch.empty(img_dev.shape, dtype=torch.float32).pin_memory()
-        img_host.copy_(img_dev)
-        tok_host = torch.from_numpy(tok_np).pin_memory()
+        # pinned host inputs: the whole step when it is one batch, else two micro-batch buffers used alternately
+        # (every micro-batch is still copied host -> device inside the timed region)
+        n_host = min(n_micro, 2)
+        img_host = torch.empty((n_host * micro,) + tuple(img_dev.shape[1:]), dtype=torch.float32).pin_memory()
+        img_host.copy_(img_dev[:n_host * micro])
+        tok_host = torch.from_numpy(tok_np[:n_host * micro]).pin_memory()
         out_host = torch.zeros(3).pin_memory()
 
-        def stage_host():
-            _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host.data_ptr()), _lib.F32, B, sp), "msclip_stage_images")
+        def stage_host(m=0):
+            _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host.data_ptr() + m * img_micro_bytes), _lib.F32, micro, sp),
+                       "msclip_stage_images")
 
         def step_host():
-            # a training loop's input pipeline: the images of the NEXT step start their H2D copy (second staging
-            # slot) before this step is issued, so every step still moves its full 2.47 GB over PCIe, overlapped
-            # with compute; tokens (2.5 MB) and the loss read-back ride the compute stream
-            stage_host()
-            _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_host.data_ptr()), _lib.F32, C.c_void_p(tok_host.data_ptr()), B,
-                                             C.c_void_p(out_host.data_ptr()),
-                                             C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
-                       "msclip_forward_loss(host)")
+            # a training loop's input pipeline: the images of the NEXT (micro-)step start their H2D copy (second staging
+            # slot) before this one is issued, so every step still moves all of its image bytes over PCIe, overlapped
+            # with compute; tokens (2.5 MB per 4096) and the loss read-back ride the compute stream
+            if n_micro == 1:
+                stage_host()
+                _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_host.data_ptr()), _lib.F32, C.c_void_p(tok_host.data_ptr()), B,
+                                                 C.c_void_p(out_host.data_ptr()),
+                                                 C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
+                           "msclip_forward_loss(host)")
+                return
+            for m in range(n_micro):
+                stage_host((m + 1) % n_host)
+                _lib.check(L.msclip_encode_pairs(h, C.c_void_p(img_host.data_ptr() + (m % n_host) * img_micro_bytes), _lib.F32,
+                                                 C.c_void_p(tok_host.data_ptr() + (m % n_host) * tok_micro_bytes), micro, m * micro, sp),
+                           "msclip_encode_pairs(host)")
+            _lib.check(L.msclip_contrastive_loss(h, B, scale.value, C.c_void_p(out_host.data_ptr()),
+                                                 C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
+                       "msclip_contrastive_loss(host)")
 
         stage_host()
         for _ in range(3):
@@ -263,43 +456,47 @@ def run_ours(args, cfg, rank, world, local):
         loss_f32_host = float(out_host[2])
         odt_img = _lib.torch_operand_dtype(args.precision)
         e2e = {"value": B * world * e2e_steps / sec_h, "unit": UNIT, "ms_per_step": sec_h / e2e_steps * 1e3,
-               "h2d_bytes_per_step": int(img_host.numel() * 4 + tok_host.numel() * 8), "d2h_bytes_per_step": 12 if world == 1 else 8,
-               "steps": e2e_steps, "api": "msclip_stage_images (prefetch of the next step) + msclip_forward_loss, pinned host pointers",
+               "h2d_bytes_per_step": int(n_micro * (img_micro_bytes + tok_micro_bytes)), "d2h_bytes_per_step": 12 if world == 1 else 8,
+               "steps": e2e_steps, "api": ("msclip_stage_images (prefetch of the next step) + msclip_forward_loss, pinned host pointers"
+                                           if n_micro == 1 else
+                                           "per micro-batch: msclip_stage_images (prefetch of the next one) + msclip_encode_pairs; "
+                                           "then msclip_contrastive_loss; pinned host pointers"),
                "host_image_dtype": "f32"}
         # what bounds it: the raw pinned host->device rate of this box
         cp0, cp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cp0.record(stream)
-        img_dev.copy_(img_host, non_blocking=True)
+        img_dev[:n_host * micro].copy_(img_host, non_blocking=True)
         cp1.record(stream)
         torch.cuda.synchronize()
         e2e["h2d_gb_per_s_measured"] = img_host.numel() * 4 / (cp0.elapsed_time(cp1) / 1e3) / 1e9
         # secondary: the same call with the images already in the 16-bit operand type on the host (the reference
         # casts with image.type(self.dtype) before the first conv, M.py:2980; the first kernel rounds fp32 pixels
         # to this type anyway, so the result is bit-identical) - half the PCIe bytes
-        img_host16 = torch.empty(img_dev.shape, dtype=odt_img).pin_memory()
-        img_host16.copy_(img_dev)
-        code16 = _lib.F16 if args.precision == "fp16" else _lib.BF16
+        if n_micro == 1:
+            img_host16 = torch.empty(img_dev.shape, dtype=odt_img).pin_memory()
+            img_host16.copy_(img_dev)
+            code16 = _lib.F16 if args.precision == "fp16" else _lib.BF16
 
-        def step_host16():
+            def step_host16():
+                _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host16.data_ptr()), code16, B, sp), "msclip_stage_images")
+                _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_host16.data_ptr()), code16, C.c_void_p(tok_host.data_ptr()), B,
+                                                 C.c_void_p(out_host.data_ptr()),
+                                                 C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
+                           "msclip_forward_loss(host, 16-bit images)")
+
             _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host16.data_ptr()), code16, B, sp), "msclip_stage_images")
-            _lib.check(L.msclip_forward_loss(h, C.c_void_p(img_host16.data_ptr()), code16, C.c_void_p(tok_host.data_ptr()), B,
-                                             C.c_void_p(out_host.data_ptr()),
-                                             C.c_void_p(out_host.data_ptr() + 8) if world == 1 else None, sp),
-                       "msclip_forward_loss(host, 16-bit images)")
-
-        _lib.check(L.msclip_stage_images(h, C.c_void_p(img_host16.data_ptr()), code16, B, sp), "msclip_stage_images")
-        for _ in range(3):
-            step_host16()
-        sec_h16, _ = timed(step_host16, e2e_steps)
-        e2e["with_16bit_host_images"] = {"value": B * world * e2e_steps / sec_h16, "ms_per_step": sec_h16 / e2e_steps * 1e3,
-                                         "h2d_bytes_per_step": int(img_host16.numel() * 2 + tok_host.numel() * 8),
-                                         "loss_bit_identical_to_f32_images": bool(float(out_host[2]) == loss_f32_host) if world == 1 else None}
-        del img_host16
+            for _ in range(3):
+                step_host16()
+            sec_h16, _ = timed(step_host16, e2e_steps)
+            e2e["with_16bit_host_images"] = {"value": B * world * e2e_steps / sec_h16, "ms_per_step": sec_h16 / e2e_steps * 1e3,
+                                             "h2d_bytes_per_step": int(img_host16.numel() * 2 + tok_host.numel() * 8),
+                                             "loss_bit_identical_to_f32_images": bool(float(out_host[2]) == loss_f32_host) if world == 1 else None}
+            del img_host16
         del img_host
 
     # ---- roofline of the dominant kernel: the shared-block fc1 GEMM (+bias+QuickGELU) at the text-tower M
     pk = peaks()
-    M, N, K = B * cfg.context_length, 4 * cfg.width, cfg.width
+    M, N, K = micro * cfg.context_length, 4 * cfg.width, cfg.width
     odt = _lib.torch_operand_dtype(args.precision)
     a = torch.randn(M, K, device=dev).to(odt)
     w = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(odt)
@@ -332,20 +529,28 @@ def run_ours(args, cfg, rank, world, local):
                                "note": "per-GPU pairs/s x 23.549 GFLOP/pair against the sustained cuBLAS peak"}}
     del a, w, o
 
+    # ---- comparators: the reference forward run eagerly on this GPU; NCCL exchange + logits + CE
+    comparators = {}
+    if world > 1 and not args.no_comparators:
+        comparators["loss_stage_vs_nccl"] = nccl_loss_comparator(model, L, h, dev, B, world, sp, scale.value)
     if rank != 0:
         return
+    if world == 1 and not args.no_comparators and reference_module_available():
+        free_before = torch.cuda.mem_get_info()[0]
+        comparators["reference_eager_b200"] = eager_reference_on_gpu(cfg, sd_np, dev, min(micro, 4096))
+        comparators["reference_eager_b200"]["free_hbm_gb_before"] = free_before / 1e9
     cpu = None
     if not args.no_cpu:
-        v, sec_step, cores = cpu_oracle_throughput(cfg, sd_np, args.cpu_sample, 2, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"CPU oracle (torch fp32 port of the reference forward + loss), {args.cpu_sample} pairs x 2 timed steps"}
+        v, sec_step, cores, kind, desc = cpu_baseline(cfg, sd_np, args.cpu_sample, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-        "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak",
+        "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic", "config": workload_config(args, cfg, world), "impl": "ours",
         "loss": loss_value, "loss_expected_ln_G": math.log(B * world),
         "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary, "roofline": roofline, "cpu_baseline": cpu,
-        "device_bytes": int(L.msclip_device_bytes(h)),
+        "device_bytes": int(L.msclip_device_bytes(h)), "comparators": comparators or None,
     }
     emit(line)
 
@@ -378,7 +583,11 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="pairs per GPU per step")
     ap.add_argument("--patch", type=int, default=32, choices=[16, 32])
     ap.add_argument("--layers", type=int, default=12)
-    ap.add_argument("--cpu-sample", type=int, default=32, help="pairs per CPU-oracle step")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: total pairs per step over all GPUs (e.g. 32768), encoded per rank in micro-batches "
+                         "of --batch pairs with ONE loss over the whole global batch; 0 = weak scaling (--batch pairs per GPU)")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="pairs per step of the CPU reference arm")
+    ap.add_argument("--no-comparators", action="store_true", help="skip the eager-PyTorch-on-B200 / NCCL comparators")
     ap.add_argument("--min-warmup", type=int, default=3, help="timing rule: at least 3 warm-up steps (lower only for profiling)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="MMA operand type (library build)")
     ap.add_argument("--no-e2e", action="store_true")

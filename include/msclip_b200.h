@@ -97,8 +97,11 @@ int msclip_forward(msclip_handle h, const void* image, int image_dtype, const in
 /* ---- sharded contrastive loss (data parallel, one process per GPU) -----------------------------------
  * Each rank owns `b_local` pairs; global row index = rank * b_local + i (rank order of gather_tensors,
  * comm.py:150-153).  The embedding exchange is NOT a collective: every rank publishes its normalised
- * bf16 embeddings in a library-owned, IPC-exported buffer and the loss kernel of every other rank loads
- * them over NVLink.  Setup (once):
+ * embeddings (IEEE fp16 in both library builds: |x| <= 1, 11-bit significand) in a library-owned, IPC-exported
+ * buffer and the loss kernel of every other rank loads them over NVLink; the stream waits for the peers' publish
+ * flags with stream memory operations (no kernel spins, no time-out: a late rank is waited for like in a collective).
+ * At most 64 ranks of one NVLink domain (CUDA IPC); beyond that use gather_tensors + msclip_similarity_logits.
+ * Setup (once):
  *   1. msclip_comm_init(h, rank, world, max_b_local)              allocates the exchange buffer
  *   2. msclip_comm_export(h, handle_bytes[64])                    -> exchange the 64-byte handles out of band
  *   3. msclip_comm_import(h, all_handles[world*64])               (torch.distributed / MPI / files ...)
@@ -106,6 +109,10 @@ int msclip_forward(msclip_handle h, const void* image, int image_dtype, const in
 int msclip_comm_init(msclip_handle h, int rank, int world, int max_b_local);
 int msclip_comm_export(msclip_handle h, void* handle_out_64);
 int msclip_comm_import(msclip_handle h, const void* handles_world_x_64);
+/* Same-process peers (one process driving several GPUs with peer access enabled, or several handles on one GPU):
+ * instead of steps 2-3 hand every handle the others' exchange buffers as plain device pointers. */
+int msclip_comm_buffer(msclip_handle h, void** base_out);
+int msclip_comm_import_pointers(msclip_handle h, void* const* bases_world);
 
 /* Loss of the features produced by the LAST msclip_encode_image / msclip_encode_text calls of this handle
  * (kept on the device in bf16), batch b_local each.  partial_out[2] (host or device) receives this rank's
@@ -113,7 +120,19 @@ int msclip_comm_import(msclip_handle h, const void* handles_world_x_64);
  * With world == 1 loss_out (optional, may be NULL) receives the final loss. */
 int msclip_contrastive_loss(msclip_handle h, int b_local, float scale, float* partial_out, float* loss_out,
                             void* stream);
-/* encode_image + encode_text + msclip_contrastive_loss with scale = exp(logit_scale). */
+/* The same loss for embeddings computed elsewhere: img_feat / txt_feat [b_local, embed_dim] f32, already normalised
+ * (what gather_tensors would be given, M.py:3139-3140); device or host pointers. */
+int msclip_contrastive_loss_features(msclip_handle h, const float* img_feat, const float* txt_feat, int b_local,
+                                     float scale, float* partial_out, float* loss_out, void* stream);
+/* Micro-batching (BASELINE.json: global batch 32 768 on 1 / 2 / 4 GPUs): run both towers
+ * for b_micro pairs and keep their normalised embeddings as rows [row_offset, row_offset + b_micro) of this rank's
+ * shard of the NEXT msclip_contrastive_loss.  row_offset must be 0 (new shard) or the number of rows encoded so far;
+ * the shard must fit the exchange buffer (msclip_comm_init(h, rank, world, b_local) first, also with world == 1).
+ * n_micro calls followed by msclip_contrastive_loss(h, n_micro * b_micro, ...) give the loss over the whole global
+ * batch - the same value as one msclip_forward_loss over all rows at once. */
+int msclip_encode_pairs(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int b_micro,
+                        int row_offset, void* stream);
+/* msclip_encode_pairs(row_offset = 0) + msclip_contrastive_loss with scale = exp(logit_scale). */
 int msclip_forward_loss(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int b_local,
                         float* partial_out, float* loss_out, void* stream);
 

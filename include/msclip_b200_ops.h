@@ -85,7 +85,7 @@ int msclip_op_front_conv(const void* img, int dtype, int batch, int height, int 
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                               const float* b, float* x_out, int batch, int grid, void* stream);
 /* parts2[0] = sum_i (lse_j s_ij - s_ii), parts2[1] = sum_j (lse_i s_ij - s_jj), s = scale * img . txt^T */
-int msclip_op_contrastive_lse(const void* img_bf16, const void* txt_bf16, int b, float scale, void* workspace,
+int msclip_op_contrastive_lse(const void* img_f16, const void* txt_f16, int b, float scale, void* workspace,
                               float* parts2, void* stream);
 size_t msclip_op_contrastive_lse_workspace(int b);
 

@@ -62,8 +62,12 @@ _SIGNATURES = {
     "msclip_comm_init": (_I, [_P, _I, _I, _I]),
     "msclip_comm_export": (_I, [_P, _P]),
     "msclip_comm_import": (_I, [_P, _P]),
+    "msclip_comm_buffer": (_I, [_P, C.POINTER(_P)]),
+    "msclip_comm_import_pointers": (_I, [_P, C.POINTER(_P)]),
     "msclip_contrastive_loss": (_I, [_P, _I, _F, _P, _P, _P]),
     "msclip_forward_loss": (_I, [_P, _P, _I, _P, _I, _P, _P, _P]),
+    "msclip_encode_pairs": (_I, [_P, _P, _I, _P, _I, _I, _P]),
+    "msclip_contrastive_loss_features": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "msclip_launch_count": (_L, [_P]),
     "msclip_device_bytes": (_L, [_P]),
     # include/msclip_b200_ops.h

@@ -62,11 +62,34 @@ def exchange_bytes(payload: bytes, group=None) -> bytes:
     return b"".join(bytes(p.cpu().tolist()) for p in parts)
 
 
+MAX_P2P_WORLD = 64     # publish-flag slots of the exchange buffer (msclip_comm_init refuses more)
+
+
+def same_node(group=None) -> bool:
+    """True when every rank of the group runs on this host (CUDA IPC reaches only GPUs of one node)."""
+    import socket
+    rank, world = rank_world(group)
+    if world == 1:
+        return True
+    names = [None] * world
+    dist.all_gather_object(names, socket.gethostname(), group=group)
+    return len(set(names)) == 1
+
+
 def setup_peer_exchange(handle, max_b_local: int, group=None, precision=None):
     """comm_init -> export IPC handle -> all-gather the 64-byte handles -> import.  Returns
-    (rank, world, max_b_local)."""
+    ((rank, world, max_b_local), mode): mode "p2p" = in-kernel NVLink exchange; "gather" = the ranks span several
+    nodes (or exceed the flag slots), so the caller must use ``gather_tensors`` + logits + CE instead.  Every rank
+    must ask for the same ``max_b_local``."""
     rank, world = rank_world(group)
     L = _lib.lib(precision)
+    if world > 1:
+        sizes = [None] * world
+        dist.all_gather_object(sizes, int(max_b_local), group=group)
+        if len(set(sizes)) != 1:
+            raise ValueError(f"setup_peer_exchange: max_b_local differs between ranks: {sizes}")
+        if world > MAX_P2P_WORLD or not same_node(group):
+            return (rank, world, int(max_b_local)), "gather"
     _lib.check(L.msclip_comm_init(handle, rank, world, int(max_b_local)), "msclip_comm_init", precision)
     if world > 1:
         buf = (C.c_uint8 * 64)()
@@ -76,4 +99,4 @@ def setup_peer_exchange(handle, max_b_local: int, group=None, precision=None):
         arr = (C.c_uint8 * len(everyone)).from_buffer_copy(everyone)
         _lib.check(L.msclip_comm_import(handle, arr), "msclip_comm_import", precision)
         dist.barrier(group)
-    return rank, world, int(max_b_local)
+    return (rank, world, int(max_b_local)), "p2p"

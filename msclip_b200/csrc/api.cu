@@ -161,10 +161,32 @@ int msclip_comm_import(msclip_handle h, const void* handles) {
   return comm_import(h, handles);
 }
 
+int msclip_comm_buffer(msclip_handle h, void** base_out) {
+  MSCLIP_REQUIRE(h != nullptr && base_out != nullptr && h->xchg != nullptr, "msclip_comm_buffer: call msclip_comm_init first");
+  *base_out = h->xchg;
+  return 0;
+}
+int msclip_comm_import_pointers(msclip_handle h, void* const* bases_world) {
+  MSCLIP_REQUIRE(h != nullptr && bases_world != nullptr, "null argument");
+  return comm_import_pointers(h, bases_world);
+}
+
 int msclip_contrastive_loss(msclip_handle h, int b_local, float scale, float* partial_out, float* loss_out,
                             void* stream) {
   MSCLIP_REQUIRE(h != nullptr, "null handle");
   return engine_contrastive_loss(h, b_local, scale, partial_out, loss_out, as_stream(stream));
+}
+
+int msclip_contrastive_loss_features(msclip_handle h, const float* img_feat, const float* txt_feat, int b_local, float scale,
+                                     float* partial_out, float* loss_out, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_contrastive_loss_features(h, img_feat, txt_feat, b_local, scale, partial_out, loss_out, as_stream(stream));
+}
+
+int msclip_encode_pairs(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int b_micro,
+                        int row_offset, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_encode_pairs(h, image, image_dtype, tokens, b_micro, row_offset, as_stream(stream));
 }
 
 int msclip_forward_loss(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int b_local,
@@ -239,15 +261,15 @@ int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9
                               const float* b, float* x_out, int batch, int grid, void* stream) {
   return launch_adapter_fuse_ln(x, t, dw_w9, dw_bias, w, b, x_out, batch, grid, nullptr, nullptr, as_stream(stream));
 }
-int msclip_op_contrastive_lse(const void* img_bf16, const void* txt_bf16, int b, float scale, void* workspace,
+int msclip_op_contrastive_lse(const void* img_f16, const void* txt_f16, int b, float scale, void* workspace,
                               float* parts2, void* stream) {
   // single-process form: shard tables with one entry each, built in the caller-provided workspace tail
   const size_t need = contrastive_loss_workspace_bytes(1, b);
   const void** tab = reinterpret_cast<const void**>(static_cast<uint8_t*>(workspace) + ((need + 15) & ~size_t(15)));
-  const void* host_tab[2] = {img_bf16, txt_bf16};
+  const void* host_tab[2] = {img_f16, txt_f16};
   MSCLIP_CHECK_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice, as_stream(stream)));
-  return launch_contrastive_loss_ex(static_cast<const op16*>(img_bf16), static_cast<const op16*>(txt_bf16),
-                                    reinterpret_cast<const op16* const*>(tab), reinterpret_cast<const op16* const*>(tab + 1),
+  return launch_contrastive_loss_ex(static_cast<const emb16*>(img_f16), static_cast<const emb16*>(txt_f16),
+                                    reinterpret_cast<const emb16* const*>(tab), reinterpret_cast<const emb16* const*>(tab + 1),
                                     nullptr, 0, 1, 0, b, 512, scale, workspace, parts2, as_stream(stream));
 }
 size_t msclip_op_contrastive_lse_workspace(int b) { return ((contrastive_loss_workspace_bytes(1, b) + 15) & ~size_t(15)) + 64; }

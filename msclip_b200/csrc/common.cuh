@@ -328,14 +328,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // Instruction descriptor for kind::f16: D=fp32 (bits 4-5 = 1), A=B=op16 (bits 7-9, 10-12 = 1),
 // both operands K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t umma_idesc_f32acc(int m, int n) {
-  return (1u << 4) | (kUmmaOperandFormat << 7) | (kUmmaOperandFormat << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc_fmt(int m, int n, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc(int m, int n) { return umma_idesc_f32acc_fmt(m, n, kUmmaOperandFormat); }
 
 // ------------------------------------------------------------------------------------ host: TMA maps
 // rows x cols op16 row-major (pitch ld elements), box = box_rows x 64 columns, 128-B swizzle,
 // out-of-bounds elements read as zero.
+int stream_wait_value_geq(cudaStream_t stream, const uint32_t* addr, uint32_t value);  // 0 = queued
 int make_tmap_op16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);
 

@@ -276,7 +276,7 @@ adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t,
 
 // one warp per row of width E (multiple of 4, <= 1024)
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
-l2norm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, op16* __restrict__ out_bf16, int rows, int E,
+l2norm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, emb16* __restrict__ out_f16, int rows, int E,
               int normalise) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
@@ -298,9 +298,11 @@ l2norm_kernel(const float* __restrict__ x, float* __restrict__ out_f32, op16* __
     if (c >= n4) continue;
     const float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
     if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(r) * E)[c] = o;
-    if (out_bf16)
-      reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(r) * E)[c] =
-          make_uint2(pack16(o.x, o.y), pack16(o.z, o.w));
+    if (out_f16) {
+      const __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+      reinterpret_cast<uint2*>(out_f16 + static_cast<long long>(r) * E)[c] =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
   }
 }
 
@@ -391,11 +393,11 @@ int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, c
   return 0;
 }
 
-int launch_l2norm(const float* x, float* out_f32, op16* out_bf16, int rows, int E, int normalise,
+int launch_l2norm(const float* x, float* out_f32, emb16* out_f16, int rows, int E, int normalise,
                   cudaStream_t stream) {
   if (rows <= 0) return 0;
   MSCLIP_REQUIRE(E % 4 == 0 && E <= 1024, "l2norm: width must be a multiple of 4 and <= 1024");
-  l2norm_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(x, out_f32, out_bf16,
+  l2norm_kernel<<<(rows + kRowsPerBlock - 1) / kRowsPerBlock, 32 * kRowsPerBlock, 0, stream>>>(x, out_f32, out_f16,
                                                                                               rows, E, normalise);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;

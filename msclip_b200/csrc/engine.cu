@@ -232,6 +232,14 @@ struct Packer {
   }
 };
 
+// MSCLIP_LN_FOLD=1 folds the LayerNorms in front of QKV / fc1 into the GEMM epilogues (gemm_common.cuh).  Correct and
+// parity-tested, but the GEMMs of this path are epilogue-bound: the extra epilogue work costs more (QKV +15 %,
+// fc1 +17 %, out-proj +43 %, fc2 +24 %) than the 47 LayerNorm launches it removes (8.2 ms), so it stays off.
+static const bool g_ln_fold = [] {
+  const char* e = getenv("MSCLIP_LN_FOLD");
+  return e != nullptr && e[0] == '1';
+}();
+
 static void pack_block(Packer& P, const std::string& p, BlockWeights& bw, const float* qscale_dev,
                        const BlockWeights* share_from) {
   const std::string& shared_p = p;
@@ -254,7 +262,8 @@ static void pack_block(Packer& P, const std::string& p, BlockWeights& bw, const 
   bw.ln1_b = P.keep_f32(p + ".ln_1.bias");
   bw.ln2_w = P.keep_f32(p + ".ln_2.weight");
   bw.ln2_b = P.keep_f32(p + ".ln_2.bias");
-  // LN fold: this tower's gamma / beta folded into its own copies of the QKV and fc1 weights
+  // LN fold (opt-in experiment): this tower's gamma / beta folded into its own copies of the QKV and fc1 weights
+  if (!g_ln_fold) return;
   P.ln_fold(p + ".attn.in_proj_weight", p + ".attn.in_proj_bias", qscale_dev, p + ".ln_1", &bw.w_qkv_ln, &bw.cs_qkv,
             &bw.b_qkv_ln);
   P.ln_fold(p + ".mlp.c_fc.weight", p + ".mlp.c_fc.bias", nullptr, p + ".ln_2", &bw.w_fc1_ln, &bw.cs_fc1, &bw.b_fc1_ln);
@@ -463,9 +472,10 @@ static int require_ready(msclip_ctx* h) {
 }
 
 // exchange buffer layout helpers ------------------------------------------------------------------------
+constexpr int kMaxWorld = 64;  // publish flags: 64 x uint32 = the 256-byte tail of the exchange buffer
 static size_t xchg_feat_bytes(const msclip_ctx* h) { return static_cast<size_t>(h->max_b_local) * h->cfg.embed_dim * 2; }
-static op16* xchg_slot(const msclip_ctx* h, void* base, int parity, int modality) {
-  return reinterpret_cast<op16*>(static_cast<uint8_t*>(base) + (parity * 2 + modality) * xchg_feat_bytes(h));
+static emb16* xchg_slot(const msclip_ctx* h, void* base, int parity, int modality) {
+  return reinterpret_cast<emb16*>(static_cast<uint8_t*>(base) + (parity * 2 + modality) * xchg_feat_bytes(h));
 }
 static uint32_t* xchg_flags(const msclip_ctx* h, void* base) {
   return reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(base) + 4 * xchg_feat_bytes(h));
@@ -487,13 +497,16 @@ static int upload_tables(msclip_ctx* h) {
 
 int comm_init(msclip_ctx* h, int rank, int world, int max_b_local) {
   MSCLIP_REQUIRE(world >= 1 && rank >= 0 && rank < world && max_b_local >= 1, "comm_init: bad rank/world/batch");
+  // one publish flag per rank in a 256-byte flag area; the exchange is CUDA IPC, i.e. one NVLink domain / node
+  MSCLIP_REQUIRE(world <= kMaxWorld, "comm_init: at most 64 ranks (single NVLink domain) - use the gather_tensors path beyond");
   if (h->xchg) {
     MSCLIP_CHECK_CUDA(cudaDeviceSynchronize());
     for (int r = 0; r < static_cast<int>(h->peer_base.size()); ++r)
-      if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+      if (r != h->rank && h->peer_base[r] && !h->peers_borrowed) cudaIpcCloseMemHandle(h->peer_base[r]);
     cudaFree(h->xchg);
     h->xchg = nullptr;
   }
+  h->peers_borrowed = false;
   h->rank = rank;
   h->world = world;
   h->max_b_local = max_b_local;
@@ -503,7 +516,7 @@ int comm_init(msclip_ctx* h, int rank, int world, int max_b_local) {
   h->peer_base.assign(world, nullptr);
   h->peer_base[rank] = h->xchg;
   h->epoch = 0;
-  h->last_img_batch = h->last_txt_batch = -1;
+  h->img_rows = h->txt_rows = 0;
   if (world == 1) MSCLIP_TRY(upload_tables(h));
   return 0;
 }
@@ -530,6 +543,19 @@ int comm_import(msclip_ctx* h, const void* handles) {
   return upload_tables(h);
 }
 
+// Peers that live in THIS process (one process driving several GPUs with peer access enabled, or several handles on
+// one GPU): their exchange buffers are plain device pointers, no IPC handle needed.
+int comm_import_pointers(msclip_ctx* h, void* const* bases) {
+  MSCLIP_REQUIRE(h->xchg != nullptr, "comm_import_pointers: call msclip_comm_init first");
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank) continue;
+    MSCLIP_REQUIRE(bases[r] != nullptr, "comm_import_pointers: null peer buffer");
+    h->peer_base[r] = bases[r];
+  }
+  h->peers_borrowed = true;
+  return upload_tables(h);
+}
+
 // world == 1 needs no msclip_comm_* calls: the exchange buffer is created (and grown) on demand
 static int ensure_xchg(msclip_ctx* h, int batch) {
   if (h->xchg == nullptr || (h->world == 1 && batch > h->max_b_local)) return comm_init(h, 0, 1, std::max(batch, 256));
@@ -537,14 +563,6 @@ static int ensure_xchg(msclip_ctx* h, int batch) {
 }
 
 // ------------------------------------------------------------------------------------ shared block
-// MSCLIP_LN_FOLD=1 folds the LayerNorms in front of QKV / fc1 into the GEMM epilogues (gemm_common.cuh).  Correct and
-// parity-tested, but the GEMMs of this path are epilogue-bound: the extra epilogue work costs more (QKV +15 %,
-// fc1 +17 %, out-proj +43 %, fc2 +24 %) than the 47 LayerNorm launches it removes (8.2 ms), so it stays off.
-static const bool g_ln_fold = [] {
-  const char* e = getenv("MSCLIP_LN_FOLD");
-  return e != nullptr && e[0] == '1';
-}();
-
 // rec: the two row-record buffers of the LN fold; rec[0] describes x on entry and on return (hbuf = centred copy of x)
 static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, op16* hbuf,
                      op16* qkv, op16* attn, op16* fc1, float** rec, cudaStream_t s) {
@@ -598,7 +616,7 @@ static const int kTowerChunk = 4096;               // sequences per pass through
 // image tower for `batch` images already on the device; feat_bf16 (optional) receives the op16 copy of
 // the normalised features for the loss kernel
 static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, float* out_dev, int normalize,
-                        op16* feat_bf16, cudaStream_t s) {
+                        emb16* feat_bf16, cudaStream_t s) {
   const msclip_config& c = h->cfg;
   const int w = c.width, R = c.image_resolution, g = h->grid, L = h->l_img, c0 = w / 16;
   const int H1 = R / 2;
@@ -809,7 +827,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
 // L = positions per sequence the tower runs over (context_length, or the longest live prefix of the batch: with the
 // causal mask nothing after a sequence's EOT token can reach the row that is pooled, M.py:2965-2971 + 3057-3060);
 // tokens keep their pitch of context_length
-static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float* out_dev, int normalize, op16* feat_bf16,
+static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float* out_dev, int normalize, emb16* feat_bf16,
                       cudaStream_t s) {
   const msclip_config& c = h->cfg;
   const int w = c.width, Lt = c.context_length;
@@ -904,8 +922,37 @@ static const void* take_staged(msclip_ctx* h, const void* image, size_t bytes, c
 // parity of the exchange buffer the *next* loss call will read
 static int next_parity(const msclip_ctx* h) { return static_cast<int>((h->epoch + 1) & 1); }
 
+// Where the 16-bit copy of `batch` normalised embeddings goes: rows [row_offset, row_offset + batch) of the exchange slot
+// the next loss call reads.  row_offset == 0 starts a new shard, row_offset == rows filled so far appends a micro-batch.
+static int shard_rows(msclip_ctx* h, int modality, int batch, int row_offset, emb16** fb) {
+  *fb = nullptr;
+  int& filled = modality == 0 ? h->img_rows : h->txt_rows;
+  MSCLIP_REQUIRE(row_offset == 0 || row_offset == filled,
+                 "micro-batches must be appended in order (row_offset == rows encoded so far)");
+  if (row_offset == 0) {
+    MSCLIP_TRY(ensure_xchg(h, batch));
+  } else {
+    MSCLIP_REQUIRE(h->xchg != nullptr && row_offset + batch <= h->max_b_local,
+                   "micro-batching: call msclip_comm_init(h, rank, world, b_local) with the full local batch first");
+  }
+  filled = 0;
+  if (row_offset + batch <= h->max_b_local) {
+    *fb = xchg_slot(h, h->xchg, next_parity(h), modality) + static_cast<size_t>(row_offset) * h->cfg.embed_dim;
+    filled = row_offset + batch;
+  }
+  return 0;
+}
+
+static int encode_image_at(msclip_ctx* h, const void* image, int dtype, int batch, float* out, int normalize, int row_offset,
+                           cudaStream_t s);
+
 int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, float* out, int normalize,
                         cudaStream_t s) {
+  return encode_image_at(h, image, dtype, batch, out, normalize, 0, s);
+}
+
+static int encode_image_at(msclip_ctx* h, const void* image, int dtype, int batch, float* out, int normalize, int row_offset,
+                           cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));
   if (batch == 0) return 0;
   MSCLIP_REQUIRE(batch > 0 && image != nullptr && out != nullptr, "encode_image: bad arguments");
@@ -934,14 +981,11 @@ int engine_encode_image(msclip_ctx* h, const void* image, int dtype, int batch, 
     WS(o, float, "img_out", static_cast<size_t>(batch) * c.embed_dim);
     out_dev = o;
   }
-  op16* fb = nullptr;
-  if (normalize) {
-    MSCLIP_TRY(ensure_xchg(h, batch));
-    if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 0);
-  }
+  emb16* fb = nullptr;
+  if (normalize) MSCLIP_TRY(shard_rows(h, 0, batch, row_offset, &fb));
+  else h->img_rows = 0;
   MSCLIP_TRY(vision_tower(h, img_dev, dtype, batch, out_dev, normalize, fb, s));
   if (slot) MSCLIP_CHECK_CUDA(cudaEventRecord(slot->consumed, s));
-  h->last_img_batch = fb ? batch : -1;
   if (!out_dev_ptr) {
     MSCLIP_CHECK_CUDA(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(batch) * c.embed_dim * 4, cudaMemcpyDeviceToHost, s));
     MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -956,14 +1000,14 @@ int engine_set_text_trim(msclip_ctx* h, int enable) {
 }
 
 static int encode_text_impl(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, bool allow_trim,
-                            cudaStream_t s);
+                            int row_offset, cudaStream_t s);
 
 int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, cudaStream_t s) {
-  return encode_text_impl(h, tokens, batch, out, normalize, h != nullptr && h->text_trim, s);
+  return encode_text_impl(h, tokens, batch, out, normalize, h != nullptr && h->text_trim, 0, s);
 }
 
 static int encode_text_impl(msclip_ctx* h, const int64_t* tokens, int batch, float* out, int normalize, bool allow_trim,
-                            cudaStream_t s) {
+                            int row_offset, cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));
   if (batch == 0) return 0;
   MSCLIP_REQUIRE(batch > 0 && tokens != nullptr && out != nullptr, "encode_text: bad arguments");
@@ -988,11 +1032,9 @@ static int encode_text_impl(msclip_ctx* h, const int64_t* tokens, int batch, flo
     WS(o, float, "txt_out", static_cast<size_t>(batch) * c.embed_dim);
     out_dev = o;
   }
-  op16* fb = nullptr;
-  if (normalize) {
-    MSCLIP_TRY(ensure_xchg(h, batch));
-    if (batch <= h->max_b_local) fb = xchg_slot(h, h->xchg, next_parity(h), 1);
-  }
+  emb16* fb = nullptr;
+  if (normalize) MSCLIP_TRY(shard_rows(h, 1, batch, row_offset, &fb));
+  else h->txt_rows = 0;
   int live = c.context_length;
   if (allow_trim) {
     // one tiny reduction + a 4-byte read-back: prompts are mostly far shorter than the 77-token context
@@ -1006,7 +1048,6 @@ static int encode_text_impl(msclip_ctx* h, const int64_t* tokens, int batch, flo
     live = std::min(c.context_length, std::max(hmax, 16));
   }
   MSCLIP_TRY(text_tower(h, tok_dev, batch, live, out_dev, normalize, fb, s));
-  h->last_txt_batch = fb ? batch : -1;
   if (!out_dev_ptr) {
     MSCLIP_CHECK_CUDA(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(batch) * c.embed_dim * 4, cudaMemcpyDeviceToHost, s));
     MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -1080,7 +1121,7 @@ int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* t
   const int E = h->cfg.embed_dim;
   WS(fi, float, "fwd_img", static_cast<size_t>(std::max(batch, 1)) * E);
   WS(ft, float, "fwd_txt", static_cast<size_t>(std::max(batch, 1)) * E);
-  MSCLIP_TRY(encode_text_impl(h, tokens, batch, ft, 1, false, s));
+  MSCLIP_TRY(encode_text_impl(h, tokens, batch, ft, 1, false, 0, s));
   MSCLIP_TRY(engine_encode_image(h, image, dtype, batch, fi, 1, s));
   return engine_similarity_logits(h, fi, batch, ft, batch, std::exp(h->logit_scale), logits, s);
 }
@@ -1088,7 +1129,7 @@ int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* t
 __global__ void publish_kernel(uint32_t* const* flag_tables, int world, int rank, uint32_t epoch) {
   // embeddings were written by earlier kernels of this stream; make them visible system-wide, then raise
   // this rank's flag in every peer's (and our own) flag array
-  const int r = threadIdx.x;
+  const int r = threadIdx.x;  // launched with kMaxWorld threads
   if (r < world) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_tables[r] + rank), "r"(epoch) : "memory");
@@ -1101,21 +1142,28 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
                             cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));
   MSCLIP_REQUIRE(b_local >= 1, "contrastive_loss: empty batch");
-  MSCLIP_REQUIRE(h->xchg != nullptr && h->last_img_batch == b_local && h->last_txt_batch == b_local,
-                 "contrastive_loss: encode_image and encode_text (normalize=1) of b_local rows must precede it");
+  MSCLIP_REQUIRE(h->xchg != nullptr && h->img_rows == b_local && h->txt_rows == b_local,
+                 "contrastive_loss: encode_image and encode_text (normalize=1) of b_local rows (in one call or as "
+                 "micro-batches, msclip_encode_pairs) must precede it");
   MSCLIP_REQUIRE(h->world == 1 || h->shard_tables != nullptr, "contrastive_loss: msclip_comm_import has not been called");
   const int W = h->world, E = h->cfg.embed_dim;
   h->epoch += 1;
   const int par = static_cast<int>(h->epoch & 1);
   void** tables = static_cast<void**>(h->shard_tables);
-  const op16* const* img_tab = reinterpret_cast<const op16* const*>(tables + (par * 2 + 0) * W);
-  const op16* const* txt_tab = reinterpret_cast<const op16* const*>(tables + (par * 2 + 1) * W);
+  const emb16* const* img_tab = reinterpret_cast<const emb16* const*>(tables + (par * 2 + 0) * W);
+  const emb16* const* txt_tab = reinterpret_cast<const emb16* const*>(tables + (par * 2 + 1) * W);
   const uint32_t* flags = nullptr;
   if (W > 1) {
-    publish_kernel<<<1, 32, 0, s>>>(h->peer_flag_tables, W, h->rank, h->epoch);
+    publish_kernel<<<1, kMaxWorld, 0, s>>>(h->peer_flag_tables, W, h->rank, h->epoch);
     MSCLIP_CHECK_CUDA(cudaGetLastError());
     count_launch(1);
     flags = xchg_flags(h, h->xchg);
+    // The stream - not a kernel holding every SM - waits for the peers: one stream memory operation per peer flag
+    // (cuStreamWaitValue32, cyclic >=).  Like an NCCL collective this simply waits as long as a peer needs (rank skew
+    // from an eval pass, a checkpoint save or a data stall is not an error); the acquire loads inside the loss
+    // kernel then succeed on their first poll.  Without stream memory operations the in-kernel poll does the waiting.
+    for (int r = 0; r < W; ++r)
+      if (r != h->rank && stream_wait_value_geq(s, flags + r, h->epoch) != 0) break;
   }
   void* wsp = nullptr;
   MSCLIP_TRY(ws_get(h, "loss_ws", contrastive_loss_workspace_bytes(W, b_local), &wsp));
@@ -1140,31 +1188,54 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
     need_sync |= !dev;
   }
   if (need_sync) MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
-  h->last_img_batch = h->last_txt_batch = -1;
+  h->img_rows = h->txt_rows = 0;
   return 0;
 }
 
-int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,
-                        float* partial_out, float* loss_out, cudaStream_t s) {
+// Loss of embeddings computed elsewhere (fp32, already L2-normalised, device or host): they are rounded to the fp16
+// exchange format into this rank's shard, then msclip_contrastive_loss runs as usual (peers included).
+int engine_contrastive_loss_features(msclip_ctx* h, const float* img_feat, const float* txt_feat, int b_local, float scale,
+                                     float* partial_out, float* loss_out, cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));
-  MSCLIP_REQUIRE(b_local >= 1 && image && tokens, "forward_loss: bad arguments");
+  MSCLIP_REQUIRE(b_local >= 1 && img_feat && txt_feat, "contrastive_loss_features: bad arguments");
+  const int E = h->cfg.embed_dim;
+  const float* src[2] = {img_feat, txt_feat};
+  for (int m = 0; m < 2; ++m) {
+    const float* x = src[m];
+    if (!is_device_pointer(x)) {
+      float* stage = nullptr;
+      MSCLIP_TRY(ws_get(h, m == 0 ? "feat_in_img" : "feat_in_txt", static_cast<size_t>(b_local) * E * 4, reinterpret_cast<void**>(&stage)));
+      MSCLIP_CHECK_CUDA(cudaMemcpyAsync(stage, x, static_cast<size_t>(b_local) * E * 4, cudaMemcpyHostToDevice, s));
+      x = stage;
+    }
+    emb16* fb = nullptr;
+    MSCLIP_TRY(shard_rows(h, m, b_local, 0, &fb));
+    MSCLIP_REQUIRE(fb != nullptr, "contrastive_loss_features: batch exceeds the exchange buffer (msclip_comm_init max_b_local)");
+    MSCLIP_TRY(launch_l2norm(x, nullptr, fb, b_local, E, 0, s));
+    count_launch(1);
+  }
+  return engine_contrastive_loss(h, b_local, scale, partial_out, loss_out, s);
+}
+
+// Both towers for b_micro pairs; their embeddings become rows [row_offset, row_offset + b_micro) of this rank's shard
+// of the next contrastive loss (micro-batching: BASELINE.json's global batch of 32 768 on fewer than 8 GPUs).
+int engine_encode_pairs(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_micro, int row_offset,
+                        cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  MSCLIP_REQUIRE(b_micro >= 1 && row_offset >= 0 && image && tokens, "encode_pairs: bad arguments");
   MSCLIP_TRY(ensure_streams(h));
   const msclip_config& c = h->cfg;
   const int E = c.embed_dim;
-  WS(fi, float, "fwd_img", static_cast<size_t>(b_local) * E);
-  WS(ft, float, "fwd_txt", static_cast<size_t>(b_local) * E);
+  WS(fi, float, "fwd_img", static_cast<size_t>(b_micro) * E);
+  WS(ft, float, "fwd_txt", static_cast<size_t>(b_micro) * E);
   // host images: start the (large) transfer first, run the text tower while it is in flight
   const void* img_dev = image;
   bool prestaged = false;
-  {
-    const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
-    const size_t img_bytes = static_cast<size_t>(b_local) * 3 * c.image_resolution * c.image_resolution * esz;
-    for (int i = 0; i < 2; ++i)
-      prestaged |= h->staged[i].pending && h->staged[i].host == image && h->staged[i].bytes == img_bytes;
-  }
+  const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
+  const size_t img_bytes = static_cast<size_t>(b_micro) * 3 * c.image_resolution * c.image_resolution * esz;
+  for (int i = 0; i < 2; ++i)
+    prestaged |= h->staged[i].pending && h->staged[i].host == image && h->staged[i].bytes == img_bytes;
   if (!prestaged && !is_device_pointer(image)) {
-    const size_t esz = dtype == MSCLIP_F32 ? 4 : 2;
-    const size_t img_bytes = static_cast<size_t>(b_local) * 3 * c.image_resolution * c.image_resolution * esz;
     WS(stage, uint8_t, "img_stage", img_bytes);
     MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_main, s));
     MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_main, 0));
@@ -1172,9 +1243,14 @@ int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64
     MSCLIP_CHECK_CUDA(cudaEventRecord(h->ev_copy, h->copy_stream));
     img_dev = stage;
   }
-  MSCLIP_TRY(encode_text_impl(h, tokens, b_local, ft, 1, false, s));
+  MSCLIP_TRY(encode_text_impl(h, tokens, b_micro, ft, 1, false, row_offset, s));
   if (img_dev != image) MSCLIP_CHECK_CUDA(cudaStreamWaitEvent(s, h->ev_copy, 0));
-  MSCLIP_TRY(engine_encode_image(h, img_dev, dtype, b_local, fi, 1, s));
+  return encode_image_at(h, img_dev, dtype, b_micro, fi, 1, row_offset, s);
+}
+
+int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,
+                        float* partial_out, float* loss_out, cudaStream_t s) {
+  MSCLIP_TRY(engine_encode_pairs(h, image, dtype, tokens, b_local, 0, s));
   return engine_contrastive_loss(h, b_local, std::exp(h->logit_scale), partial_out, loss_out, s);
 }
 
@@ -1186,7 +1262,7 @@ msclip_ctx::~msclip_ctx() {
   for (void* p : weight_allocs) cudaFree(p);
   for (auto& kv : ws) cudaFree(kv.second.p);
   for (int r = 0; r < static_cast<int>(peer_base.size()); ++r)
-    if (r != rank && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
+    if (r != rank && peer_base[r] && !peers_borrowed) cudaIpcCloseMemHandle(peer_base[r]);
   for (auto& st : staged) {
     if (st.dev) cudaFree(st.dev);
     if (st.ready) cudaEventDestroy(st.ready);

@@ -94,10 +94,13 @@ struct msclip_ctx {
   void* xchg = nullptr;  // [2 parity][2 modality][max_b_local, E] op16, then uint32 flags[world]
   size_t xchg_bytes = 0;
   std::vector<void*> peer_base;    // imported peer bases (own base at [rank])
+  bool peers_borrowed = false;     // peer bases are same-process device pointers (not IPC mappings to close)
   void* shard_tables = nullptr;    // device: [2 parity][2 modality][world] pointers
   uint32_t** peer_flag_tables = nullptr;  // device: [world] pointers to each rank's flag array
   uint32_t epoch = 0;
-  int last_img_batch = -1, last_txt_batch = -1;
+  // rows of this rank's shard (exchange slot of the NEXT loss) filled so far by encode_image / encode_text: one call
+  // with the whole local batch, or several micro-batches appended back to back (msclip_encode_pairs)
+  int img_rows = 0, txt_rows = 0;
 
   ~msclip_ctx();
 };
@@ -117,12 +120,17 @@ int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* t
                    cudaStream_t stream);
 int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* partial_out, float* loss_out,
                             cudaStream_t stream);
+int engine_contrastive_loss_features(msclip_ctx* h, const float* img_feat, const float* txt_feat, int b_local, float scale,
+                                     float* partial_out, float* loss_out, cudaStream_t stream);
+int engine_encode_pairs(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_micro, int row_offset,
+                        cudaStream_t stream);
 int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,
                         float* partial_out, float* loss_out, cudaStream_t stream);
 int engine_stage_images(msclip_ctx* h, const void* image_host, int dtype, int batch, cudaStream_t stream);
 int comm_init(msclip_ctx* h, int rank, int world, int max_b_local);
 int comm_export(msclip_ctx* h, void* handle_out);
 int comm_import(msclip_ctx* h, const void* handles);
+int comm_import_pointers(msclip_ctx* h, void* const* bases);
 
 int64_t launch_count();
 void count_launch(int n);

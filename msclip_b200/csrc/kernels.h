@@ -29,6 +29,12 @@ typedef __nv_bfloat162 op162;
 constexpr uint32_t kUmmaOperandFormat = 1;
 #endif
 
+// Normalised embeddings handed to the contrastive loss (and exchanged between ranks) are IEEE fp16 in BOTH builds:
+// |x| <= 1, so fp16's 11-bit significand applies (8x less rounding error than bf16 at the same size and tensor-core
+// rate) and its narrow exponent costs nothing (elements below 6e-5 lose < 3e-8 absolute).
+typedef __half emb16;
+constexpr uint32_t kUmmaFormatF16 = 0;
+
 __host__ __device__ inline op16 to_op16(float x) {
 #ifdef MSCLIP_FP16
   return __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
@@ -100,7 +106,7 @@ int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, c
                            const float* b, float* x_out, int batch, int g, op16* xc, float* rec, cudaStream_t stream);
 // out[r] = x[r] / ||x[r]|| (optional) as f32 and op16 copies; width E (<= 1024, multiple of 4)
 int check_token_error(cudaStream_t stream);  // synchronises; non-zero if an out-of-range token id was seen
-int launch_l2norm(const float* x, float* out_f32, op16* out_bf16, int rows, int E, int normalise, cudaStream_t stream);
+int launch_l2norm(const float* x, float* out_f32, emb16* out_f16, int rows, int E, int normalise, cudaStream_t stream);
 
 // ---- conv helpers (conv.cu) -------------------------------------------------------------------
 // NCHW fp32 image -> im2col rows [B*Ho*Wo, 32] op16 for the 3x3 stride-2 pad-1 first convs; k = c*9+ky*3+kx
@@ -144,8 +150,8 @@ int launch_attention(const op16* qkv, op16* out, int batch, int L, int heads, in
 // loss_parts[0] = sum_i (lse_i - s_ii) over local image rows, [1] = same over local text rows;
 // loss = (sum over ranks of parts[0] + parts[1]) / (2 G).  img_shards / txt_shards: device arrays of
 // `world` rank-ordered shard pointers; flags: this rank's device array of `world` publish flags or null.
-int launch_contrastive_loss_ex(const op16* img_local, const op16* txt_local, const op16* const* img_shards,
-                               const op16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
+int launch_contrastive_loss_ex(const emb16* img_local, const emb16* txt_local, const emb16* const* img_shards,
+                               const emb16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
                                int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
                                cudaStream_t stream);
 size_t contrastive_loss_workspace_bytes(int world, int b_local);

@@ -30,7 +30,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 struct LossParams {
-  const op16* const* col_shards[2];  // [dir] -> device table of `world` shard pointers (columns of that direction)
+  const emb16* const* col_shards[2];  // [dir] -> device table of `world` shard pointers (columns of that direction)
   const uint32_t* flags;             // optional: this rank's flag array [world], raised by the owners; null for world == 1
   uint32_t epoch;
   int world, rank, b_local, tiles_per_shard, n_col_tiles, n_row_blocks, b_pad;
@@ -100,7 +100,7 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
     __syncthreads();
   }
   {
-    const op16* src = p.col_shards[dir][owner] + static_cast<long long>(c0) * kLossE;
+    const emb16* src = p.col_shards[dir][owner] + static_cast<long long>(c0) * kLossE;
     // 128 rows x 64 chunks of 16 B; adjacent threads read adjacent chunks of one row (coalesced)
     for (int i = threadIdx.x; i < kLossBN * (kLossE / 8); i += kLossThreads) {
       const int r = i >> 6;
@@ -135,7 +135,7 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f32acc(128, kLossBN);
+      constexpr uint32_t idesc = umma_idesc_f32acc_fmt(128, kLossBN, kUmmaFormatF16);
       const uint32_t b_base = smem_u32(sB);
       int s = 0;
       uint32_t ph = 0;
@@ -265,8 +265,8 @@ size_t contrastive_loss_workspace_bytes(int world, int b_local) {
          2 * static_cast<size_t>(b_local) * sizeof(float);
 }
 
-int launch_contrastive_loss_ex(const op16* img_local, const op16* txt_local, const op16* const* img_shards,
-                               const op16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
+int launch_contrastive_loss_ex(const emb16* img_local, const emb16* txt_local, const emb16* const* img_shards,
+                               const emb16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
                                int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
                                cudaStream_t stream) {
   MSCLIP_REQUIRE(E == kLossE, "contrastive loss: embedding width must be 512");

@@ -52,6 +52,26 @@ int make_tmap_op16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+// cuStreamWaitValue32(stream, addr, value, GEQ): the stream stalls (no SM is occupied) until the 32-bit word at
+// `addr` - device memory that a peer GPU writes over NVLink - satisfies (int32)(*addr - value) >= 0.
+int stream_wait_value_geq(cudaStream_t stream, const uint32_t* addr, uint32_t value) {
+  typedef CUresult (*WaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  static WaitFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WaitFn>(p);
+  });
+  if (fn == nullptr) return 1;
+  return fn(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ) ==
+                 CUDA_SUCCESS
+             ? 0
+             : 1;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -45,17 +45,23 @@ class _PatchingLoader(importlib.abc.Loader):
 
 
 class _Finder(importlib.abc.MetaPathFinder):
+    _busy = False
+
     def find_spec(self, fullname, path, target=None):
-        if fullname != TARGET:
+        if fullname != TARGET or self._busy:
             return None
-        for finder in sys.meta_path:
-            if finder is self or not hasattr(finder, "find_spec"):
-                continue
-            spec = finder.find_spec(fullname, path, target)
-            if spec is not None and spec.loader is not None:
-                spec.loader = _PatchingLoader(spec.loader)
-                return spec
-        return None
+        self._busy = True          # other wrapping finders on sys.meta_path delegate back to us: answer only once
+        try:
+            for finder in sys.meta_path:
+                if finder is self or not hasattr(finder, "find_spec"):
+                    continue
+                spec = finder.find_spec(fullname, path, target)
+                if spec is not None and spec.loader is not None:
+                    spec.loader = _PatchingLoader(spec.loader)
+                    return spec
+            return None
+        finally:
+            self._busy = False
 
 
 def install() -> None:

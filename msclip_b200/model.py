@@ -91,7 +91,10 @@ class CLIP(nn.Module):
                 node.register_parameter(leaf, p)
         self._handle = C.c_void_p()
         self._synced = None         # fingerprint of the tensors last handed to the library
+        self._tensors = None        # cached (key, tensor) list behind that fingerprint
         self._comm = None           # (rank, world, max_b_local) once the peer exchange is set up
+        self._comm_mode = "p2p"     # "p2p": in-kernel NVLink gather; "gather": gather_tensors fallback (multi-node)
+        self._checked_b = set()     # local batch sizes already verified to be equal on every rank
 
     # ---- reference attributes -----------------------------------------------------------------------
     @property
@@ -127,19 +130,40 @@ class CLIP(nn.Module):
             pass
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # the library allocates and launches on the CURRENT device: every call runs under _on_device()
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _on_device(self):
+        """Make the parameters' device current for the duration of a library call (model.to('cuda:1') without
+        torch.cuda.set_device(1) must not put workspace and launches on cuda:0)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise _lib.MsclipError("msclip_b200 needs an sm_100 GPU: there is no CPU fallback (move the model with .cuda())")
+        return torch.cuda.device(dev)
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() replace parameter storage: drop the cached tensor list
+        self._tensors = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._tensors = None
+        return super().load_state_dict(*args, **kwargs)
 
     def _sync_weights(self):
-        """Hand the current state_dict to the library if any tensor changed since the last call."""
-        sd = self.state_dict(keep_vars=True)
-        finger = tuple((t.data_ptr(), t._version) for t in sd.values())
+        """Hand the current state_dict to the library if any tensor changed since the last call.  The (key, tensor)
+        list is cached, so the steady-state cost is one (data_ptr, version) comparison per tensor (zero-shot makes
+        ~1000 small encode_text calls, tools/zero_shot.py:125-131)."""
+        if self._tensors is None:
+            self._tensors = list(self.state_dict(keep_vars=True).items())
+        finger = tuple((t.data_ptr(), t._version) for _, t in self._tensors)
         if finger == self._synced:
             return
         if not torch.cuda.is_available():
             raise _lib.MsclipError("msclip_b200 needs an sm_100 GPU: there is no CPU fallback")
         h = self._ensure_handle()
         L = self._library()
-        for key, t in sd.items():
+        for key, t in self._tensors:
             if t.dtype == torch.long:
                 dt, tt = _lib.I64, t
             else:
@@ -161,11 +185,12 @@ class CLIP(nn.Module):
         if image.dtype not in _IMAGE_DTYPES:
             image = image.float()
         image = image.contiguous()
-        self._sync_weights()
-        out = torch.empty((image.shape[0], c.embed_dim), dtype=torch.float32, device=image.device)
-        self._check(self._library().msclip_encode_image(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
-                                                  image.shape[0], C.c_void_p(out.data_ptr()), int(bool(norm)),
-                                                  self._stream()), "msclip_encode_image")
+        with self._on_device():
+            self._sync_weights()
+            out = torch.empty((image.shape[0], c.embed_dim), dtype=torch.float32, device=self.device)
+            self._check(self._library().msclip_encode_image(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+                                                      image.shape[0], C.c_void_p(out.data_ptr()), int(bool(norm)),
+                                                      self._stream()), "msclip_encode_image")
         return out
 
     def prefetch_images(self, image: torch.Tensor) -> None:
@@ -175,9 +200,10 @@ class CLIP(nn.Module):
             return
         if image.dtype not in _IMAGE_DTYPES or not image.is_contiguous():
             raise ValueError("prefetch_images needs a contiguous float32 / bfloat16 / float16 CPU tensor")
-        self._sync_weights()
-        self._check(self._library().msclip_stage_images(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
-                                                       image.shape[0], self._stream()), "msclip_stage_images")
+        with self._on_device():
+            self._sync_weights()
+            self._check(self._library().msclip_stage_images(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+                                                           image.shape[0], self._stream()), "msclip_stage_images")
 
     @torch.no_grad()
     def encode_text(self, text: torch.Tensor, norm: bool = True, action=None) -> torch.Tensor:
@@ -187,11 +213,17 @@ class CLIP(nn.Module):
         if text.dim() != 2 or text.shape[1] != c.context_length:
             raise ValueError(f"expected [B, {c.context_length}] token ids, got {tuple(text.shape)}")
         text = text.to(torch.long).contiguous()
-        self._sync_weights()
-        out = torch.empty((text.shape[0], c.embed_dim), dtype=torch.float32, device=text.device)
-        self._check(self._library().msclip_encode_text(self._handle, C.c_void_p(text.data_ptr()), text.shape[0],
-                                                 C.c_void_p(out.data_ptr()), int(bool(norm)), self._stream()),
-                   "msclip_encode_text")
+        if text.numel():
+            # nn.Embedding raises on out-of-range ids (M.py:3047); so do we, before anything is launched
+            lo, hi = int(text.min()), int(text.max())
+            if lo < 0 or hi >= c.vocab_size:
+                raise IndexError(f"token id out of range [0, {c.vocab_size}): min {lo}, max {hi}")
+        with self._on_device():
+            self._sync_weights()
+            out = torch.empty((text.shape[0], c.embed_dim), dtype=torch.float32, device=self.device)
+            self._check(self._library().msclip_encode_text(self._handle, C.c_void_p(text.data_ptr()), text.shape[0],
+                                                     C.c_void_p(out.data_ptr()), int(bool(norm)), self._stream()),
+                       "msclip_encode_text")
         return out
 
     def set_text_trim(self, enable: bool) -> None:
@@ -205,12 +237,13 @@ class CLIP(nn.Module):
         """scale * I @ T^T (M.py:3141/3146; tools/zero_shot.py:266 with scale = 100)."""
         fi = image_features.float().contiguous()
         ft = text_features.float().contiguous()
-        self._ensure_handle()
-        out = torch.empty((fi.shape[0], ft.shape[0]), dtype=torch.float32, device=fi.device)
-        self._check(self._library().msclip_similarity_logits(self._handle, C.c_void_p(fi.data_ptr()), fi.shape[0],
-                                                       C.c_void_p(ft.data_ptr()), ft.shape[0], float(scale),
-                                                       C.c_void_p(out.data_ptr()), self._stream()),
-                   "msclip_similarity_logits")
+        with self._on_device():
+            self._ensure_handle()
+            out = torch.empty((fi.shape[0], ft.shape[0]), dtype=torch.float32, device=fi.device)
+            self._check(self._library().msclip_similarity_logits(self._handle, C.c_void_p(fi.data_ptr()), fi.shape[0],
+                                                           C.c_void_p(ft.data_ptr()), ft.shape[0], float(scale),
+                                                           C.c_void_p(out.data_ptr()), self._stream()),
+                       "msclip_similarity_logits")
         return out
 
     @torch.no_grad()
@@ -230,36 +263,103 @@ class CLIP(nn.Module):
 
     # ---- the fused training-step path ------------------------------------------------------------------
     def setup_data_parallel(self, max_b_local: int, group=None):
-        """Register the peer-visible embedding buffers of all ranks (one process per GPU)."""
+        """Register the peer-visible embedding buffers of all ranks (one process per GPU).  ``max_b_local`` is the
+        largest local batch the loss will see (with micro-batching: the whole local shard).  Ranks that cannot reach
+        each other through CUDA IPC (more than one node) fall back to ``gather_tensors`` + logits + cross-entropy,
+        the reference-shaped path (lib/utils/comm.py:140-154)."""
         from .comm import setup_peer_exchange
-        self._sync_weights()
-        self._comm = setup_peer_exchange(self._handle, max_b_local, group, self.precision)
+        with self._on_device():
+            self._sync_weights()
+            self._comm, self._comm_mode = setup_peer_exchange(self._handle, max_b_local, group, self.precision)
+        self._group = group
+        self._checked_b = set()
         return self._comm
 
+    def _require_equal_shards(self, b: int):
+        """gather_tensors / the P2P exchange both assume equal shards on every rank; verify once per batch size."""
+        world = self._comm[1] if self._comm else 1
+        if world == 1 or b in self._checked_b:
+            return
+        t = torch.tensor([b], dtype=torch.int64, device=self.device)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        torch.distributed.all_gather(parts, t, group=getattr(self, "_group", None))
+        sizes = [int(p) for p in parts]
+        if any(x != b for x in sizes):
+            raise ValueError(f"contrastive_loss needs the same local batch on every rank, got {sizes}")
+        self._checked_b.add(b)
+
     @torch.no_grad()
-    def contrastive_loss(self, image: torch.Tensor, text: torch.Tensor, reduce: bool = True):
-        """Symmetric cross-entropy of exp(logit_scale) * I_all @ T_all^T over the global batch
-        (SURVEY.md section 8a rows G, C, L).  Returns a 0-dim tensor; with world > 1 and ``reduce`` the
-        per-rank partial sums are summed with one 2-float all-reduce."""
+    def encode_pairs(self, image: torch.Tensor, text: torch.Tensor, row_offset: int = 0) -> None:
+        """Micro-batching: run both towers on ``image`` / ``text`` and keep the normalised embeddings as rows
+        [row_offset, row_offset + B) of this rank's shard of the next ``loss_of_encoded`` (msclip_encode_pairs)."""
         if image.shape[0] != text.shape[0]:
             raise ValueError("image and text batch sizes differ")
         if image.dtype not in _IMAGE_DTYPES:
             image = image.float()
         image, text = image.contiguous(), text.to(torch.long).contiguous()
-        self._sync_weights()
-        b = image.shape[0]
+        with self._on_device():
+            self._sync_weights()
+            self._check(self._library().msclip_encode_pairs(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+                                                           C.c_void_p(text.data_ptr()), image.shape[0], int(row_offset),
+                                                           self._stream()), "msclip_encode_pairs")
+
+    @torch.no_grad()
+    def loss_of_encoded(self, b_local: int, reduce: bool = True):
+        """Symmetric cross-entropy over the rows retained by ``encode_pairs`` (b_local per rank)."""
         world = self._comm[1] if self._comm else 1
-        dev = self.device
-        parts = torch.empty(2, dtype=torch.float32, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        self._check(self._library().msclip_forward_loss(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
-                                                  C.c_void_p(text.data_ptr()), b, C.c_void_p(parts.data_ptr()),
-                                                  C.c_void_p(loss.data_ptr()) if world == 1 else None, self._stream()),
-                   "msclip_forward_loss")
+        self._require_equal_shards(b_local)
+        with self._on_device():
+            parts = torch.empty(2, dtype=torch.float32, device=self.device)
+            loss = torch.empty((), dtype=torch.float32, device=self.device)
+            scale = C.c_float()
+            self._check(self._library().msclip_logit_scale_exp(self._handle, C.byref(scale)), "msclip_logit_scale_exp")
+            self._check(self._library().msclip_contrastive_loss(self._handle, int(b_local), scale.value, C.c_void_p(parts.data_ptr()),
+                                                               C.c_void_p(loss.data_ptr()) if world == 1 else None, self._stream()),
+                       "msclip_contrastive_loss")
         if world == 1:
             return loss
         if reduce:
-            torch.distributed.all_reduce(parts)
+            torch.distributed.all_reduce(parts, group=getattr(self, "_group", None))
+        return parts.sum() / (2.0 * world * b_local)
+
+    @torch.no_grad()
+    def contrastive_loss(self, image: torch.Tensor, text: torch.Tensor, reduce: bool = True, micro_batch: Optional[int] = None):
+        """Symmetric cross-entropy of exp(logit_scale) * I_all @ T_all^T over the global batch
+        (SURVEY.md section 8a rows G, C, L).  Returns a 0-dim tensor; with world > 1 and ``reduce`` the
+        per-rank partial sums are summed with one 2-float all-reduce.  ``micro_batch``: encode the local batch in
+        pieces of that many pairs (their embeddings are retained on the device) and take ONE loss over all of them -
+        how a global batch of 32 768 runs on fewer than 8 GPUs (needs ``setup_data_parallel(len(image))`` first)."""
+        if image.shape[0] != text.shape[0]:
+            raise ValueError("image and text batch sizes differ")
+        b = image.shape[0]
+        world = self._comm[1] if self._comm else 1
+        if self._comm_mode == "gather" and world > 1:
+            # ranks on different nodes: reference-shaped path (all-gather, logits, CE) - correct everywhere, not fused
+            logits = self.forward(image, text)
+            target = torch.arange(logits.shape[0], device=logits.device)
+            ce = torch.nn.functional.cross_entropy
+            return 0.5 * (ce(logits, target) + ce(logits.t(), target))
+        if micro_batch is not None and micro_batch < b:
+            for lo in range(0, b, micro_batch):
+                self.encode_pairs(image[lo:lo + micro_batch], text[lo:lo + micro_batch], lo)
+            return self.loss_of_encoded(b, reduce)
+        if image.dtype not in _IMAGE_DTYPES:
+            image = image.float()
+        image, text = image.contiguous(), text.to(torch.long).contiguous()
+        self._require_equal_shards(b)
+        with self._on_device():
+            self._sync_weights()
+            dev = self.device
+            parts = torch.empty(2, dtype=torch.float32, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            self._check(self._library().msclip_forward_loss(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
+                                                      C.c_void_p(text.data_ptr()), b, C.c_void_p(parts.data_ptr()),
+                                                      C.c_void_p(loss.data_ptr()) if world == 1 else None, self._stream()),
+                       "msclip_forward_loss")
+        if world == 1:
+            return loss
+        if reduce:
+            torch.distributed.all_reduce(parts, group=getattr(self, "_group", None))
         return parts.sum() / (2.0 * world * b)
 
     def launch_count(self) -> int:

@@ -16,7 +16,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MSCLIP_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """/root/reference in the authoring container; on the GPU box the byte-identical copy that
+    tools/stage_reference.py placed in the git-ignored baseline/_ref/ (it travels with the working tree)."""
+    cands = [os.environ.get("MSCLIP_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "lib", "models", "clip_openai_pe_res_v1.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

@@ -45,6 +45,8 @@ def main():
     for it in range(3):                               # several epochs: exercises the double-buffered exchange
         loss = float(model.contrastive_loss(img, tok))
         out[f"fused_p2p_{it}"] = loss
+    # micro-batched shard (msclip_encode_pairs x n + one loss): bit-identical to the one-shot call
+    out["fused_p2p_micro"] = float(model.contrastive_loss(img, tok, micro_batch=max(8, b_local // 3)))
     # (b) NCCL comparator with the same per-rank features
     fi, ft = model.encode_image(img), model.encode_text(tok)
     fi_all, ft_all = gather_tensors(fi), gather_tensors(ft)

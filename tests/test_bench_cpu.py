@@ -1,4 +1,4 @@
-"""bench.py contract checks that need no GPU: the reference arm (CPU oracle) prints exactly one JSON line with the
+"""bench.py contract checks that need no GPU: the reference arm (the real reference module on CPU) prints exactly one JSON line with the
 keys the driver reads, and the product arm refuses to run without a CUDA device (no CPU fallback)."""
 import json
 import os
@@ -25,7 +25,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
                 "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the real reference module when it is on the box (baseline/_ref or /root/reference), else the oracle port
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    assert (d["cpu_baseline"]["kind"] == "reference") == ref_shim.reference_available()
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 

@@ -6,12 +6,10 @@
 Three-way protocol of SURVEY.md 7.2(1): ours-vs-fp32 reference, the reference's own autocast(bf16)
 forward-vs-fp32 reference (stored in the golden files), and the bound we hold ourselves to:
   * features, Frobenius-relative:  <= 6e-3 and strictly better than the reference's own bf16 mode
-  * logits, Frobenius-relative:    <= 1.35 x the reference's own bf16 mode (same bf16-operand arithmetic: the
+  * logits, Frobenius-relative:    <= 1.0 x the reference's own bf16 mode (same bf16-operand arithmetic: the
                                    error of near-orthogonal dot products is dominated by operand rounding)
                                    and max |error| <= 1.5e-3 x logit scale (i.e. 1.5e-3 in cosine units)
-  * loss, relative:                <= 1e-3   (north star); the T = 100 correlated case sits at the bf16 floor
-                                   (1.06e-3, the reference's own bf16 mode: 2.4e-3) and is held to half of the
-                                   reference's bf16 error instead
+  * loss, relative:                <= 1e-3   (north star), every case, fused kernel and logits path alike
 The same model built on the fp16-operand library (same kernels, -DMSCLIP_FP16) is held to the north star's
 literal bar: features <= 1e-3, loss <= 1e-3 (<= 2e-4 observed), max |logit error| <= 3e-4 x scale.
 The residual stream, LayerNorm, softmax and every accumulator are fp32 in both builds.
@@ -102,10 +100,9 @@ def test_matches_reference_golden(name, precision):
         return
     assert o["image_features"] < FEAT_TOL and o["text_features"] < FEAT_TOL and o["image_features_unnormalised"] < FEAT_TOL, o
     assert o["logits_max_abs"] <= COS_TOL * scale, o
-    loss_tol = max(LOSS_TOL, 0.5 * a["loss"])
-    assert o["loss_from_logits"] < loss_tol and o["loss_fused_kernel"] < loss_tol, o
+    assert o["loss_from_logits"] < LOSS_TOL and o["loss_fused_kernel"] < LOSS_TOL, o      # north star: <= 1e-3 relative
     assert o["image_features"] < a["image_features"] and o["text_features"] < a["text_features"], (o, a)
-    assert o["logits"] <= 1.35 * a["logits"], (o, a)
+    assert o["logits"] <= 1.0 * a["logits"], (o, a)           # no worse than the reference's own bf16
 
 
 def test_fresh_seed_against_cpu_oracle():
@@ -124,6 +121,11 @@ def test_fresh_seed_against_cpu_oracle():
     mx = float((got - ref_logits).abs().max())
     _record("fresh_seed_l4", {"logits": r, "logits_max_abs": mx})
     assert mx <= COS_TOL * 100.0
+    # Frobenius-relative as well: 5 x 5 near-orthogonal pairs at T = 100 (|logit| ~ 2), bf16 operand rounding only
+    assert r <= 3e-2, r
+    ref_loss, got_loss = float(O.contrastive_loss(ref_logits)), float(O.contrastive_loss(got.double()))
+    fused = float(model.contrastive_loss(torch.from_numpy(img).cuda(), torch.from_numpy(tok).cuda()))
+    assert abs(got_loss - ref_loss) <= LOSS_TOL * abs(ref_loss) and abs(fused - ref_loss) <= LOSS_TOL * abs(ref_loss)
 
 
 def test_host_buffers_equal_device_buffers():
@@ -310,3 +312,68 @@ def test_loss_matches_logits_path_at_odd_batch_sizes():
         fused = float(model.contrastive_loss(img, tok))
         ref = loss_of(model(img, tok).cpu())
         assert abs(fused - ref) <= 1e-3 * abs(ref) + 2e-4, (b, fused, ref)
+
+
+def test_micro_batched_loss_equals_one_shot():
+    """SURVEY.md 8(d) config 4 on fewer GPUs than shards: the local batch goes through the towers in micro-batches whose
+    embeddings are retained (msclip_encode_pairs), then ONE loss over all rows.  Every kernel is row-independent, so
+    the result is bit-identical to the one-shot msclip_forward_loss."""
+    cfg = MSCLIPConfig(layers=3)
+    sd_np = synth.synth_state_dict(cfg, seed=9, logit_scale=math.log(1 / 0.07))
+    b = 40
+    img = torch.from_numpy(synth.synth_images(b, 5)).cuda()
+    tok = torch.from_numpy(synth.synth_tokens(b, 5, ragged=True)).cuda()
+    model = build_model(cfg, sd_np)
+    one = float(model.contrastive_loss(img, tok))
+    model.setup_data_parallel(b)                       # world 1: sizes the exchange buffer for the whole shard
+    for micro in (8, 16, 40):                          # 40: degenerate (one micro-batch); 16: ragged last piece
+        got = float(model.contrastive_loss(img, tok, micro_batch=micro))
+        assert got == one, (micro, got, one)
+    # out-of-order / overflowing micro-batches are refused, not mis-computed
+    model.encode_pairs(img[:8], tok[:8], 0)
+    with pytest.raises(Exception):
+        model.encode_pairs(img[:8], tok[:8], 16)
+    with pytest.raises(Exception):
+        model.loss_of_encoded(b)
+    ref = float(O.contrastive_loss(O.forward(img.cpu(), tok.cpu(), O.to_torch(sd_np), cfg)))
+    assert abs(one - ref) <= LOSS_TOL * abs(ref)
+
+
+def test_two_ranks_on_one_gpu_run_the_p2p_protocol():
+    """The sharded loss (publish flags, stream waits, rank-ordered shard tables, double-buffered epochs) with world = 2
+    on ONE GPU: two handles, each on its own stream, exchange buffers handed over as same-process pointers
+    (msclip_comm_import_pointers).  Must equal the single-handle loss over the concatenated batch - the same check
+    tests/test_multigpu.py makes across real GPUs, runnable on the single-GPU box."""
+    import ctypes as C
+    from msclip_b200 import _lib
+    cfg = MSCLIPConfig(layers=2)
+    sd_np = synth.synth_state_dict(cfg, seed=13, logit_scale=math.log(1 / 0.07))
+    b = 24
+    img = torch.from_numpy(synth.synth_images(2 * b, 31)).cuda()
+    tok = torch.from_numpy(synth.synth_tokens(2 * b, 31, ragged=True)).cuda()
+    solo = build_model(cfg, sd_np)
+    truth = float(solo.contrastive_loss(img, tok))
+    L = _lib.lib("bf16")
+    ranks = [build_model(cfg, sd_np) for _ in range(2)]
+    bases = (C.c_void_p * 2)()
+    for r, m in enumerate(ranks):
+        m._sync_weights()
+        _lib.check(L.msclip_comm_init(m._handle, r, 2, b), "comm_init")
+        base = C.c_void_p()
+        _lib.check(L.msclip_comm_buffer(m._handle, C.byref(base)), "comm_buffer")
+        bases[r] = base.value
+    for m in ranks:
+        _lib.check(L.msclip_comm_import_pointers(m._handle, bases), "comm_import_pointers")
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    parts = torch.zeros(2, 2, device="cuda")
+    torch.cuda.synchronize()
+    for epoch in range(3):                             # both parities of the exchange buffer, then reuse
+        for r, m in enumerate(ranks):                  # nothing blocks the host: rank 0's loss is queued behind a
+            sp = C.c_void_p(streams[r].cuda_stream)    # stream wait on rank 1's flag, which rank 1's stream raises
+            lo = r * b
+            _lib.check(L.msclip_forward_loss(m._handle, C.c_void_p(img[lo:lo + b].data_ptr()), _lib.F32,
+                                             C.c_void_p(tok[lo:lo + b].data_ptr()), b, C.c_void_p(parts[r].data_ptr()),
+                                             None, sp), "forward_loss")
+        torch.cuda.synchronize()
+        got = float(parts.sum()) / (2.0 * 2 * b)
+        assert abs(got - truth) <= 2e-6 * abs(truth), (epoch, got, truth)
