@@ -66,6 +66,15 @@ int msclip_op_attention(const void* qkv_bf16, void* out_bf16, int batch, int seq
 int msclip_op_im2col_first(const void* img, int dtype, void* out_bf16, int batch, int height, int width, void* stream);
 int msclip_op_im2col_nhwc(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                           int ksize, int stride, int pad, void* out_bf16, int64_t out_ld, int out_off, void* stream);
+/* msclip_op_conv_gemm with the A operand fetched by im2col-mode TMA (no gather warps): same arguments and the same
+ * dense (ky, kx, c) weight; `w_padded_scratch` (n * msclip_op_conv_tma_kpad(c0, k0, c1, k1) 16-bit elements) receives the
+ * padded-K weight copy the kernel consumes.  n a multiple of 48; epilogue EPI_RELU_BF16 or EPI_F32. */
+int msclip_op_conv_tma(const void* in0, int h0, int w0, int cpix0, int coff0, int c0, int k0, int s0, int p0, const void* in1,
+                       int h1, int w1, int cpix1, int coff1, int c1, int k1, int s1, int p1, int batch, int ho, int wo,
+                       const void* w_dense, int64_t ldw, int n, const float* bias, void* out, int64_t ldo, int epilogue,
+                       void* w_padded_scratch, void* stream);
+int msclip_op_conv_tma_kpad(int c0, int k0, int c1, int k1);
+
 /* Implicit-GEMM convolution: out[batch*ho*wo, n] = epi(patches . w^T + bias); K = (ky,kx,c) patch of source 0
  * followed by that of the optional source 1 (in1 = NULL: single source).  NHWC bf16 inputs. */
 int msclip_op_conv_gemm(const void* in0, int h0, int w0, int cpix0, int coff0, int c0, int k0, int s0, int p0, const void* in1,

@@ -81,6 +81,9 @@ _SIGNATURES = {
     "msclip_op_im2col_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P]),
     "msclip_op_conv_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P,
                                 _P, _L, _I, _P]),
+    "msclip_op_conv_tma": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _I, _P,
+                               _P, _L, _I, _P, _P]),
+    "msclip_op_conv_tma_kpad": (_I, [_I, _I, _I, _I]),
     "msclip_op_patch_pool": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "msclip_op_front_conv": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P]),
     "msclip_op_adapter_fuse_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),

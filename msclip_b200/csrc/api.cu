@@ -244,6 +244,24 @@ int msclip_op_conv_gemm(const void* in0, int h0, int w0, int cpix0, int coff0, i
   return launch_conv_gemm(src, in1 ? 2 : 1, batch, ho, wo, static_cast<const op16*>(w_bf16), ldw, n, bias, out, ldo, epilogue,
                           as_stream(stream));
 }
+int msclip_op_conv_tma(const void* in0, int h0, int w0, int cpix0, int coff0, int c0, int k0, int s0, int p0, const void* in1,
+                       int h1, int w1, int cpix1, int coff1, int c1, int k1, int s1, int p1, int batch, int ho, int wo,
+                       const void* w_dense, int64_t ldw, int n, const float* bias, void* out, int64_t ldo, int epilogue,
+                       void* w_padded_scratch, void* stream) {
+  // same arguments as msclip_op_conv_gemm (dense (ky, kx, c) weight); the padded-K copy the TMA kernel consumes is
+  // built in the caller's scratch buffer of n * msclip_op_conv_tma_kpad(...) elements
+  ConvSource src[2] = {{in0, h0, w0, cpix0, coff0, c0, k0, s0, p0}, {in1, h1, w1, cpix1, coff1, c1, k1, s1, p1}};
+  const int nsrc = in1 ? 2 : 1;
+  const int kp = conv_tma_kpad(src, nsrc);
+  MSCLIP_TRY(launch_pack_conv_kpad(static_cast<const op16*>(w_dense), ldw, src, nsrc, n, static_cast<op16*>(w_padded_scratch),
+                                   as_stream(stream)));
+  return launch_conv_tma(src, nsrc, batch, ho, wo, static_cast<const op16*>(w_padded_scratch), kp, n, bias, out, ldo, epilogue,
+                         as_stream(stream));
+}
+int msclip_op_conv_tma_kpad(int c0, int k0, int c1, int k1) {
+  ConvSource src[2] = {{nullptr, 0, 0, 0, 0, c0, k0, 1, 0}, {nullptr, 0, 0, 0, 0, c1, k1, 1, 0}};
+  return conv_tma_kpad(src, c1 > 0 ? 2 : 1);
+}
 int msclip_op_patch_pool(const void* in_bf16, int batch, int height, int width, int cpix, int c_off, int channels,
                          int k, const float* w, const float* bias, void* out_bf16, void* stream) {
   return launch_patch_pool(static_cast<const op16*>(in_bf16), batch, height, width, cpix, c_off, channels, k, w, bias,

@@ -159,6 +159,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// im2col-mode load (NHWC activation as a rank-4 tensor {C, W, H, N}): `pixelsPerColumn` output pixels starting at the
+// base pixel (w, h, n) - input coordinates of the window origin, i.e. out * stride - pad - are traversed with the
+// convolution stride along W, then H, then N inside the descriptor's bounding box; every pixel is displaced by the
+// filter tap (off_w, off_h) and contributes `channelsPerPixel` channels from c.  Out-of-image elements read as zero.
+// The box lands exactly like a 2D tile of [pixels][64 channels]: 128-byte rows, SWIZZLE_128B.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------ clusters / CTA pairs
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -210,6 +225,15 @@ __device__ __forceinline__ void tma_load_2d_pair_mcast(void* smem_dst, const CUt
       " [%0], [%1, {%4, %5}], [%2], %3;"
       ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c,
+                                                        int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
@@ -336,6 +360,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f32acc(int m, int n) { return 
 // ------------------------------------------------------------------------------------ host: TMA maps
 // rows x cols op16 row-major (pitch ld elements), box = box_rows x 64 columns, 128-B swizzle,
 // out-of-bounds elements read as zero.
+// NHWC op16 activation [N, H, W, cpix] (channel window [c_off, c_off + C)) as an im2col-mode map for a ksize x ksize /
+// stride / pad convolution: boxes of 128 output pixels x 64 channels, 128-B swizzle, zero fill outside the image and
+// beyond channel C.
+int make_tmap_im2col_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int cpix, int c_off, int C, int ksize,
+                          int stride, int pad);
 int stream_wait_value_geq(cudaStream_t stream, const uint32_t* addr, uint32_t value);  // 0 = queued
 int make_tmap_op16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);

@@ -203,6 +203,49 @@ int launch_pack_ln_fold(const float* src, const float* row_scale, const float* g
   return 0;
 }
 
+// dense K = (source, tap, c) -> padded K = (source, tap, 64-channel block, 64): one thread per padded element
+struct KpadDesc {
+  int nsrc, N;
+  int C[2], taps[2], cblk[2], dense_begin[2], pad_begin[2];
+  int kpad;
+};
+__global__ void __launch_bounds__(256)
+pack_conv_kpad_kernel(const op16* __restrict__ dense, long long ldd, op16* __restrict__ padded, KpadDesc d) {
+  const long long total = static_cast<long long>(d.N) * d.kpad;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const int n = static_cast<int>(i / d.kpad), kp = static_cast<int>(i % d.kpad);
+    const int s = (d.nsrc > 1 && kp >= d.pad_begin[1]) ? 1 : 0;
+    const int r = kp - d.pad_begin[s];
+    const int per_tap = d.cblk[s] * 64;
+    const int tap = r / per_tap, c = r - tap * per_tap;
+    op16 v = to_op16(0.f);
+    if (c < d.C[s]) v = dense[n * ldd + d.dense_begin[s] + tap * d.C[s] + c];
+    padded[i] = v;
+  }
+}
+
+int launch_pack_conv_kpad(const op16* dense, int64_t ldd, const ConvSource* src, int nsrc, int N, op16* padded,
+                          cudaStream_t stream) {
+  KpadDesc d = {};
+  d.nsrc = nsrc;
+  d.N = N;
+  int kd = 0, kp = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    d.C[i] = src[i].C;
+    d.taps[i] = src[i].ksize * src[i].ksize;
+    d.cblk[i] = (src[i].C + 63) / 64;
+    d.dense_begin[i] = kd;
+    d.pad_begin[i] = kp;
+    kd += d.taps[i] * d.C[i];
+    kp += d.taps[i] * d.cblk[i] * 64;
+  }
+  d.kpad = kp;
+  MSCLIP_REQUIRE(kp == conv_tma_kpad(src, nsrc) && ldd >= kd, "pack_conv_kpad: layout mismatch");
+  pack_conv_kpad_kernel<<<flat_grid(static_cast<long long>(N) * kp), 256, 0, stream>>>(dense, ldd, padded, d);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_pack_op16(const float* src, int64_t sn, int64_t sk, const float* row_scale, op16* dst, int64_t ldd, int N,
                      int K, cudaStream_t stream) {
   if (N <= 0 || K <= 0) return 0;

@@ -48,22 +48,6 @@ struct ConvParams {
   GemmParams g;
 };
 
-// q = n / d for 0 <= n < 2^31 as umulhi(n, mul) >> shr (d == 1: mul = 0 selects the identity)
-inline void find_divisor(uint32_t d, uint32_t* mul, uint32_t* shr) {
-  if (d == 1) {
-    *mul = 0;
-    *shr = 0;
-    return;
-  }
-  uint32_t lg = 0;
-  while ((1ull << lg) < d) ++lg;
-  const uint32_t p = 31 + lg;
-  *mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
-  *shr = p - 32;
-}
-__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr) {
-  return mul != 0 ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr) : n;
-}
 
 template <int BN>
 struct ConvCfg {

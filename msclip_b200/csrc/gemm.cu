@@ -35,7 +35,7 @@ struct GemmCfg {
   static constexpr int kChunk = (BN % 32 == 0) ? 32 : 16;                     // columns per tcgen05.ld
   static_assert(kStageB % 1024 == 0, "B stage must keep 1024-byte alignment");
   static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint");
-  static_assert(CG == 1 || BN % 32 == 0, "pair tiles split N in two halves");
+  static_assert(CG == 1 || BN % 16 == 0, "pair tiles: each CTA stages BN / 2 rows of W (whole 8-row swizzle groups)");
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) per 256 x BN tile -
@@ -47,10 +47,14 @@ struct GemmCfg {
 // LN = 1 / 2: LayerNorm folding, see gemm_common.cuh (consume in the epilogue of QKV / fc1, emit from out-proj / fc2)
 // NE = number of epilogue warps (a multiple of 4: NE / 4 warps share each TMEM lane quarter and split the tile's column
 // chunks between them); 8 by default, 12 / 16 selectable for the CTA-pair tiles (see g_epi_warps below).
-template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8>
+// CONV = 1: implicit-GEMM convolution - the A operand is the im2col view of one or two NHWC activations, fetched by
+// im2col-mode TMA (one instruction per k-block = filter tap x 64 channels: the hardware walks the 128 output pixels of
+// the tile with the convolution stride, applies the tap offset and zero-fills the padding), tmap_a / tmap_a2 = the
+// sources' im2col maps.  Everything downstream of the smem ring is the plain GEMM.
+template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8, int CONV = 0>
 __global__ void __launch_bounds__(128 + 32 * NE, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,6 +77,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
+    if (CONV) tma_prefetch_desc(&tmap_a2);
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
@@ -109,14 +114,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m0 = (tile / p.tiles_n) * (kBM * CG * NP) + static_cast<int>(pair_idx) * (kBM * CG) +
                        static_cast<int>(cta_rank) * kBM;
         const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        // CONV: first output pixel of this CTA's 128 rows -> (image, oy, ox); filter position of the k-block
+        int img = 0, oy = 0, ox = 0, src = 0, ky = 0, kx = 0, cb = 0;
+        if (CONV) {
+          const ConvGeom& g = p.conv;
+          img = fast_div(m0, g.hw_mul, g.hw_shr);
+          const int rem = m0 - img * (g.Ho * g.Wo);
+          oy = fast_div(rem, g.wo_mul, g.wo_shr);
+          ox = rem - oy * g.Wo;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1, 1);
           uint8_t* sa = smem + s * Cfg::kStage;
+          int cw = 0, chh = 0, cc = 0;
+          uint16_t offw = 0, offh = 0;
+          const CUtensorMap* ta = &tmap_a;
+          if (CONV) {
+            const ConvGeom& g = p.conv;
+            if (kb == g.kb_begin1) {
+              src = 1;
+              ky = kx = cb = 0;
+            }
+            ta = src ? &tmap_a2 : &tmap_a;
+            cw = ox * g.stride[src] - g.pad[src];
+            chh = oy * g.stride[src] - g.pad[src];
+            cc = cb * kBK;
+            offw = static_cast<uint16_t>(kx);
+            offh = static_cast<uint16_t>(ky);
+            if (++cb == g.cblk[src]) {
+              cb = 0;
+              if (++kx == g.ksize[src]) {
+                kx = 0;
+                ++ky;
+              }
+            }
+          }
           if (CG == 2) {
             // both CTAs' bytes are counted on the leader's barrier, which the leader arms for the pair
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), leader_rank);
             if (leader) mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage * 2);
-            tma_load_2d_pair(sa, &tmap_a, bar, kb * kBK, m0);
+            if (CONV) tma_load_im2col_4d_pair(sa, ta, bar, cc, cw, chh, img, offw, offh);
+            else tma_load_2d_pair(sa, &tmap_a, bar, kb * kBK, m0);
             if (NP == 1) {
               tma_load_2d_pair(sa + Cfg::kStageA, &tmap_b, bar, kb * kBK, n0);
             } else {
@@ -130,7 +168,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::kStage);
-            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
+            if (CONV) tma_load_im2col_4d(sa, ta, &full_bar[s], cc, cw, chh, img, offw, offh);
+            else tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBK, m0);
             tma_load_2d(sa + Cfg::kStageA, &tmap_b, &full_bar[s], kb * kBK, n0);
           }
           if (++s == Cfg::kStages) {
@@ -287,12 +326,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
-template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8>
-int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8, int CONV = 0>
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream,
+                   const CUtensorMap* ta2 = nullptr) {
   using Cfg = GemmCfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG, NP, LN, NE>,
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG, NP, LN, NE, CONV>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
@@ -310,7 +350,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MSCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG, NP, LN, NE>, ta, tb, p));
+  MSCLIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG, NP, LN, NE, CONV>, ta, ta2 ? *ta2 : ta, tb, p));
   return 0;
 }
 
@@ -493,6 +533,106 @@ static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t l
     case 96: return launch_bn<96, 1, 1>(ta, tb, p, epi, stream);
     case 64: return launch_bn<64, 1, 1>(ta, tb, p, epi, stream);
     case 48: return launch_bn<48, 1, 1>(ta, tb, p, epi, stream);
+  }
+  return 2;
+}
+
+// ---- implicit-GEMM convolution fed by im2col-mode TMA ---------------------------------------------------------
+// K layout of the packed weight: for every source, every filter tap (ky, kx) and every 64-channel block: 64 columns
+// (channels beyond C are zero) - conv_tma_kpad() columns in total.
+int conv_tma_kpad(const ConvSource* src, int nsrc) {
+  int k = 0;
+  for (int i = 0; i < nsrc; ++i) k += src[i].ksize * src[i].ksize * ((src[i].C + kBK - 1) / kBK) * kBK;
+  return k;
+}
+
+namespace {
+template <int BN, int CG>
+int launch_conv_tma_bn(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmParams& p, int epi,
+                       cudaStream_t stream) {
+  switch (epi) {
+    case EPI_RELU_BF16: return launch_variant<BN, EPI_RELU_BF16, CG, 1, 0, 8, 1>(ta, tb, p, stream, &ta2);
+    case EPI_F32: return launch_variant<BN, EPI_F32, CG, 1, 0, 8, 1>(ta, tb, p, stream, &ta2);
+  }
+  set_last_error("launch_conv_tma: unsupported epilogue " + std::to_string(epi));
+  return 2;
+}
+}  // namespace
+
+// MSCLIP_CONV_PAIR=0: one CTA per 128-pixel tile instead of CTA pairs (A/B timing)
+static const bool g_conv_pair = [] {
+  const char* e = getenv("MSCLIP_CONV_PAIR");
+  return e == nullptr || e[0] != '0';
+}();
+
+int launch_conv_tma(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const op16* Wp, int64_t ldw, int N,
+                    const float* bias, void* out, int64_t ldo, int epi, cudaStream_t stream) {
+  MSCLIP_REQUIRE(nsrc == 1 || nsrc == 2, "conv_tma: one or two sources");
+  MSCLIP_REQUIRE(batch > 0 && Ho > 0 && Wo > 0 && N > 0, "conv_tma: empty problem");
+  const int K = conv_tma_kpad(src, nsrc);
+  MSCLIP_REQUIRE(ldw % 8 == 0 && ldw >= K, "conv_tma: weight pitch (padded K layout, see conv_tma_kpad)");
+  int bn = 0;
+  const int cands[4] = {256, 192, 96, 48};
+  for (int i = 0; i < 4 && bn == 0; ++i)
+    if (N % cands[i] == 0) bn = cands[i];
+  MSCLIP_REQUIRE(bn != 0, "conv_tma: N must be a multiple of 48");
+  const long long M = static_cast<long long>(batch) * Ho * Wo;
+  MSCLIP_REQUIRE(M < (1ll << 31), "conv_tma: too many output pixels for one launch");
+  const bool f32_out = (epi == EPI_F32);
+  const bool vec_ok = ldo % (f32_out ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                      (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  MSCLIP_REQUIRE(vec_ok, "conv_tma: output rows and bias must be 16-byte aligned");
+  GemmParams p = {};
+  CUtensorMap ta[2], tb;
+  int kb = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    const ConvSource& s = src[i];
+    MSCLIP_REQUIRE(s.C % 8 == 0 && s.cpix % 8 == 0 && s.c_off % 8 == 0, "conv_tma: channels must be multiples of 8");
+    MSCLIP_REQUIRE((s.H + 2 * s.pad - s.ksize) / s.stride + 1 == Ho && (s.W + 2 * s.pad - s.ksize) / s.stride + 1 == Wo,
+                   "conv_tma: source geometry does not produce the output grid");
+    MSCLIP_TRY(make_tmap_im2col_nhwc(&ta[i], s.in, batch, s.H, s.W, s.cpix, s.c_off, s.C, s.ksize, s.stride, s.pad));
+    p.conv.ksize[i] = s.ksize;
+    p.conv.stride[i] = s.stride;
+    p.conv.pad[i] = s.pad;
+    p.conv.cblk[i] = (s.C + kBK - 1) / kBK;
+    if (i == 1) p.conv.kb_begin1 = kb;
+    kb += s.ksize * s.ksize * p.conv.cblk[i];
+  }
+  if (nsrc == 1) {
+    ta[1] = ta[0];
+    p.conv.kb_begin1 = kb;  // never reached
+    p.conv.ksize[1] = p.conv.stride[1] = p.conv.cblk[1] = 1;
+  }
+  p.conv.Ho = Ho;
+  p.conv.Wo = Wo;
+  find_divisor(static_cast<uint32_t>(Ho) * static_cast<uint32_t>(Wo), &p.conv.hw_mul, &p.conv.hw_shr);
+  find_divisor(static_cast<uint32_t>(Wo), &p.conv.wo_mul, &p.conv.wo_shr);
+  const int cg = (g_conv_pair && M >= 256) ? 2 : 1;
+  MSCLIP_TRY(make_tmap_op16_2d(&tb, Wp, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+                               static_cast<uint32_t>(bn / cg)));
+  p.M = static_cast<int>(M);
+  p.N = N;
+  p.K = K;
+  p.tiles_n = N / bn;
+  p.alpha = 1.0f;
+  p.vec_ok = 1;
+  p.total_tiles = static_cast<int>((M + kBM * cg - 1) / (kBM * cg)) * p.tiles_n;
+  p.bias = bias;
+  p.out = out;
+  p.ldo = ldo;
+  if (cg == 2) {
+    switch (bn) {
+      case 256: return launch_conv_tma_bn<256, 2>(ta[0], ta[1], tb, p, epi, stream);
+      case 192: return launch_conv_tma_bn<192, 2>(ta[0], ta[1], tb, p, epi, stream);
+      case 96: return launch_conv_tma_bn<96, 2>(ta[0], ta[1], tb, p, epi, stream);
+      case 48: return launch_conv_tma_bn<48, 2>(ta[0], ta[1], tb, p, epi, stream);
+    }
+  }
+  switch (bn) {
+    case 256: return launch_conv_tma_bn<256, 1>(ta[0], ta[1], tb, p, epi, stream);
+    case 192: return launch_conv_tma_bn<192, 1>(ta[0], ta[1], tb, p, epi, stream);
+    case 96: return launch_conv_tma_bn<96, 1>(ta[0], ta[1], tb, p, epi, stream);
+    case 48: return launch_conv_tma_bn<48, 1>(ta[0], ta[1], tb, p, epi, stream);
   }
   return 2;
 }

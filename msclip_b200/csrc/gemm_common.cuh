@@ -14,6 +14,34 @@ constexpr int kNumEpilogueWarps = 8;
 constexpr int kGemmThreads = 128 + 32 * kNumEpilogueWarps;  // TMA, MMA, TMEM-alloc, spare + epilogue warps
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 
+// A operand = implicit im2col of up to two NHWC sources onto one Ho x Wo output grid (conv_tma: the producer issues
+// one im2col-mode TMA per k-block = one filter tap x 64 channels).  K index = (source, tap, 64-channel block, channel).
+struct ConvGeom {
+  int Ho, Wo;
+  uint32_t hw_mul, hw_shr, wo_mul, wo_shr;  // n / (Ho*Wo), n / Wo as multiply-high + shift
+  int kb_begin1;                            // first k-block of source 1 (== number of k-blocks when there is one source)
+  int ksize[2], stride[2], pad[2], cblk[2]; // cblk = 64-channel blocks per tap
+};
+
+// q = n / d for 0 <= n < 2^31 as umulhi(n, mul) >> shr (d == 1: mul = 0 selects the identity)
+inline void find_divisor(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  if (d == 1) {
+    *mul = 0;
+    *shr = 0;
+    return;
+  }
+  uint32_t lg = 0;
+  while ((1ull << lg) < d) ++lg;
+  const uint32_t p = 31 + lg;
+  *mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+  *shr = p - 32;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr) {
+  return mul != 0 ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr) : n;
+}
+#endif
+
 struct GemmParams {
   int M, N, K;
   int tiles_n, total_tiles;
@@ -30,6 +58,7 @@ struct GemmParams {
   op16* out16;           // LN = 2: op16(x_new - shift), the next GEMM's A operand, pitch ldo16
   const float* colsum;   // LN = 1: sum_k W'[n][k] of the packed (gamma-folded) weight
   long long ldo16;
+  ConvGeom conv;         // CONV kernels only
 };
 
 // ---- LayerNorm folding --------------------------------------------------------------------------------------

@@ -141,6 +141,17 @@ struct ConvSource {
 int launch_conv_gemm(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const op16* W, int64_t ldw, int N,
                      const float* bias, void* out, int64_t ldo, int epi, cudaStream_t stream);
 
+// The same convolution with the A operand fetched by im2col-mode TMA (gemm.cu, gemm_tcgen05_kernel<..., CONV = 1>): no
+// gather warps, one TMA instruction per filter tap x 64-channel block.  Wp is the weight in the padded K layout
+// [N][source][ky][kx][64-channel block][64] (conv_tma_kpad columns; launch_pack_conv_kpad builds it from the dense
+// (ky, kx, c) layout); N a multiple of 48; epi EPI_RELU_BF16 or EPI_F32.
+int conv_tma_kpad(const ConvSource* src, int nsrc);
+int launch_conv_tma(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, const op16* Wp, int64_t ldw, int N,
+                    const float* bias, void* out, int64_t ldo, int epi, cudaStream_t stream);
+// dense [N][sum_src ksize^2 * C] op16 -> padded layout [N][conv_tma_kpad] (zeros in the padding columns)
+int launch_pack_conv_kpad(const op16* dense, int64_t ldd, const ConvSource* src, int nsrc, int N, op16* padded,
+                          cudaStream_t stream);
+
 // ---- attention (attention.cu): qkv op16 [B*L, 3*768] (q pre-scaled) -> out op16 [B*L, 768] ------
 int launch_attention(const op16* qkv, op16* out, int batch, int L, int heads, int causal, cudaStream_t stream);
 

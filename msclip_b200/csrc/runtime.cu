@@ -52,6 +52,48 @@ int make_tmap_op16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_im2col_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int cpix, int c_off, int C, int ksize,
+                          int stride, int pad) {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  });
+  MSCLIP_REQUIRE(fn != nullptr, "cuTensorMapEncodeIm2col is unavailable (no CUDA driver?)");
+  const uint8_t* origin = static_cast<const uint8_t*>(base) + static_cast<size_t>(c_off) * 2;
+  MSCLIP_REQUIRE((reinterpret_cast<uintptr_t>(origin) & 15) == 0 && (cpix * 2) % 16 == 0,
+                 "im2col TMA: base and pixel pitch must be 16-byte aligned");
+  MSCLIP_REQUIRE(ksize >= 1 && stride >= 1 && stride <= 8 && pad >= 0 && pad < 128 && ksize - 1 - pad < 128,
+                 "im2col TMA: filter geometry out of range");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(cpix) * 2, static_cast<cuuint64_t>(W) * cpix * 2,
+                           static_cast<cuuint64_t>(H) * W * cpix * 2};
+  // window origins (base pixels) live in [lower, dim + upper): lower = -pad, upper = pad - (ksize - 1)
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = fn(out, MSCLIP_TMA_DTYPE, 4, const_cast<uint8_t*>(origin), dims, strides, lower, upper, 64, 128, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeIm2col failed with CUresult " + std::to_string(static_cast<int>(r)) + " (N=" +
+                   std::to_string(N) + " H=" + std::to_string(H) + " W=" + std::to_string(W) + " C=" + std::to_string(C) +
+                   " cpix=" + std::to_string(cpix) + " k=" + std::to_string(ksize) + " s=" + std::to_string(stride) + " p=" +
+                   std::to_string(pad) + ")");
+    return 1;
+  }
+  return 0;
+}
+
 // cuStreamWaitValue32(stream, addr, value, GEQ): the stream stalls (no SM is occupied) until the 32-bit word at
 // `addr` - device memory that a peer GPU writes over NVLink - satisfies (int32)(*addr - value) >= 0.
 int stream_wait_value_geq(cudaStream_t stream, const uint32_t* addr, uint32_t value) {

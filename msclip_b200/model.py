@@ -32,6 +32,10 @@ from .synth import alias_of, state_dict_spec
 _IMAGE_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 
 
+class TokenRangeError(_lib.MsclipError, IndexError):
+    """Out-of-range token id: an IndexError like nn.Embedding's (M.py:3047) and a library error alike."""
+
+
 class _Node(nn.Module):
     """Anonymous container: only there so parameters get the reference's dotted names."""
 
@@ -187,7 +191,7 @@ class CLIP(nn.Module):
         image = image.contiguous()
         with self._on_device():
             self._sync_weights()
-            out = torch.empty((image.shape[0], c.embed_dim), dtype=torch.float32, device=self.device)
+            out = torch.empty((image.shape[0], c.embed_dim), dtype=torch.float32, device=image.device)
             self._check(self._library().msclip_encode_image(self._handle, C.c_void_p(image.data_ptr()), _IMAGE_DTYPES[image.dtype],
                                                       image.shape[0], C.c_void_p(out.data_ptr()), int(bool(norm)),
                                                       self._stream()), "msclip_encode_image")
@@ -217,10 +221,10 @@ class CLIP(nn.Module):
             # nn.Embedding raises on out-of-range ids (M.py:3047); so do we, before anything is launched
             lo, hi = int(text.min()), int(text.max())
             if lo < 0 or hi >= c.vocab_size:
-                raise IndexError(f"token id out of range [0, {c.vocab_size}): min {lo}, max {hi}")
+                raise TokenRangeError(f"token id out of range [0, {c.vocab_size}): min {lo}, max {hi}")
         with self._on_device():
             self._sync_weights()
-            out = torch.empty((text.shape[0], c.embed_dim), dtype=torch.float32, device=self.device)
+            out = torch.empty((text.shape[0], c.embed_dim), dtype=torch.float32, device=text.device)
             self._check(self._library().msclip_encode_text(self._handle, C.c_void_p(text.data_ptr()), text.shape[0],
                                                      C.c_void_p(out.data_ptr()), int(bool(norm)), self._stream()),
                        "msclip_encode_text")

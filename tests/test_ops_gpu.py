@@ -383,6 +383,69 @@ def test_conv_gemm_two_sources(H, cin, stride):
     assert r < tol16(), r
 
 
+TMA_CONV_CASES = CONV_CASES + [
+    ("stem0_dense", 3, 112, 48,  0,    48,  3, 2, 1, 96),      # the engine's layout: dense 48-channel pixels
+    ("win_of_96",   2, 56,  96,  48,   48,  3, 2, 1, 48),      # channel window with an offset
+    ("b16_stride1", 2, 14,  384, 0,    384, 3, 1, 1, 768),
+    ("ragged_tail", 7, 28,  192, 0,    192, 3, 2, 1, 384),     # 7 * 196 = 1372 pixels: last tile / pair half empty
+    ("tiny",        1, 8,   64,  0,    64,  3, 2, 1, 96),      # fewer pixels than one tile
+]
+
+
+@pytest.mark.parametrize("name,B,H,cpix,coff,Cc,k,s,p,N", TMA_CONV_CASES, ids=[c[0] for c in TMA_CONV_CASES])
+def test_conv_tma_matches_conv2d(name, B, H, cpix, coff, Cc, k, s, p, N):
+    """Convolution with the A operand fetched by im2col-mode TMA (gemm_tcgen05_kernel<..., CONV = 1>) against F.conv2d on
+    the same rounded operands, and bit-for-bit against the gather-fed implicit-GEMM kernel (same products, same
+    fp32 accumulation order per k-block: the padded K columns only add exact zeros)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(B, H, H, cpix, device="cuda", generator=g).to(op_dtype())
+    w = (torch.randn(N, Cc, k, k, device="cuda", generator=g) / math.sqrt(Cc * k * k)).to(op_dtype())
+    bias = torch.randn(N, device="cuda", generator=g)
+    Ho = (H + 2 * p - k) // s + 1
+    wk = w.permute(0, 2, 3, 1).reshape(N, k * k * Cc).contiguous()         # K order (ky, kx, c)
+    out = torch.full((B * Ho * Ho, N), float("nan"), device="cuda", dtype=op_dtype())
+    kp = LIB.msclip_op_conv_tma_kpad(Cc, k, 0, 0)
+    assert kp == k * k * ((Cc + 63) // 64) * 64
+    scratch = torch.empty(N * kp, device="cuda", dtype=op_dtype())
+    check(LIB.msclip_op_conv_tma(ptr(x), H, H, cpix, coff, Cc, k, s, p, None, 0, 0, 0, 0, 0, 0, 0, 0, B, Ho, Ho,
+                                 ptr(wk), k * k * Cc, N, ptr(bias), ptr(out), N, _lib.EPI_RELU_BF16, ptr(scratch), stream()))
+    nchw = x[..., coff:coff + Cc].permute(0, 3, 1, 2).float()
+    ref = torch.relu(F.conv2d(nchw, w.float(), bias, stride=s, padding=p)).permute(0, 2, 3, 1).reshape(B * Ho * Ho, N)
+    r = rel(out.float(), ref)
+    _record(f"conv_tma/{name}", {"rel": r})
+    assert torch.isfinite(out.float()).all()
+    assert r < tol16(), r
+    old = torch.zeros_like(out)
+    check(LIB.msclip_op_conv_gemm(ptr(x), H, H, cpix, coff, Cc, k, s, p, None, 0, 0, 0, 0, 0, 0, 0, 0, B, Ho, Ho,
+                                  ptr(wk), k * k * Cc, N, ptr(bias), ptr(old), N, _lib.EPI_RELU_BF16, stream()))
+    assert rel(out.float(), old.float()) < 2e-3                         # different k-block boundaries -> fp32 sum order
+
+
+@pytest.mark.parametrize("H,cin,stride", [(56, 96, 2), (28, 192, 2), (14, 384, 1), (14, 384, 2)])
+def test_conv_tma_two_sources(H, cin, stride):
+    """ConvResBlock tail (M.py:1855-1861) with both K segments fetched by im2col-mode TMA (1x1 / stride 1 and 1x1 / stride s)."""
+    B = 3
+    Ho = H // stride
+    g = torch.Generator(device="cuda").manual_seed(2)
+    pfeat = torch.randn(B, H, H, cin, device="cuda", generator=g).to(op_dtype())
+    y2 = torch.randn(B, Ho, Ho, cin, device="cuda", generator=g).to(op_dtype())
+    w3 = (torch.randn(2 * cin, cin, device="cuda", generator=g) / math.sqrt(cin)).to(op_dtype())
+    wr = (torch.randn(2 * cin, cin, device="cuda", generator=g) / math.sqrt(cin)).to(op_dtype())
+    bias = torch.randn(2 * cin, device="cuda", generator=g)
+    wk = torch.cat([w3, wr], dim=1).contiguous()
+    out = torch.full((B * Ho * Ho, 2 * cin), float("nan"), device="cuda", dtype=op_dtype())
+    kp = LIB.msclip_op_conv_tma_kpad(cin, 1, cin, 1)
+    scratch = torch.empty(2 * cin * kp, device="cuda", dtype=op_dtype())
+    check(LIB.msclip_op_conv_tma(ptr(y2), Ho, Ho, cin, 0, cin, 1, 1, 0, ptr(pfeat), H, H, cin, 0, cin, 1, stride, 0,
+                                 B, Ho, Ho, ptr(wk), 2 * cin, 2 * cin, ptr(bias), ptr(out), 2 * cin,
+                                 _lib.EPI_RELU_BF16, ptr(scratch), stream()))
+    ps = pfeat[:, ::stride, ::stride, :].float().reshape(-1, cin)
+    ref = torch.relu(y2.float().reshape(-1, cin) @ w3.float().t() + ps @ wr.float().t() + bias)
+    r = rel(out.float(), ref)
+    _record(f"conv_tma2/H{H}_s{stride}", {"rel": r})
+    assert r < tol16(), r
+
+
 @pytest.mark.parametrize("H,cpix,coff,Cc,k", [(112, 96, 48, 48, 16), (56, 96, 0, 96, 8), (14, 384, 0, 384, 1), (7, 768, 0, 768, 1)])
 def test_patch_pool(H, cpix, coff, Cc, k):
     B = 2

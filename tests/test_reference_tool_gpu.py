@@ -66,5 +66,6 @@ def test_unmodified_zero_shot_tool_runs_on_the_dropin(tmp_path, layers):
     assert res["image_features"] < 6e-3 and res["class_embeddings"] < 6e-3, res          # FEAT_TOL of test_model_gpu
     assert res["logits_max_abs"] <= 1.5e-3 * 100.0, res                                  # COS_TOL x scale
     assert res["clear_agree"] == res["clear_margin_images"], res
+    assert res["top1_agree"] >= 0.9 * n_img, res               # 48 / 48 observed on random-init weights
     assert abs(acc_ref - res["accuracy_from_dump_reference"]) < 1e-3, res
     assert abs(acc_our - res["accuracy_from_dump_dropin"]) < 1e-3, res
