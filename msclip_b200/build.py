@@ -19,7 +19,7 @@ OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATHS = {"bf16": os.path.join(HERE, "libmsclip_b200.so"), "fp16": os.path.join(HERE, "libmsclip_b200_fp16.so")}
 LIB_PATH = LIB_PATHS["bf16"]
 SOURCES = ["runtime.cu", "gemm.cu", "conv_gemm.cu", "elementwise.cu", "conv.cu", "front.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
-HEADERS = ["common.cuh", "gemm_common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
+HEADERS = ["common.cuh", "gemm_common.cuh", "rowops.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
            os.path.join("..", "..", "include", "msclip_b200_ops.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -217,6 +217,14 @@ struct Packer {
       shift[i] = b[i] - m[i] * scale[i];
     }
   }
+  // dense (source, ky, kx, c) weight -> the padded layout the im2col-TMA convolution consumes (gemm.cu, conv_tma_kpad)
+  void kpad(ConvWeights& cw, int c0, int k0, int c1 = 0, int k1 = 0) {
+    ConvSource src[2] = {{nullptr, 0, 0, 0, 0, c0, k0, 1, 0}, {nullptr, 0, 0, 0, 0, c1, k1, 1, 0}};
+    const int nsrc = c1 > 0 ? 2 : 1;
+    cw.K_tma = conv_tma_kpad(src, nsrc);
+    cw.w_tma = static_cast<op16*>(dalloc(static_cast<size_t>(cw.N) * cw.K_tma * 2));
+    if (cw.w_tma && launch_pack_conv_kpad(cw.w, cw.K, src, nsrc, cw.N, cw.w_tma, stream)) rc = 1;
+  }
   // conv weight [N,C,kh,kw] * scale[n] -> dst[n*ldk + koff + (ky*kw+kx)*C + c]
   void conv_into(const std::string& k, const std::vector<float>& scale, std::vector<float>& dst, int ldk, int koff) {
     const RawTensor& t = raw(k);
@@ -350,6 +358,7 @@ int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
       h->stem[i].b = P.up_f32(B);
       h->stem[i].N = N;
       h->stem[i].K = K;
+      P.kpad(h->stem[i], ch, 3);
       ch *= 2;
     }
     std::vector<float> W(static_cast<size_t>(w) * w, 0.f);
@@ -376,6 +385,7 @@ int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
       std::vector<float> W(static_cast<size_t>(mid) * 9 * mid, 0.f);
       P.conv_into(p + "conv2.weight", sc, W, 9 * mid, 0);
       h->br2[j] = {P.up_bf16(W), P.up_f32(sh), mid, 9 * mid};
+      P.kpad(h->br2[j], mid, 3);
     }
     {  // conv3 on the main path and the strided 1x1 shortcut become one GEMM over K = [y2 | x_strided]
       P.bn(p + "bn3", 1e-6f, sc, sh);
@@ -386,6 +396,7 @@ int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
       P.conv_into(p + "residual_conv.weight", sc2, W, K, mid);
       for (int n = 0; n < cout; ++n) B[n] = sh[n] + sh2[n];
       h->br3[j] = {P.up_bf16(W), P.up_f32(B), cout, K};
+      P.kpad(h->br3[j], mid, 1, cin, 1);
     }
   }
   // ---- lateral adapters (M.py:1556-1637)
@@ -563,11 +574,40 @@ static int ensure_xchg(msclip_ctx* h, int batch) {
 }
 
 // ------------------------------------------------------------------------------------ shared block
-// rec: the two row-record buffers of the LN fold; rec[0] describes x on entry and on return (hbuf = centred copy of x)
+// MSCLIP_LN_WARPS=0: separate LayerNorm launches instead of the LayerNorm warps inside the residual GEMMs (A/B timing)
+static const bool g_ln_warps = [] {
+  const char* e = getenv("MSCLIP_LN_WARPS");
+  return e == nullptr || e[0] != '0';
+}();
+
+// rec: the two row-record buffers of the LN fold; rec[0] describes x on entry and on return (hbuf = centred copy of x).
+// h_ready: hbuf already holds ln_1(x) of this block - written by the LayerNorm warps of the previous block's fc2 kernel.
+// next: the block that follows with nothing in between (its ln_1 is then produced by this block's fc2 kernel), or null.
+// Returns (through h_ready) whether hbuf holds ln_1 of `next` on return.
 static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, op16* hbuf,
-                     op16* qkv, op16* attn, op16* fc1, float** rec, cudaStream_t s) {
+                     op16* qkv, op16* attn, op16* fc1, float** rec, bool* h_ready, const BlockWeights* next, cudaStream_t s) {
   const int w = h->cfg.width;
   const int M = batch * L;
+  if (!g_ln_fold && g_ln_warps && M >= 256 && w == 768) {
+    // out-proj and fc2 update the residual stream AND emit the LayerNorm the next GEMM consumes (gemm.cu, LN = 3)
+    int launches = 5;
+    if (!*h_ready) {
+      MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
+      ++launches;
+    }
+    MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, qkv, 3 * w, nullptr, 0, EPI_BF16, s));
+    MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
+    MSCLIP_TRY(launch_gemm_resid_ln(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, bw.ln2_w, bw.ln2_b, hbuf, w, s));
+    MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
+    if (next != nullptr)
+      MSCLIP_TRY(launch_gemm_resid_ln(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, next->ln1_w, next->ln1_b, hbuf, w, s));
+    else
+      MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, x, w, EPI_RESID_F32, s));
+    *h_ready = next != nullptr;
+    count_launch(launches);
+    return 0;
+  }
+  *h_ready = false;
   if (g_ln_fold) {
     MSCLIP_TRY(launch_gemm_ln(hbuf, w, bw.w_qkv_ln, w, M, 3 * w, w, bw.b_qkv_ln, qkv, 3 * w, nullptr, 0, EPI_BF16, 1, rec[0],
                               nullptr, nullptr, 0, bw.cs_qkv, s));
@@ -602,6 +642,17 @@ static const bool g_front_fused = [] {
   const char* e = getenv("MSCLIP_FRONT_FUSED");
   return e == nullptr || e[0] != '0';
 }();
+// MSCLIP_CONV_GATHER=1 keeps the gather-fed implicit-GEMM kernel (conv_gemm.cu) instead of the im2col-TMA one (A/B timing)
+static const bool g_conv_gather = [] {
+  const char* e = getenv("MSCLIP_CONV_GATHER");
+  return e != nullptr && e[0] == '1';
+}();
+static int conv_layer(const ConvSource* src, int nsrc, int nb, int Ho, const ConvWeights& cw, void* out, int64_t ldo,
+                      cudaStream_t s) {
+  if (g_conv_gather)
+    return launch_conv_gemm(src, nsrc, nb, Ho, Ho, cw.w, cw.K, cw.N, cw.b, out, ldo, EPI_RELU_BF16, s);
+  return launch_conv_tma(src, nsrc, nb, Ho, Ho, cw.w_tma, cw.K_tma, cw.N, cw.b, out, ldo, EPI_RELU_BF16, s);
+}
 static int env_int(const char* name, int dflt, int lo, int hi) {
   const char* e = getenv(name);
   if (e == nullptr || e[0] == 0) return dflt;
@@ -704,8 +755,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
                                  nullptr, 0, EPI_RELU_BF16, s));
         } else {
           const ConvSource src = {cur, Hc, Hc, cpix, 0, ch, 3, st, 1};
-          MSCLIP_TRY(launch_conv_gemm(&src, 1, nb, Ho, Ho, h->stem[i].w, 9 * ch, 2 * ch, h->stem[i].b, o, 2 * ch,
-                                      EPI_RELU_BF16, s));
+          MSCLIP_TRY(conv_layer(&src, 1, nb, Ho, h->stem[i], o, 2 * ch, s));
         }
         count_launch(g_conv_im2col ? 2 : 1);
         cur = o;
@@ -753,7 +803,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
           op16* y2 = col;
           const int y2_pitch = from_front ? 2 * cin : cin;  // stage 1: left half of [y2 | p0s]
           const ConvSource s2 = {actC, Hc, Hc, cin, 0, cin, 3, st, 1};
-          MSCLIP_TRY(launch_conv_gemm(&s2, 1, nb, Ho, Ho, h->br2[j].w, 9 * cin, cin, h->br2[j].b, y2, y2_pitch, EPI_RELU_BF16, s));
+          MSCLIP_TRY(conv_layer(&s2, 1, nb, Ho, h->br2[j], y2, y2_pitch, s));
           // p_j = relu(bn3(conv1x1(y2)) + residual_bn(conv1x1_s(p))): one GEMM over K = [y2 | strided p]
           if (from_front) {
             // both halves are dense and adjacent (the front kernel wrote the strided pixels of p_0 next to y2):
@@ -762,8 +812,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
                                    nullptr, 0, EPI_RELU_BF16, s));
           } else {
             const ConvSource s3[2] = {{y2, Ho, Ho, cin, 0, cin, 1, 1, 0}, {p, Hc, Hc, cpix, coff, cin, 1, st, 0}};
-            MSCLIP_TRY(launch_conv_gemm(s3, 2, nb, Ho, Ho, h->br3[j].w, 2 * cin, 2 * cin, h->br3[j].b, pn, 2 * cin,
-                                        EPI_RELU_BF16, s));
+            MSCLIP_TRY(conv_layer(s3, 2, nb, Ho, h->br3[j], pn, 2 * cin, s));
           }
         }
         p = pn;
@@ -799,6 +848,7 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     float* gt = gridtmp + static_cast<size_t>(b0) * g * g * w;
     MSCLIP_TRY(launch_image_embed_ln_pre(gt, h->cls, h->vpos, h->ln_pre_w, h->ln_pre_b, xc, nb, L, xcen, rec[0], s));
     count_launch(1);
+    bool h_ready = false;
     for (int idx = 1; idx < c.layers; ++idx) {
       for (int j = 0; j < n_active; ++j) {
         if (kLateral[j] != idx) continue;
@@ -809,8 +859,13 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, xcen, rec[0], s));
         count_launch(2);
         std::swap(xc, xo);
+        h_ready = false;
       }
-      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, rec, s));
+      // the next block's ln_1 can ride on this block's fc2 unless a lateral adapter rewrites x in between
+      bool adapter_next = false;
+      for (int j = 0; j < n_active; ++j) adapter_next |= kLateral[j] == idx + 1;
+      const BlockWeights* next = (idx + 1 < c.layers && !adapter_next) ? &h->vblocks[idx + 1] : nullptr;
+      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, rec, &h_ready, next, s));
     }
     // CLS -> ln_post -> proj -> L2 norm (M.py:2685-2690, 2982-2983)
     MSCLIP_TRY(launch_layernorm_op16(xc, L, h->ln_post_w, h->ln_post_b, pool_ln, nb, s));
@@ -849,8 +904,10 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
     const int64_t* tk = tok + static_cast<size_t>(b0) * Lt;
     MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0], s));
     count_launch(1);
+    bool h_ready = false;
     for (int idx = 0; idx < c.layers; ++idx)
-      MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, rec, s));
+      MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, rec, &h_ready,
+                           idx + 1 < c.layers ? &h->tblocks[idx + 1] : nullptr, s));
     MSCLIP_TRY(launch_eot_layernorm_op16(x, L, tk, Lt, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->tproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));

@@ -40,6 +40,8 @@ struct ConvWeights {
   op16* w = nullptr;   // [N, K] op16, BN scale folded
   float* b = nullptr;  // [N] BN shift (null = no bias)
   int N = 0, K = 0;
+  op16* w_tma = nullptr;  // the same weight in the padded K layout of the im2col-TMA kernel (conv_tma_kpad columns)
+  int K_tma = 0;
 };
 
 struct AdapterWeights {

@@ -15,6 +15,7 @@
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include "gemm_common.cuh"
+#include "rowops.cuh"
 
 namespace msclip {
 
@@ -51,8 +52,14 @@ struct GemmCfg {
 // im2col-mode TMA (one instruction per k-block = filter tap x 64 channels: the hardware walks the 128 output pixels of
 // the tile with the convolution stride, applies the tap offset and zero-fills the padding), tmap_a / tmap_a2 = the
 // sources' im2col maps.  Everything downstream of the smem ring is the plain GEMM.
+// LN = 3 (EPI_RESID_F32, N = 768, CTA pairs): the three column tiles of a 256-row block are taken back to back by the
+// same CTA pair, and four extra "LayerNorm warps" per CTA (512 threads; registers re-partitioned with setmaxnreg) wait
+// until the epilogue warps have stored all 768 columns of the CTA's 128 rows, re-read them (L2 hits: they were written
+// microseconds earlier by the same SM) and write LayerNorm(x_new) as the next GEMM's 16-bit A operand - with the row
+// arithmetic of layernorm_kernel (rowops.cuh), so the result is bit-identical to the separate pass it replaces.
+constexpr int kLnWarps = 4;
 template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8, int CONV = 0>
-__global__ void __launch_bounds__(128 + 32 * NE, 1)
+__global__ void __launch_bounds__(128 + 32 * NE + (LN == 3 ? 32 * kLnWarps : 0), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using Cfg = GemmCfg<BN, CG>;
@@ -62,7 +69,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rows_done_bar = tempty_bar + 2;  // LN = 3: epilogue warps -> LayerNorm warps (row block stored), 2 slots
+  uint64_t* ln_free_bar = rows_done_bar + 2; // LN = 3: LayerNorm warps -> epilogue warps (slot consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_free_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,6 +97,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], NE * CG);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&rows_done_bar[i], NE);
+      mbar_init(&ln_free_bar[i], kLnWarps);
     }
     fence_mbar_init();
   }
@@ -105,12 +116,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_kb = (p.K + kBK - 1) / kBK;
+  static_assert(LN != 3 || (CG == 2 && NP == 1 && NE == 8 && EPI == EPI_RESID_F32 && BN == 256), "LayerNorm warps: pair tiles of the residual GEMMs");
+  // LN = 3: 512 threads -> 128 registers each (ptxas takes the ceiling from the launch bounds, setmaxnreg does not raise
+  // it for a region): the epilogue warps drain the accumulator in 16-column pieces there, like the 12 / 16-warp variants
+  // it-th tile of this CTA (pair / cluster), -1 past the end.  LN = 3 walks row blocks (first_tile / tile_step count
+  // 256-row blocks) and takes the tiles_n column tiles of a block back to back.
+  auto tile_at = [&](int it) -> int {
+    if (LN == 3) {
+      const int blk = it / p.tiles_n;
+      const int mb = first_tile + blk * tile_step;
+      return mb * p.tiles_n < p.total_tiles ? mb * p.tiles_n + (it - blk * p.tiles_n) : -1;
+    }
+    const int t = first_tile + it * tile_step;
+    return t < p.total_tiles ? t : -1;
+  };
 
+  if (warp < 4) {
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
         const int m0 = (tile / p.tiles_n) * (kBM * CG * NP) + static_cast<int>(pair_idx) * (kBM * CG) +
                        static_cast<int>(cta_rank) * kBM;
         const int n0 = (tile % p.tiles_n) * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
@@ -186,7 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
         mbar_wait(&tempty_bar[as], aph ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
@@ -216,12 +242,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (as == 0) aph ^= 1;
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else if (warp < 4 + NE) {
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;    // which share of the tile's column chunks this warp drains
     constexpr int kParts = NE / 4;
     // more epilogue warps run under a tighter register cap: they drain the tile in 16-column pieces
-    constexpr int kCh = (NE > 8 && Cfg::kChunk == 32) ? 16 : Cfg::kChunk;
+    constexpr int kCh = ((NE > 8 || LN == 3) && Cfg::kChunk == 32) ? 16 : Cfg::kChunk;
     constexpr int kNumCh = BN / kCh;
     static_assert(NE % 4 == 0 && kParts >= 1 && (LN != 2 || kParts == 2), "LN emit slots assume two column halves per tile");
     constexpr int kPerHalf = (kNumCh + kParts - 1) / kParts;
@@ -229,7 +256,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int c_end = (c_begin + kPerHalf < kNumCh) ? c_begin + kPerHalf : kNumCh;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+    for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       const int m0 = (tile / p.tiles_n) * (kBM * CG * NP) + static_cast<int>(pair_idx) * (kBM * CG) +
                      static_cast<int>(cta_rank) * kBM;
       const int n0 = (tile % p.tiles_n) * BN;
@@ -314,9 +341,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), leader_rank));
         else mbar_arrive(&tempty_bar[as]);
+        if (LN == 3 && tile % p.tiles_n == p.tiles_n - 1) {
+          // all column tiles of this row block are stored (by this warp; __syncwarp ordered the other lanes' stores
+          // before this arrive): hand the block to the LayerNorm warps once its slot has been consumed
+          const int blk = it / p.tiles_n;
+          mbar_wait(&ln_free_bar[blk & 1], ((blk >> 1) & 1) ^ 1, 5);
+          mbar_arrive(&rows_done_bar[blk & 1]);
+        }
       }
       as ^= 1;
       if (as == 0) aph ^= 1;
+    }
+  } else if (LN == 3) {
+    // ------------------------------------------------------------------ LayerNorm warps
+    const int lw = warp - (4 + NE);
+    const float* xsrc = reinterpret_cast<const float*>(p.out);
+    for (int blk = 0;; ++blk) {
+      const int mb = first_tile + blk * tile_step;
+      if (mb * p.tiles_n >= p.total_tiles) break;
+      const int r0 = mb * (kBM * CG) + static_cast<int>(cta_rank) * kBM + lw * (kBM / kLnWarps);
+      mbar_wait(&rows_done_bar[blk & 1], (blk >> 1) & 1, 6);
+      // two rows in flight per warp (12 x 16 bytes per lane); .cg loads: the rows live in L2, not in this SM's L1
+#pragma unroll 1
+      for (int r = r0; r < r0 + kBM / kLnWarps; r += 2) {
+        float4 va[rowops::kVec], vb[rowops::kVec];
+        const bool oka = r < p.M, okb = r + 1 < p.M;
+        const float4* sa = reinterpret_cast<const float4*>(xsrc + static_cast<long long>(r) * p.ldo);
+        const float4* sb = reinterpret_cast<const float4*>(xsrc + static_cast<long long>(r + 1) * p.ldo);
+#pragma unroll
+        for (int i = 0; i < rowops::kVec; ++i) {
+          if (oka) va[i] = __ldcg(sa + lane + 32 * i);
+          if (okb) vb[i] = __ldcg(sb + lane + 32 * i);
+        }
+        if (oka) {
+          rowops::layer_norm_row(va, p.lnw_gamma, p.lnw_beta, lane);
+          rowops::store_row_bf16(p.lnw_out + static_cast<long long>(r) * p.lnw_ld, lane, va);
+        }
+        if (okb) {
+          rowops::layer_norm_row(vb, p.lnw_gamma, p.lnw_beta, lane);
+          rowops::store_row_bf16(p.lnw_out + static_cast<long long>(r + 1) * p.lnw_ld, lane, vb);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ln_free_bar[blk & 1]);
     }
   }
   tc_fence_before();
@@ -337,10 +404,11 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     configured = true;
   }
   const int units = num_sms() / (CG * NP);  // CTAs, CTA pairs or clusters that can be resident
-  const int n = p.total_tiles < units ? p.total_tiles : units;
+  const int work = LN == 3 ? p.total_tiles / p.tiles_n : p.total_tiles;  // LN = 3 schedules whole row blocks
+  const int n = work < units ? work : units;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n * CG * NP);
-  cfg.blockDim = dim3(128 + 32 * NE);
+  cfg.blockDim = dim3(128 + 32 * NE + (LN == 3 ? 32 * kLnWarps : 0));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -487,6 +555,40 @@ int launch_gemm_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M
                                       : launch_variant<256, EPI_BF16, 1, 1, 1>(ta, tb, p, stream);
   return cg == 2 ? launch_variant<256, EPI_QGELU_BF16, 2, 1, 1>(ta, tb, p, stream)
                  : launch_variant<256, EPI_QGELU_BF16, 1, 1, 1>(ta, tb, p, stream);
+}
+
+// x (fp32, in place) += A . W^T + bias, and h = LayerNorm(x) * gamma + beta as op16 - the residual GEMMs of the shared
+// block (out-proj M.py:747 + ln_2, fc2 M.py:798 + the next block's ln_1, M.py:1027-1028) with the LayerNorm done by extra
+// warps of the same kernel (LN = 3 above).  N must be 768, M >= 256.
+int launch_gemm_resid_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, float* x,
+                         int64_t ldx, const float* gamma, const float* beta, op16* h, int64_t ldh, cudaStream_t stream) {
+  MSCLIP_REQUIRE(M >= 256 && N == rowops::kD && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
+                 "launch_gemm_resid_ln: needs M >= 256, N = 768 and 16-byte aligned operand rows");
+  MSCLIP_REQUIRE(ldx % 4 == 0 && ldh % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(h) & 7) == 0 &&
+                     (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(beta) & 15) == 0 && bias && gamma && beta,
+                 "launch_gemm_resid_ln: x, h, bias, gamma and beta must be aligned and non-null");
+  CUtensorMap ta, tb;
+  MSCLIP_TRY(make_tmap_op16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM));
+  MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw), 128));
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.tiles_n = N / 256;
+  p.alpha = 1.0f;
+  p.vec_ok = 1;
+  p.total_tiles = ((M + 2 * kBM - 1) / (2 * kBM)) * p.tiles_n;
+  p.bias = bias;
+  p.out = x;
+  p.resid = x;
+  p.ldo = ldx;
+  p.ldr = ldx;
+  p.lnw_gamma = gamma;
+  p.lnw_beta = beta;
+  p.lnw_out = h;
+  p.lnw_ld = ldh;
+  return launch_variant<256, EPI_RESID_F32, 2, 1, 3>(ta, tb, p, stream);
 }
 
 static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,

@@ -59,6 +59,12 @@ struct GemmParams {
   const float* colsum;   // LN = 1: sum_k W'[n][k] of the packed (gamma-folded) weight
   long long ldo16;
   ConvGeom conv;         // CONV kernels only
+  // LN = 3 (out-proj, fc2; N = 768): four extra warps per CTA re-read every finished 128 x 768 row block of `out`
+  // from L2 and write its LayerNorm (the next GEMM's A operand) - the separate LayerNorm pass over HBM disappears
+  const float* lnw_gamma;
+  const float* lnw_beta;
+  op16* lnw_out;
+  long long lnw_ld;
 };
 
 // ---- LayerNorm folding --------------------------------------------------------------------------------------

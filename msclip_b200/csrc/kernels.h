@@ -70,6 +70,11 @@ int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, i
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
                        cudaStream_t stream);
 
+// Residual GEMM + LayerNorm of the updated rows in one kernel (gemm.cu, LN = 3): x += A . W^T + bias (fp32, in place);
+// h = LayerNorm(x) * gamma + beta (op16, bit-identical to launch_layernorm_op16 on the same x).  N = 768, M >= 256.
+int launch_gemm_resid_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, float* x,
+                         int64_t ldx, const float* gamma, const float* beta, op16* h, int64_t ldh, cudaStream_t stream);
+
 // LayerNorm folded into the GEMMs around it (gemm_common.cuh).  ln_mode 1 (QKV, fc1; epi EPI_BF16 / EPI_QGELU_BF16):
 // A = op16(x - shift), W = W * diag(gamma), bias = b + W . beta, colsum[n] = sum_k W'[n][k]; the epilogue applies
 // rstd * (acc - mean_c * colsum) from the row records ln_in.  ln_mode 2 (out-proj, fc2; EPI_RESID_F32, N = 768): also

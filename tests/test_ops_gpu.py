@@ -177,6 +177,33 @@ def test_gemm_rejects_bad_arguments():
     assert rc != 0 and "multiples of 8" in _lib.last_error(PREC)
 
 
+@pytest.mark.parametrize("M,K", [(4096 * 77, 768), (4096 + 77, 768), (600, 3072), (256, 768), (257, 768), (20000, 3072)])
+def test_gemm_resid_ln_equals_gemm_then_layernorm(M, K):
+    """out-proj / fc2 with the LayerNorm warps (gemm.cu, LN = 3) against the two launches they replace: the updated
+    residual stream within fp32 summation-order noise of the plain residual GEMM (different epilogue chunking, same
+    products), and h BIT-IDENTICAL to layernorm_kernel applied to the x the fused kernel wrote."""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    N = 768
+    a = torch.randn(M, K, device="cuda", generator=g).to(op_dtype())
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(op_dtype())
+    b = 0.2 * torch.randn(N, device="cuda", generator=g)
+    gamma = 1.0 + 0.3 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(N, device="cuda", generator=g)
+    x0 = torch.randn(M, N, device="cuda", generator=g) + 2.0 * torch.randn(M, 1, device="cuda", generator=g)
+    x_f, x_p = x0.clone(), x0.clone()
+    h_f = torch.full((M, N), float("nan"), device="cuda", dtype=op_dtype())
+    check(LIB.msclip_op_gemm_resid_ln(ptr(a), K, ptr(w), K, M, N, K, ptr(b), ptr(x_f), N, ptr(gamma), ptr(beta), ptr(h_f), N, stream()))
+    check(LIB.msclip_op_gemm(ptr(a), K, ptr(w), K, M, N, K, 1.0, ptr(b), ptr(x_p), N, ptr(x_p), N, _lib.EPI_RESID_F32, stream()))
+    assert torch.equal(x_f, x_p)                         # same MMAs, same epilogue arithmetic per element
+    h_ref = torch.empty(M, N, device="cuda", dtype=op_dtype())
+    check(LIB.msclip_op_layernorm(ptr(x_f), 1, ptr(gamma), ptr(beta), ptr(h_ref), M, stream()))
+    assert torch.equal(h_f.view(torch.int16), h_ref.view(torch.int16))
+    ref = x0.double() + a.double() @ w.double().t() + b.double()
+    r = rel(x_f, ref.float())
+    _record(f"gemm_resid_ln/M{M}_K{K}", {"rel": r})
+    assert r < 2e-5, r
+
+
 def _ln_records(x):
     """Row records of the LN fold as the elementwise producers write them: shift = row mean, slice 0 = sums."""
     mean = x.mean(-1, keepdim=True)
