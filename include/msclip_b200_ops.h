@@ -56,9 +56,12 @@ int msclip_op_gemm_ln(const void* a, int64_t lda, const void* w, int64_t ldw, in
 /* Residual GEMM + LayerNorm of the updated rows in ONE kernel (out-proj + ln_2, fc2 + the next block's ln_1,
  * M.py:1027-1028): x[m, 768] (f32, in place) += a . w^T + bias, then h_out = LayerNorm(x) * gamma + beta (16-bit), written by
  * four extra warps per CTA that re-read each finished 128-row block from L2.  n must be 768, m >= 256.
- * h_out is bit-identical to msclip_op_layernorm applied to the updated x. */
+ * h_out is bit-identical to msclip_op_layernorm applied to the updated x.  `counters`: msclip_op_gemm_resid_ln_counters(m)
+ * zero-initialised uint32 words of device memory (left zero by every call). */
 int msclip_op_gemm_resid_ln(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, const float* bias, float* x,
-                            int64_t ldx, const float* gamma, const float* beta, void* h_out, int64_t ldh, void* stream);
+                            int64_t ldx, const float* gamma, const float* beta, void* h_out, int64_t ldh, void* counters,
+                            void* stream);
+size_t msclip_op_gemm_resid_ln_counters(int m);
 
 /* w_out[n,k] = bf16(w[n,k] * row_scale[n] * gamma[k]); colsum[n] = sum_k w_out[n,k]; bias_out[n] = row_scale[n] *
  * (bias[n] + sum_k w[n,k] * beta[k]); row_scale / bias may be NULL. */

@@ -74,7 +74,8 @@ _SIGNATURES = {
     "msclip_op_gemm": (_I, [_P, _L, _P, _L, _I, _I, _I, _F, _P, _P, _L, _P, _L, _I, _P]),
     "msclip_op_set_gemm_pair_mode": (None, [_I]),
     "msclip_op_gemm_ln": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _P, _L, _I, _I, _P, _P, _P, _L, _P, _P]),
-    "msclip_op_gemm_resid_ln": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _P, _P, _P, _L, _P]),
+    "msclip_op_gemm_resid_ln": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _P, _L, _P, _P, _P, _L, _P, _P]),
+    "msclip_op_gemm_resid_ln_counters": (C.c_size_t, [_I]),
     "msclip_op_pack_ln_fold": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "msclip_op_layernorm": (_I, [_P, _I, _P, _P, _P, _I, _P]),
     "msclip_op_attention": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -215,10 +215,12 @@ int msclip_op_gemm_ln(const void* a, int64_t lda, const void* w, int64_t ldw, in
                         epilogue, ln_mode, ln_in, ln_out, static_cast<op16*>(out16), ldo16, colsum, as_stream(stream));
 }
 int msclip_op_gemm_resid_ln(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n, int k, const float* bias, float* x,
-                            int64_t ldx, const float* gamma, const float* beta, void* h_out, int64_t ldh, void* stream) {
+                            int64_t ldx, const float* gamma, const float* beta, void* h_out, int64_t ldh, void* counters,
+                            void* stream) {
   return launch_gemm_resid_ln(static_cast<const op16*>(a), lda, static_cast<const op16*>(w), ldw, m, n, k, bias, x, ldx, gamma, beta,
-                              static_cast<op16*>(h_out), ldh, as_stream(stream));
+                              static_cast<op16*>(h_out), ldh, static_cast<uint32_t*>(counters), as_stream(stream));
 }
+size_t msclip_op_gemm_resid_ln_counters(int m) { return gemm_resid_ln_counters(m); }
 int msclip_op_pack_ln_fold(const float* w, const float* row_scale, const float* gamma, const float* beta, const float* bias,
                            void* w_out_bf16, float* colsum, float* bias_out, int n, int k, void* stream) {
   return launch_pack_ln_fold(w, row_scale, gamma, beta, bias, static_cast<op16*>(w_out_bf16), colsum, bias_out, n, k,

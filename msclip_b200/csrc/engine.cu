@@ -574,10 +574,16 @@ static int ensure_xchg(msclip_ctx* h, int batch) {
 }
 
 // ------------------------------------------------------------------------------------ shared block
-// MSCLIP_LN_WARPS=0: separate LayerNorm launches instead of the LayerNorm warps inside the residual GEMMs (A/B timing)
+// MSCLIP_LN_WARPS=1: out-proj / fc2 run as gemm.cu's LN = 3 variant, whose four extra "LayerNorm warps" per CTA normalise
+// every finished row block (the next GEMM's A operand) instead of a separate LayerNorm launch.  Bit-identical
+// (tests/test_ops_gpu.py::test_gemm_resid_ln_equals_gemm_then_layernorm) but NOT faster on the B200, so off by default:
+// text out-proj 0.95 ms fused vs 0.54 + 0.22 ms in two launches, fc2 1.59 vs 1.21 + 0.22 (tools/ln_probe.py, round 2).
+// Four warps per SM normalise ~0.75 us per row each (one dependent reduction chain at a time) - 0.4 ms for the text
+// tower's 315 392 rows, more than the HBM-bound LayerNorm kernel needs with 64 warps per SM - and they take issue slots
+// and L2 bandwidth from the epilogue warps of an already memory-bound kernel.
 static const bool g_ln_warps = [] {
   const char* e = getenv("MSCLIP_LN_WARPS");
-  return e == nullptr || e[0] != '0';
+  return e != nullptr && e[0] == '1';
 }();
 
 // rec: the two row-record buffers of the LN fold; rec[0] describes x on entry and on return (hbuf = centred copy of x).
@@ -597,10 +603,18 @@ static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch,
     }
     MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, qkv, 3 * w, nullptr, 0, EPI_BF16, s));
     MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
-    MSCLIP_TRY(launch_gemm_resid_ln(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, bw.ln2_w, bw.ln2_b, hbuf, w, s));
+    uint32_t* cnt = nullptr;
+    {
+      const size_t words = gemm_resid_ln_counters(M);
+      DevBuf& cb = h->ws["ln_counters"];
+      const bool fresh = cb.bytes < words * 4;
+      MSCLIP_TRY(ws_get(h, "ln_counters", words * 4, reinterpret_cast<void**>(&cnt)));
+      if (fresh) MSCLIP_CHECK_CUDA(cudaMemsetAsync(cnt, 0, h->ws["ln_counters"].bytes, s));  // kernels leave them zero
+    }
+    MSCLIP_TRY(launch_gemm_resid_ln(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, bw.ln2_w, bw.ln2_b, hbuf, w, cnt, s));
     MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
     if (next != nullptr)
-      MSCLIP_TRY(launch_gemm_resid_ln(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, next->ln1_w, next->ln1_b, hbuf, w, s));
+      MSCLIP_TRY(launch_gemm_resid_ln(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, next->ln1_w, next->ln1_b, hbuf, w, cnt, s));
     else
       MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, x, w, EPI_RESID_F32, s));
     *h_ready = next != nullptr;

@@ -23,16 +23,25 @@ namespace {
 
 using namespace gemm_detail;
 
-template <int BN, int CG>
+constexpr int kLnWarps = 4;        // LN = 3: LayerNorm warps per CTA
+constexpr int kLnSlotsQ = 4;       // tiles the epilogue may run ahead of the LayerNorm warps (short: the rows must still be in L2)
+constexpr int kLnRowSlots = 4;     // fp32 rows each LayerNorm warp keeps in flight (bulk copies into its shared-memory ring)
+constexpr int kLnRowBytes = 768 * 4;
+
+template <int BN, int CG, int LN = 0>
 struct GemmCfg {
   static constexpr int kBRows = BN / CG;               // rows of W this CTA stages per k-block
   static constexpr int kStageA = kBM * kBK * 2;
   static constexpr int kStageB = kBRows * kBK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStagesRaw = (192 * 1024) / kStage;
+  // LN = 3 gives one 32 KB stage to the LayerNorm warps (row staging rings + gamma / beta)
+  static constexpr int kRingBytes = (LN == 3 ? 160 : 192) * 1024;
+  static constexpr int kStagesRaw = kRingBytes / kStage;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kBarrierBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStage + kBarrierBytes + 1024;  // + alignment slack
+  static constexpr int kBarrierBytes = 512;
+  static constexpr int kLnParamBytes = (LN == 3) ? 2 * kLnRowBytes : 0;                    // gamma | beta
+  static constexpr int kLnStageBytes = (LN == 3) ? kLnWarps * kLnRowSlots * kLnRowBytes : 0;  // row rings
+  static constexpr int kSmemBytes = kStages * kStage + kBarrierBytes + kLnParamBytes + kLnStageBytes + 1024;  // + alignment slack
   static constexpr int kChunk = (BN % 32 == 0) ? 32 : 16;                     // columns per tcgen05.ld
   static_assert(kStageB % 1024 == 0, "B stage must keep 1024-byte alignment");
   static_assert(BN % 16 == 0 && BN <= 256, "UMMA N constraint");
@@ -52,26 +61,34 @@ struct GemmCfg {
 // im2col-mode TMA (one instruction per k-block = filter tap x 64 channels: the hardware walks the 128 output pixels of
 // the tile with the convolution stride, applies the tap offset and zero-fills the padding), tmap_a / tmap_a2 = the
 // sources' im2col maps.  Everything downstream of the smem ring is the plain GEMM.
-// LN = 3 (EPI_RESID_F32, N = 768, CTA pairs): the three column tiles of a 256-row block are taken back to back by the
-// same CTA pair, and four extra "LayerNorm warps" per CTA (512 threads; registers re-partitioned with setmaxnreg) wait
-// until the epilogue warps have stored all 768 columns of the CTA's 128 rows, re-read them (L2 hits: they were written
-// microseconds earlier by the same SM) and write LayerNorm(x_new) as the next GEMM's 16-bit A operand - with the row
-// arithmetic of layernorm_kernel (rowops.cuh), so the result is bit-identical to the separate pass it replaces.
-constexpr int kLnWarps = 4;
+// LN = 3 (EPI_RESID_F32, N = 768, CTA pairs): four extra "LayerNorm warps" per CTA (512 threads, 128 registers each).
+// The tile schedule is the plain one - the three column tiles of a 256-row block run on three neighbouring CTA pairs at
+// about the same time, which is what keeps the A rows and the W tiles L2-resident - so a row block is complete only once
+// three different CTAs have stored their tiles: every CTA bumps a global per-(block, CTA rank) counter after each tile.
+// Block mb is normalised by the CTA that computed its column tile mb % 3 (a fixed owner, so every CTA normalises a third
+// of the blocks it touches; "last arriver does it" piles the work on whichever pairs run late and makes them later
+// still): its LayerNorm warps wait until the counter shows all three tiles, re-read the 128 x 768 fresh rows (L2 hits)
+// and write LayerNorm(x_new) as the next GEMM's 16-bit A operand - with the row arithmetic of layernorm_kernel
+// (rowops.cuh), so the result is bit-identical to the separate pass.  The wait cannot deadlock: all CTAs are resident, a
+// CTA's epilogue never waits for another CTA, and its own LayerNorm warps lag by at most kLnSlotsQ tiles.
 template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8, int CONV = 0>
 __global__ void __launch_bounds__(128 + 32 * NE + (LN == 3 ? 32 * kLnWarps : 0), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, LN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStage);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* rows_done_bar = tempty_bar + 2;  // LN = 3: epilogue warps -> LayerNorm warps (row block stored), 2 slots
-  uint64_t* ln_free_bar = rows_done_bar + 2; // LN = 3: LayerNorm warps -> epilogue warps (slot consumed)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_free_bar + 2);
+  uint64_t* rows_done_bar = tempty_bar + 2;          // LN = 3: epilogue warps -> LayerNorm warps (tile stored), kLnSlotsQ slots
+  uint64_t* ln_free_bar = rows_done_bar + kLnSlotsQ; // LN = 3: LayerNorm warps -> epilogue warps (slot consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_free_bar + kLnSlotsQ);
+  uint64_t* ln_row_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // LN = 3: [kLnWarps][kLnRowSlots] row landed
+  float4* ln_gamma4 = reinterpret_cast<float4*>(smem + Cfg::kStages * Cfg::kStage + Cfg::kBarrierBytes);
+  float4* ln_beta4 = ln_gamma4 + 768 / 4;
+  uint8_t* ln_rows = reinterpret_cast<uint8_t*>(ln_beta4 + 768 / 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,10 +114,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], NE * CG);  // one arrive per epilogue warp (of both CTAs)
+    }
+    for (int i = 0; i < kLnSlotsQ; ++i) {
       mbar_init(&rows_done_bar[i], NE);
       mbar_init(&ln_free_bar[i], kLnWarps);
     }
+    if (LN == 3)
+      for (int i = 0; i < kLnWarps * kLnRowSlots; ++i) mbar_init(&ln_row_bar[i], 1);
     fence_mbar_init();
+  }
+  if (LN == 3 && warp >= 4 + NE) {
+    // LayerNorm parameters -> shared memory (read once per row by the LayerNorm warps)
+    for (int i = threadIdx.x - 32 * (4 + NE); i < 768 / 4; i += 32 * kLnWarps) {
+      ln_gamma4[i] = __ldg(reinterpret_cast<const float4*>(p.lnw_gamma) + i);
+      ln_beta4[i] = __ldg(reinterpret_cast<const float4*>(p.lnw_beta) + i);
+    }
   }
   if (warp == 2) {
     if (CG == 2) {
@@ -119,14 +147,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   static_assert(LN != 3 || (CG == 2 && NP == 1 && NE == 8 && EPI == EPI_RESID_F32 && BN == 256), "LayerNorm warps: pair tiles of the residual GEMMs");
   // LN = 3: 512 threads -> 128 registers each (ptxas takes the ceiling from the launch bounds, setmaxnreg does not raise
   // it for a region): the epilogue warps drain the accumulator in 16-column pieces there, like the 12 / 16-warp variants
-  // it-th tile of this CTA (pair / cluster), -1 past the end.  LN = 3 walks row blocks (first_tile / tile_step count
-  // 256-row blocks) and takes the tiles_n column tiles of a block back to back.
+  // it-th tile of this CTA (pair / cluster), -1 past the end
   auto tile_at = [&](int it) -> int {
-    if (LN == 3) {
-      const int blk = it / p.tiles_n;
-      const int mb = first_tile + blk * tile_step;
-      return mb * p.tiles_n < p.total_tiles ? mb * p.tiles_n + (it - blk * p.tiles_n) : -1;
-    }
     const int t = first_tile + it * tile_step;
     return t < p.total_tiles ? t : -1;
   };
@@ -341,12 +363,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), leader_rank));
         else mbar_arrive(&tempty_bar[as]);
-        if (LN == 3 && tile % p.tiles_n == p.tiles_n - 1) {
-          // all column tiles of this row block are stored (by this warp; __syncwarp ordered the other lanes' stores
-          // before this arrive): hand the block to the LayerNorm warps once its slot has been consumed
-          const int blk = it / p.tiles_n;
-          mbar_wait(&ln_free_bar[blk & 1], ((blk >> 1) & 1) ^ 1, 5);
-          mbar_arrive(&rows_done_bar[blk & 1]);
+        if (LN == 3) {
+          // this warp's part of the tile is stored (__syncwarp ordered the other lanes' stores before this arrive):
+          // tell the LayerNorm warps, once they have consumed the slot's previous tile
+          const int slot = it % kLnSlotsQ;
+          mbar_wait(&ln_free_bar[slot], ((it / kLnSlotsQ) & 1) ^ 1, 5);
+          mbar_arrive(&rows_done_bar[slot]);
         }
       }
       as ^= 1;
@@ -354,36 +376,127 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (LN == 3) {
     // ------------------------------------------------------------------ LayerNorm warps
+    // Every warp runs on its own (no barrier between them) with two cursors over this CTA's tile sequence:
+    //   it_pub  - next tile to acknowledge: once the epilogue warps have stored it, warp 0 adds 1 to the row block's
+    //             global counter (release at GPU scope) and every warp frees the queue slot;
+    //   it_proc - next OWNED tile (column tile == block % 3) whose row block this CTA normalises: when the block's
+    //             counter shows all three tiles, the warp streams its 32 rows through its shared-memory ring.
+    // Waiting for sibling CTAs therefore never holds back the acknowledgements (and through them the epilogue), and the
+    // poll is a relaxed load (an acquire load costs an L1 invalidation per iteration) followed by one fence.
     const int lw = warp - (4 + NE);
     const float* xsrc = reinterpret_cast<const float*>(p.out);
-    for (int blk = 0;; ++blk) {
-      const int mb = first_tile + blk * tile_step;
-      if (mb * p.tiles_n >= p.total_tiles) break;
-      const int r0 = mb * (kBM * CG) + static_cast<int>(cta_rank) * kBM + lw * (kBM / kLnWarps);
-      mbar_wait(&rows_done_bar[blk & 1], (blk >> 1) & 1, 6);
-      // two rows in flight per warp (12 x 16 bytes per lane); .cg loads: the rows live in L2, not in this SM's L1
+    constexpr int kV = rowops::kVec;
+    constexpr int kRows = kBM / kLnWarps;
+    constexpr uint32_t kTileMask = 15u, kWarpDone = 16u;  // counter = tiles stored (low bits) + 16 per LayerNorm warp done
+    uint8_t* ring = ln_rows + lw * (kLnRowSlots * kLnRowBytes);
+    uint64_t* rbar = ln_row_bar + lw * kLnRowSlots;
+    uint32_t ln_row_phase = 0u;  // bit s: parity the next wait on row slot s expects
+    auto owned = [&](int tile) { return (tile % p.tiles_n) == ((tile / p.tiles_n) % p.tiles_n); };
+    int it_pub = 0, it_proc = 0;
+    while (it_proc < it_pub && !owned(tile_at(it_proc))) ++it_proc;
+    for (;;) {
+      const int t_pub = tile_at(it_pub);
+      const bool have_owned = it_proc < it_pub;  // it_proc always rests on an owned, acknowledged tile (or == it_pub)
+      if (t_pub < 0 && !have_owned) break;
+      bool progressed = false;
+      // ---- normalise the oldest owned block if its three tiles are visible
+      if (have_owned) {
+        const int tile = tile_at(it_proc);
+        const int mb = tile / p.tiles_n;
+        uint32_t* cnt = p.lnw_counters + 2 * mb + cta_rank;
+        uint32_t seen = 0;
+        if (lane == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+        seen = __shfl_sync(0xffffffffu, seen, 0);
+        if ((seen & kTileMask) >= static_cast<uint32_t>(p.tiles_n)) {
+          const int r0 = mb * (kBM * CG) + static_cast<int>(cta_rank) * kBM + lw * kRows;
+          const int nrows = p.M - r0 < kRows ? (p.M - r0 > 0 ? p.M - r0 : 0) : kRows;
+          auto fetch = [&](int i) {  // lane 0: row r0 + i -> slot i % kLnRowSlots (one 3 KB bulk copy, no registers held)
+            const int sl = i % kLnRowSlots;
+            mbar_arrive_expect_tx(&rbar[sl], kLnRowBytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(ring + sl * kLnRowBytes)),
+                         "l"(xsrc + static_cast<long long>(r0 + i) * p.ldo), "n"(kLnRowBytes), "r"(smem_u32(&rbar[sl]))
+                         : "memory");
+          };
+          if (lane == 0) {
+            // acquire the three tiles (written with generic-proxy stores by up to three SMs, released through the
+            // counter), then hand over to the async proxy the bulk copies read with
+            __threadfence();
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            for (int i = 0; i < kLnRowSlots && i < nrows; ++i) fetch(i);
+          }
 #pragma unroll 1
-      for (int r = r0; r < r0 + kBM / kLnWarps; r += 2) {
-        float4 va[rowops::kVec], vb[rowops::kVec];
-        const bool oka = r < p.M, okb = r + 1 < p.M;
-        const float4* sa = reinterpret_cast<const float4*>(xsrc + static_cast<long long>(r) * p.ldo);
-        const float4* sb = reinterpret_cast<const float4*>(xsrc + static_cast<long long>(r + 1) * p.ldo);
+          for (int i = 0; i < nrows; ++i) {
+            const int sl = i % kLnRowSlots;
+            mbar_wait(&rbar[sl], (ln_row_phase >> sl) & 1u, 7);
+            ln_row_phase ^= 1u << sl;
+            float4 v[kV];
+            const float4* src = reinterpret_cast<const float4*>(ring + sl * kLnRowBytes);
 #pragma unroll
-        for (int i = 0; i < rowops::kVec; ++i) {
-          if (oka) va[i] = __ldcg(sa + lane + 32 * i);
-          if (okb) vb[i] = __ldcg(sb + lane + 32 * i);
-        }
-        if (oka) {
-          rowops::layer_norm_row(va, p.lnw_gamma, p.lnw_beta, lane);
-          rowops::store_row_bf16(p.lnw_out + static_cast<long long>(r) * p.lnw_ld, lane, va);
-        }
-        if (okb) {
-          rowops::layer_norm_row(vb, p.lnw_gamma, p.lnw_beta, lane);
-          rowops::store_row_bf16(p.lnw_out + static_cast<long long>(r + 1) * p.lnw_ld, lane, vb);
+            for (int k = 0; k < kV; ++k) v[k] = src[lane + 32 * k];
+            __syncwarp();  // every lane has read the slot: refill it
+            if (lane == 0 && i + kLnRowSlots < nrows) fetch(i + kLnRowSlots);
+            // per row exactly rowops::layer_norm_row's arithmetic, gamma / beta from shared memory
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < kV; ++k) sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+            const float mean = warp_sum(sum) * (1.0f / rowops::kD);
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < kV; ++k) {
+              v[k].x -= mean;
+              v[k].y -= mean;
+              v[k].z -= mean;
+              v[k].w -= mean;
+              q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+            }
+            const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / rowops::kD) + rowops::kLnEps);
+            uint2* dst = reinterpret_cast<uint2*>(p.lnw_out + static_cast<long long>(r0 + i) * p.lnw_ld);
+#pragma unroll
+            for (int k = 0; k < kV; ++k) {
+              const float4 ww = ln_gamma4[lane + 32 * k];
+              const float4 bb = ln_beta4[lane + 32 * k];
+              const float ox = ww.x * (v[k].x * rstd) + bb.x;
+              const float oy = ww.y * (v[k].y * rstd) + bb.y;
+              const float oz = ww.z * (v[k].z * rstd) + bb.z;
+              const float ow = ww.w * (v[k].w * rstd) + bb.w;
+              dst[lane + 32 * k] = make_uint2(pack16(ox, oy), pack16(oz, ow));
+            }
+          }
+          if (lane == 0) {
+            // the last of the four warps to finish returns the counter to zero for the next launch
+            const uint32_t old = atomicAdd(cnt, kWarpDone);
+            if (old == static_cast<uint32_t>(p.tiles_n) + (kLnWarps - 1) * kWarpDone) *cnt = 0u;
+          }
+          ++it_proc;
+          while (it_proc < it_pub && !owned(tile_at(it_proc))) ++it_proc;
+          progressed = true;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ln_free_bar[blk & 1]);
+      // ---- acknowledge the next stored tile (blocking only when there is nothing to normalise)
+      if (t_pub >= 0) {
+        const int slot = it_pub % kLnSlotsQ;
+        const uint32_t par = (it_pub / kLnSlotsQ) & 1;
+        bool stored;
+        if (it_proc < it_pub) {
+          stored = mbar_try_wait(&rows_done_bar[slot], par);
+        } else {
+          mbar_wait(&rows_done_bar[slot], par, 6);
+          stored = true;
+        }
+        if (stored) {
+          if (lw == 0 && lane == 0) {
+            __threadfence();  // the tile (stored by the epilogue warps, observed through the mbarrier) -> GPU scope
+            atomicAdd(p.lnw_counters + 2 * (t_pub / p.tiles_n) + cta_rank, 1u);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ln_free_bar[slot]);
+          ++it_pub;
+          while (it_proc < it_pub && !owned(tile_at(it_proc))) ++it_proc;
+          progressed = true;
+        }
+      }
+      if (!progressed) __nanosleep(200);
     }
   }
   tc_fence_before();
@@ -396,7 +509,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 template <int BN, int EPI, int CG, int NP, int LN = 0, int NE = 8, int CONV = 0>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream,
                    const CUtensorMap* ta2 = nullptr) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, LN>;
   static bool configured = false;
   if (!configured) {
     MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG, NP, LN, NE, CONV>,
@@ -404,8 +517,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     configured = true;
   }
   const int units = num_sms() / (CG * NP);  // CTAs, CTA pairs or clusters that can be resident
-  const int work = LN == 3 ? p.total_tiles / p.tiles_n : p.total_tiles;  // LN = 3 schedules whole row blocks
-  const int n = work < units ? work : units;
+  const int n = p.total_tiles < units ? p.total_tiles : units;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n * CG * NP);
   cfg.blockDim = dim3(128 + 32 * NE + (LN == 3 ? 32 * kLnWarps : 0));
@@ -561,7 +673,9 @@ int launch_gemm_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M
 // block (out-proj M.py:747 + ln_2, fc2 M.py:798 + the next block's ln_1, M.py:1027-1028) with the LayerNorm done by extra
 // warps of the same kernel (LN = 3 above).  N must be 768, M >= 256.
 int launch_gemm_resid_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, float* x,
-                         int64_t ldx, const float* gamma, const float* beta, op16* h, int64_t ldh, cudaStream_t stream) {
+                         int64_t ldx, const float* gamma, const float* beta, op16* h, int64_t ldh, uint32_t* counters,
+                         cudaStream_t stream) {
+  MSCLIP_REQUIRE(counters != nullptr, "launch_gemm_resid_ln: needs the zero-initialised block counters (gemm_resid_ln_counters(M) words)");
   MSCLIP_REQUIRE(M >= 256 && N == rowops::kD && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0,
                  "launch_gemm_resid_ln: needs M >= 256, N = 768 and 16-byte aligned operand rows");
   MSCLIP_REQUIRE(ldx % 4 == 0 && ldh % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(h) & 7) == 0 &&
@@ -588,8 +702,12 @@ int launch_gemm_resid_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw,
   p.lnw_beta = beta;
   p.lnw_out = h;
   p.lnw_ld = ldh;
+  p.lnw_counters = counters;
   return launch_variant<256, EPI_RESID_F32, 2, 1, 3>(ta, tb, p, stream);
 }
+
+// one counter per (256-row block, CTA rank): zero before the first launch, left zero by every launch
+size_t gemm_resid_ln_counters(int M) { return 2 * static_cast<size_t>((M + 2 * kBM - 1) / (2 * kBM)); }
 
 static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                             const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,

@@ -65,6 +65,7 @@ struct GemmParams {
   const float* lnw_beta;
   op16* lnw_out;
   long long lnw_ld;
+  uint32_t* lnw_counters;  // [row blocks][2]: column tiles stored so far (self-cleaning)
 };
 
 // ---- LayerNorm folding --------------------------------------------------------------------------------------

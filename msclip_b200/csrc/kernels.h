@@ -72,8 +72,11 @@ int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, i
 
 // Residual GEMM + LayerNorm of the updated rows in one kernel (gemm.cu, LN = 3): x += A . W^T + bias (fp32, in place);
 // h = LayerNorm(x) * gamma + beta (op16, bit-identical to launch_layernorm_op16 on the same x).  N = 768, M >= 256.
+// counters: gemm_resid_ln_counters(M) zero-initialised 32-bit words of device memory (every launch leaves them zero again)
 int launch_gemm_resid_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, float* x,
-                         int64_t ldx, const float* gamma, const float* beta, op16* h, int64_t ldh, cudaStream_t stream);
+                         int64_t ldx, const float* gamma, const float* beta, op16* h, int64_t ldh, uint32_t* counters,
+                         cudaStream_t stream);
+size_t gemm_resid_ln_counters(int M);
 
 // LayerNorm folded into the GEMMs around it (gemm_common.cuh).  ln_mode 1 (QKV, fc1; epi EPI_BF16 / EPI_QGELU_BF16):
 // A = op16(x - shift), W = W * diag(gamma), bias = b + W . beta, colsum[n] = sum_k W'[n][k]; the epilogue applies

@@ -192,7 +192,12 @@ def test_gemm_resid_ln_equals_gemm_then_layernorm(M, K):
     x0 = torch.randn(M, N, device="cuda", generator=g) + 2.0 * torch.randn(M, 1, device="cuda", generator=g)
     x_f, x_p = x0.clone(), x0.clone()
     h_f = torch.full((M, N), float("nan"), device="cuda", dtype=op_dtype())
-    check(LIB.msclip_op_gemm_resid_ln(ptr(a), K, ptr(w), K, M, N, K, ptr(b), ptr(x_f), N, ptr(gamma), ptr(beta), ptr(h_f), N, stream()))
+    cnt = torch.zeros(LIB.msclip_op_gemm_resid_ln_counters(M), device="cuda", dtype=torch.int32)
+    for rep in range(2):                                 # twice: the counters must come back zero
+        x_f.copy_(x0)
+        check(LIB.msclip_op_gemm_resid_ln(ptr(a), K, ptr(w), K, M, N, K, ptr(b), ptr(x_f), N, ptr(gamma), ptr(beta), ptr(h_f), N,
+                                          ptr(cnt), stream()))
+        assert int(cnt.abs().sum()) == 0
     check(LIB.msclip_op_gemm(ptr(a), K, ptr(w), K, M, N, K, 1.0, ptr(b), ptr(x_p), N, ptr(x_p), N, _lib.EPI_RESID_F32, stream()))
     assert torch.equal(x_f, x_p)                         # same MMAs, same epilogue arithmetic per element
     h_ref = torch.empty(M, N, device="cuda", dtype=op_dtype())
