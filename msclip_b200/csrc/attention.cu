@@ -4,8 +4,11 @@
 // QKV weights, heads are addressed by pointer arithmetic on the [B*L, 3*768] QKV matrix (M.py:709-711),
 // scores never leave registers and the softmax is fp32 with quad shuffles.
 //
-// One CTA per (batch, head); Q/K/V head slices are staged once in padded shared memory; every warp owns
-// 16 query rows and walks the keys in chunks (online softmax across chunks for L = 197).
+// The Q / K / V head slices of a (batch, head) item ([L, 64] windows of the [B, L, 3*768] QKV tensor) are staged by
+// TMA: one thread issues three cp.async.bulk.tensor boxes of 64 columns x KVPAD rows (128-byte rows, 128-B swizzle,
+// rows >= L arrive zero-filled) that complete on an mbarrier; no thread spends instructions on copies.  Every warp owns
+// 16 query rows and walks the keys in chunks (online softmax across chunks for L = 197); ldmatrix addresses apply the
+// same XOR swizzle (conflict-free without padding).
 // Attention is 1-2 % of the path's FLOPs and the per-head problems are far
 // smaller than one 128-row tcgen05 tile, so the contractions use warp-level mma.sync m16n8k16 (op16 in,
 // fp32 accumulate); the GEMMs that carry the other 98 % are tcgen05 (gemm.cu).
@@ -17,7 +20,12 @@ namespace msclip {
 namespace {
 
 constexpr int kHeadDim = 64;
-constexpr int kLds = 72;  // padded smem row pitch in elements (144 B): conflict-free ldmatrix
+constexpr int kRowBytes = kHeadDim * 2;  // one head-slice row = 128 B = one swizzle row
+
+// shared-memory address of the 16-byte chunk `chunk` (0..7) of row `row` in a 128-B-swizzled tile (1024-B aligned base)
+__device__ __forceinline__ uint32_t sw128(uint32_t base, int row, int chunk) {
+  return base + static_cast<uint32_t>(row) * kRowBytes + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
+}
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -37,10 +45,9 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// scores, softmax and P.V for the 16 query rows of this warp; Q/K/V head slices are in shared memory
+// scores, softmax and P.V for the 16 query rows of this warp; Q/K/V head slices are in (swizzled) shared memory
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
-__device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk, const op16* sv, op16* out_base, int L,
-                                                  int width) {
+__device__ __forceinline__ void attention_compute(uint32_t sq, uint32_t sk, uint32_t sv, op16* out_base, int L, int width) {
   constexpr int NT = KC / 8;  // score n-tiles per chunk
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -52,7 +59,7 @@ __device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk
   uint32_t qf[4][4];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk)
-    ldmatrix_x4(qf[kk], smem_u32(sq + (m0 + r8 + 8 * (mi & 1)) * kLds + kk * 16 + 8 * (mi >> 1)));
+    ldmatrix_x4(qf[kk], sw128(sq, m0 + r8 + 8 * (mi & 1), 2 * kk + (mi >> 1)));
 
   float o[8][4];
 #pragma unroll
@@ -84,7 +91,7 @@ __device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint32_t kf[4];
-          ldmatrix_x4(kf, smem_u32(sk + (kv0 + 16 * jp + r8 + 8 * (mi >> 1)) * kLds + kk * 16 + 8 * (mi & 1)));
+          ldmatrix_x4(kf, sw128(sk, kv0 + 16 * jp + r8 + 8 * (mi >> 1), 2 * kk + (mi & 1)));
           mma_16816(s[2 * jp], qf[kk], kf[0], kf[1]);
           mma_16816(s[2 * jp + 1], qf[kk], kf[2], kf[3]);
         }
@@ -148,7 +155,7 @@ __device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t vf[4];
-          ldmatrix_x4_trans(vf, smem_u32(sv + (kv0 + 16 * kk2 + r8 + 8 * (mi & 1)) * kLds + 16 * dp + 8 * (mi >> 1)));
+          ldmatrix_x4_trans(vf, sw128(sv, kv0 + 16 * kk2 + r8 + 8 * (mi & 1), 2 * dp + (mi >> 1)));
           mma_16816(o[2 * dp], pa, vf[0], vf[1]);
           mma_16816(o[2 * dp + 1], pa, vf[2], vf[3]);
         }
@@ -176,126 +183,85 @@ __device__ __forceinline__ void attention_compute(const op16* sq, const op16* sk
   }
 }
 
-template <int QPAD, int KVPAD>
-__device__ __forceinline__ void stage_item(const op16* __restrict__ base, long long pitch, int width, int L, op16* sq,
-                                           op16* sk, op16* sv, bool async) {
-  // stage the Q, K, V head slices of one (batch, head) item; rows >= L are zero
-  for (int i = threadIdx.x; i < (QPAD + 2 * KVPAD) * 8; i += blockDim.x) {
-    const int c = i & 7;
-    int row = i >> 3;
-    int which = 0;
-    if (row >= QPAD) {
-      row -= QPAD;
-      which = 1;
-      if (row >= KVPAD) {
-        row -= KVPAD;
-        which = 2;
-      }
-    }
-    op16* dst = (which == 0 ? sq : (which == 1 ? sk : sv)) + row * kLds + c * 8;
-    const op16* src = base + row * pitch + which * width + c * 8;
-    if (async) {
-      const bool ok = row < L;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(ok ? src : base),
-                   "r"(ok ? 16u : 0u)
-                   : "memory");
-    } else {
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (row < L) v = *reinterpret_cast<const uint4*>(src);
-      *reinterpret_cast<uint4*>(dst) = v;
-    }
-  }
-}
-
-// cp.async staging for the persistent kernels: thread -> fixed 16-byte column c = tid & 7, rows tid / 8 + k * (threads / 8);
-// pointers advance by constants, one bounds compare per copy (stage_item spends ~15 index instructions per copy)
-template <int QPAD, int KVPAD, int THREADS>
-__device__ __forceinline__ void stage_item_async(const op16* __restrict__ base, long long pitch, int width, int L, op16* sq,
-                                                 op16* sk, op16* sv) {
-  constexpr int kRowsPerPass = THREADS / 8;
-  static_assert(QPAD % kRowsPerPass == 0 && KVPAD % kRowsPerPass == 0, "row passes must tile the staging buffers");
-  const int c = threadIdx.x & 7;
-  const int r0 = threadIdx.x >> 3;
-  const op16* src = base + r0 * pitch + c * 8;
-  const uint32_t dq = smem_u32(sq + r0 * kLds + c * 8);
-  const uint32_t dk = smem_u32(sk + r0 * kLds + c * 8);
-  const uint32_t dv = smem_u32(sv + r0 * kLds + c * 8);
+// one (batch, head) item = three boxes [KVPAD rows][64 columns] at columns which * width + h * 64 of batch entry b
+template <int KVPAD>
+__device__ __forceinline__ void tma_stage_item(const CUtensorMap* tmap, uint8_t* buf, uint64_t* bar, int b, int h, int width) {
+  constexpr uint32_t kTile = KVPAD * kRowBytes;
+  mbar_arrive_expect_tx(bar, 3 * kTile);
 #pragma unroll
-  for (int k = 0; k < KVPAD / kRowsPerPass; ++k) {
-    const bool ok = r0 + k * kRowsPerPass < L;
-    const op16* sp = ok ? src + static_cast<long long>(k * kRowsPerPass) * pitch : base;
-    const uint32_t n = ok ? 16u : 0u;
-    const uint32_t off = static_cast<uint32_t>(k * kRowsPerPass * kLds * 2);
-    if (k < QPAD / kRowsPerPass)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dq + off), "l"(sp), "r"(n) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk + off), "l"(sp + width), "r"(n) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv + off), "l"(sp + 2 * width), "r"(n) : "memory");
-  }
+  for (int which = 0; which < 3; ++which) tma_load_3d(buf + which * kTile, tmap, bar, which * width + h * kHeadDim, 0, b);
 }
 
 // one CTA per (batch, head): used for L = 197, where two staging buffers would not fit next to each other
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
 __global__ void __launch_bounds__(QPAD * 2)
-attention_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, int heads) {
+attention_kernel(const __grid_constant__ CUtensorMap tmap, op16* __restrict__ out, int L, int heads) {
   constexpr int KVPAD = KC * NCHUNK;
-  static_assert(QPAD % 16 == 0 && KC % 16 == 0 && KVPAD >= QPAD, "tile shapes");
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  op16* sq = reinterpret_cast<op16*>(att_smem);
-  op16* sk = sq + QPAD * kLds;
-  op16* sv = sk + KVPAD * kLds;
+  constexpr uint32_t kTile = KVPAD * kRowBytes;
+  static_assert(QPAD % 16 == 0 && KC % 16 == 0 && KVPAD >= QPAD && KVPAD % 8 == 0, "tile shapes");
+  extern __shared__ uint8_t att_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 3 * kTile);
   const int b = blockIdx.x / heads;
   const int h = blockIdx.x % heads;
   const int width = heads * kHeadDim;
-  const long long pitch = 3ll * width;
-  stage_item<QPAD, KVPAD>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, sq, sk, sv, false);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    tma_stage_item<KVPAD>(&tmap, smem, bar, b, h, width);
+  }
   __syncthreads();
-  attention_compute<QPAD, KC, NCHUNK, CAUSAL>(sq, sk, sv, out + static_cast<long long>(b) * L * width + h * kHeadDim, L, width);
+  mbar_wait(bar, 0, 31);
+  const uint32_t s0 = smem_u32(smem);
+  attention_compute<QPAD, KC, NCHUNK, CAUSAL>(s0, s0 + kTile, s0 + 2 * kTile, out + static_cast<long long>(b) * L * width + h * kHeadDim,
+                                               L, width);
 }
 
-// persistent variant for the short sequences (L <= 80): every CTA walks over (batch, head) items and prefetches
-// the next item's Q/K/V with cp.async into the second staging buffer while the current item is computed, so the
-// HBM stream never waits for the tensor-core / softmax phase
+// persistent variant for the short sequences (L <= 80): every CTA walks over (batch, head) items; the next item's Q / K / V
+// boxes are in flight into the second staging buffer while the current item is computed, so the HBM stream never waits
+// for the tensor-core / softmax phase
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
 __global__ void __launch_bounds__(QPAD * 2)
-attention_persistent_kernel(const op16* __restrict__ qkv, op16* __restrict__ out, int L, int heads, int items) {
+attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap, op16* __restrict__ out, int L, int heads, int items) {
   constexpr int KVPAD = KC * NCHUNK;
-  constexpr int kBuf = (QPAD + 2 * KVPAD) * kLds;
-  extern __shared__ __align__(16) uint8_t att_smem[];
-  op16* buf = reinterpret_cast<op16*>(att_smem);
+  constexpr uint32_t kTile = KVPAD * kRowBytes;
+  constexpr uint32_t kBuf = 3 * kTile;
+  static_assert(KVPAD >= QPAD && KVPAD % 8 == 0, "Q shares the K / V box height");
+  extern __shared__ uint8_t att_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * kBuf);
   const int width = heads * kHeadDim;
-  const long long pitch = 3ll * width;
   int item = blockIdx.x;
   if (item >= items) return;
-  {
-    const int b = item / heads, h = item % heads;
-    stage_item_async<QPAD, KVPAD, QPAD * 2>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, buf,
-                                            buf + QPAD * kLds, buf + (QPAD + KVPAD) * kLds);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+    tma_stage_item<KVPAD>(&tmap, smem, &bar[0], item / heads, item % heads, width);
   }
+  __syncthreads();
   for (int it = 0; item < items; item += gridDim.x, ++it) {
-    op16* cur = buf + (it & 1) * kBuf;
-    op16* nxt = buf + ((it + 1) & 1) * kBuf;
+    const int cur = it & 1;
     const int next_item = item + gridDim.x;
-    if (next_item < items) {
-      const int b = next_item / heads, h = next_item % heads;
-      stage_item_async<QPAD, KVPAD, QPAD * 2>(qkv + static_cast<long long>(b) * L * pitch + h * kHeadDim, pitch, width, L, nxt,
-                                              nxt + QPAD * kLds, nxt + (QPAD + KVPAD) * kLds);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the prefetch just issued has landed
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
+    // the other buffer was released by the __syncthreads that ended the previous iteration
+    if (threadIdx.x == 0 && next_item < items)
+      tma_stage_item<KVPAD>(&tmap, smem + (cur ^ 1) * kBuf, &bar[cur ^ 1], next_item / heads, next_item % heads, width);
+    mbar_wait(&bar[cur], (it >> 1) & 1, 32);
     const int b = item / heads, h = item % heads;
-    attention_compute<QPAD, KC, NCHUNK, CAUSAL>(cur, cur + QPAD * kLds, cur + (QPAD + KVPAD) * kLds,
+    const uint32_t s0 = smem_u32(smem + cur * kBuf);
+    attention_compute<QPAD, KC, NCHUNK, CAUSAL>(s0, s0 + kTile, s0 + 2 * kTile,
                                                  out + static_cast<long long>(b) * L * width + h * kHeadDim, L, width);
-    __syncthreads();  // all warps are done with `cur` before the next iteration prefetches into it
+    __syncthreads();  // all warps are done with `cur` before the next iteration's boxes may land in it
   }
 }
 
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
 int launch_persistent(const op16* qkv, op16* out, int batch, int L, int heads, cudaStream_t stream) {
-  constexpr int smem = 2 * (QPAD + 2 * KC * NCHUNK) * kLds * 2;
+  constexpr int smem = 2 * 3 * KC * NCHUNK * kRowBytes + 64 + 1024;  // two staging buffers, two mbarriers, alignment slack
+  CUtensorMap tmap;
+  MSCLIP_TRY(make_tmap_op16_3d(&tmap, qkv, batch, L, 3ull * heads * kHeadDim, 3ull * heads * kHeadDim, KC * NCHUNK));
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
     MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(attention_persistent_kernel<QPAD, KC, NCHUNK, CAUSAL>,
@@ -306,21 +272,23 @@ int launch_persistent(const op16* qkv, op16* out, int batch, int L, int heads, c
   }
   const int items = batch * heads;
   const int grid = items < num_sms() * ctas_per_sm ? items : num_sms() * ctas_per_sm;
-  attention_persistent_kernel<QPAD, KC, NCHUNK, CAUSAL><<<grid, QPAD * 2, smem, stream>>>(qkv, out, L, heads, items);
+  attention_persistent_kernel<QPAD, KC, NCHUNK, CAUSAL><<<grid, QPAD * 2, smem, stream>>>(tmap, out, L, heads, items);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int QPAD, int KC, int NCHUNK, bool CAUSAL>
 int launch_variant(const op16* qkv, op16* out, int batch, int L, int heads, cudaStream_t stream) {
-  constexpr int smem = (QPAD + 2 * KC * NCHUNK) * kLds * 2;
+  constexpr int smem = 3 * KC * NCHUNK * kRowBytes + 64 + 1024;
+  CUtensorMap tmap;
+  MSCLIP_TRY(make_tmap_op16_3d(&tmap, qkv, batch, L, 3ull * heads * kHeadDim, 3ull * heads * kHeadDim, KC * NCHUNK));
   static bool configured = false;
   if (!configured) {
     MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<QPAD, KC, NCHUNK, CAUSAL>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  attention_kernel<QPAD, KC, NCHUNK, CAUSAL><<<batch * heads, QPAD * 2, smem, stream>>>(qkv, out, L, heads);
+  attention_kernel<QPAD, KC, NCHUNK, CAUSAL><<<batch * heads, QPAD * 2, smem, stream>>>(tmap, out, L, heads);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

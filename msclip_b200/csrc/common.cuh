@@ -159,6 +159,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3D tile load, coordinates (c0 = innermost element index, c1, c2)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // im2col-mode load (NHWC activation as a rank-4 tensor {C, W, H, N}): `pixelsPerColumn` output pixels starting at the
 // base pixel (w, h, n) - input coordinates of the window origin, i.e. out * stride - pad - are traversed with the
 // convolution stride along W, then H, then N inside the descriptor's bounding box; every pixel is displaced by the
@@ -374,6 +383,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_f32acc(int m, int n) { return 
 // beyond channel C.
 int make_tmap_im2col_nhwc(CUtensorMap* out, const void* base, int N, int H, int W, int cpix, int c_off, int C, int ksize,
                           int stride, int pad);
+// [batch][rows][cols] op16 (row pitch ld elements, rows * ld elements per batch entry), box = 1 x box_rows x 64 columns,
+// 128-B swizzle; rows beyond `rows` read as zero (the box may be taller than the matrix: padding rows arrive zeroed)
+int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows);
 int stream_wait_value_geq(cudaStream_t stream, const uint32_t* addr, uint32_t value);  // 0 = queued
 int make_tmap_op16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);

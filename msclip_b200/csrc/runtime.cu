@@ -52,6 +52,27 @@ int make_tmap_op16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_op16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  MSCLIP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  MSCLIP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, "TMA base / row pitch must be 16-byte aligned");
+  MSCLIP_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld * 2, rows * ld * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, MSCLIP_TMA_DTYPE, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (3D) failed with CUresult " + std::to_string(static_cast<int>(r)) + " (batch=" +
+                   std::to_string(batch) + " rows=" + std::to_string(rows) + " cols=" + std::to_string(cols) + " ld=" +
+                   std::to_string(ld) + " box_rows=" + std::to_string(box_rows) + ")");
+    return 1;
+  }
+  return 0;
+}
+
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -1,0 +1,14 @@
+#!/bin/bash
+# multi-GPU pass (gpurun --gpus N): sharded-loss parity, weak-scaling bench with the NCCL loss comparator, global batch 32768
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+N=$(nvidia-smi -L | wc -l)
+echo "GPUs: $N"
+timeout 900 python -m pytest tests/test_multigpu.py -q 2>&1 | tail -4
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+echo "bench weak N=$N exit $?"; python -c "
+import json;d=json.load(open('gpurun_out/bench_n$N.json'));print(round(d['value']), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), d['gpu_launches'], d['clocks'], 'loss', d['loss'], d['loss_expected_ln_G']); print(json.dumps(d['comparators']))"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --global-batch 32768 --steps 3 --warmup 3 --no-cpu --no-comparators > gpurun_out/bench_g32k_n$N.json 2> gpurun_out/bench_g32k_n$N.err
+echo "bench global-32768 N=$N exit $?"; python -c "
+import json;d=json.load(open('gpurun_out/bench_g32k_n$N.json'));print(round(d['value']), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), d['gpu_launches'], 'loss', d['loss'], d['loss_expected_ln_G'])"
+tail -3 gpurun_out/bench_n$N.err gpurun_out/bench_g32k_n$N.err
