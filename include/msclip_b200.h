@@ -90,6 +90,18 @@ int msclip_set_text_trim(msclip_handle h, int enable);
 /* logits[n_img, n_txt] = scale * img_feat . txt_feat^T (f32 in, f32 out; split-bf16 tensor-core product). */
 int msclip_similarity_logits(msclip_handle h, const float* img_feat, int n_img, const float* txt_feat, int n_txt,
                              float scale, float* logits, void* stream);
+/* ---- zero-shot evaluation fast path (what tools/zero_shot.py:121-132, 265-266, 150-163 compute) ----
+ * msclip_zeroshot_classifier: tokens [n_classes * n_templates, context_length] int64, class-major (host or device) ->
+ * weights [n_classes, embed_dim] f32 (host or device): per class the mean over its templates of the normalised prompt
+ * embeddings, re-normalised (the tool's zeroshot_weights, transposed).  One call instead of n_classes encode_text calls:
+ * prompts are sorted by live length and encoded in chunks, each only over its longest live prefix (bit-identical
+ * embeddings).  Synchronises the stream.
+ * msclip_zeroshot_predict: logits = scale * img_feat . weights^T (scale = 100 in the tool) and the top-k (k <= 8) class
+ * indices per image, best first, all on the device (no per-batch host round trip); logits_out may be NULL. */
+int msclip_zeroshot_classifier(msclip_handle h, const int64_t* tokens, int n_classes, int n_templates, float* weights_out,
+                               void* stream);
+int msclip_zeroshot_predict(msclip_handle h, const float* img_feat, int n_img, const float* weights, int n_classes, float scale,
+                            int topk, int32_t* topk_out, float* logits_out, void* stream);
 /* CLIP.forward for one process: logits[batch, batch] = exp(logit_scale) * I . T^T. */
 int msclip_forward(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int batch,
                    float* logits, void* stream);

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "msclip_set_text_trim": (_I, [_P, _I]),
     "msclip_similarity_logits": (_I, [_P, _P, _I, _P, _I, _F, _P, _P]),
     "msclip_forward": (_I, [_P, _P, _I, _P, _I, _P, _P]),
+    "msclip_zeroshot_classifier": (_I, [_P, _P, _I, _I, _P, _P]),
+    "msclip_zeroshot_predict": (_I, [_P, _P, _I, _P, _I, _F, _I, _P, _P, _P]),
     "msclip_comm_init": (_I, [_P, _I, _I, _I]),
     "msclip_comm_export": (_I, [_P, _P]),
     "msclip_comm_import": (_I, [_P, _P]),

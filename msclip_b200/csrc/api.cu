@@ -142,6 +142,17 @@ int msclip_similarity_logits(msclip_handle h, const float* img_feat, int n_img, 
   return engine_similarity_logits(h, img_feat, n_img, txt_feat, n_txt, scale, logits, as_stream(stream));
 }
 
+int msclip_zeroshot_classifier(msclip_handle h, const int64_t* tokens, int n_classes, int n_templates, float* weights_out,
+                               void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_zeroshot_classifier(h, tokens, n_classes, n_templates, weights_out, as_stream(stream));
+}
+int msclip_zeroshot_predict(msclip_handle h, const float* img_feat, int n_img, const float* weights, int n_classes, float scale,
+                            int topk, int32_t* topk_out, float* logits_out, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_zeroshot_predict(h, img_feat, n_img, weights, n_classes, scale, topk, topk_out, logits_out, as_stream(stream));
+}
+
 int msclip_forward(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int batch,
                    float* logits, void* stream) {
   MSCLIP_REQUIRE(h != nullptr, "null handle");

@@ -351,6 +351,127 @@ int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, c
   return 0;
 }
 
+// ---- zero-shot classifier head (tools/zero_shot.py:125-131, 266, 150-163) -------------------------------------------
+// weights[c] = normalise(mean_t feat[row_of[c * n_templates + t]]): one warp per class, E = 512 (4 float4 per lane)
+__global__ void __launch_bounds__(256)
+class_mean_renorm_kernel(const float* __restrict__ feat, const int* __restrict__ row_of, int n_classes, int n_templates, int E,
+                         float* __restrict__ weights) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= n_classes) return;
+  const int n4 = E / 4;
+  float4 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < n_templates; ++t) {
+    const long long idx = static_cast<long long>(c) * n_templates + t;
+    const long long r = row_of ? row_of[idx] : idx;
+    const float4* f4 = reinterpret_cast<const float4*>(feat + r * E);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = lane + 32 * i;
+      if (col < n4) {
+        const float4 v = f4[col];
+        acc[i].x += v.x;
+        acc[i].y += v.y;
+        acc[i].z += v.z;
+        acc[i].w += v.w;
+      }
+    }
+  }
+  const float inv_t = 1.0f / static_cast<float>(n_templates);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i].x *= inv_t;
+    acc[i].y *= inv_t;
+    acc[i].z *= inv_t;
+    acc[i].w *= inv_t;
+    s += (acc[i].x * acc[i].x + acc[i].y * acc[i].y) + (acc[i].z * acc[i].z + acc[i].w * acc[i].w);
+  }
+  const float inv = 1.0f / sqrtf(warp_sum(s));  // class_embedding /= class_embedding.norm(), no eps
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int col = lane + 32 * i;
+    if (col < n4)
+      reinterpret_cast<float4*>(weights + static_cast<long long>(c) * E)[col] =
+          make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
+  }
+}
+
+// top-k (k <= 8) class indices per row of logits [rows, n]: one warp per row; every lane keeps the k best of its strided
+// share (sorted insertion), then k rounds of warp arg-max merge them (ties -> lower index, like torch.topk on CUDA is
+// NOT guaranteed to; callers compare scores, not tie order)
+__global__ void __launch_bounds__(256)
+topk_rows_kernel(const float* __restrict__ logits, int rows, int n, int k, int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float bv[8];
+  int bi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bv[i] = -INFINITY;
+    bi[i] = 0x7fffffff;
+  }
+  const float* row = logits + static_cast<long long>(r) * n;
+  for (int j = lane; j < n; j += 32) {
+    float v = row[j];
+    int idx = j;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < k && (v > bv[i] || (v == bv[i] && idx < bi[i]))) {
+        const float tv = bv[i];
+        const int ti = bi[i];
+        bv[i] = v;
+        bi[i] = idx;
+        v = tv;
+        idx = ti;
+      }
+    }
+  }
+  for (int round = 0; round < k; ++round) {
+    float v = bv[0];
+    int idx = bi[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) {
+        v = ov;
+        idx = oi;
+      }
+    }
+    if (lane == 0) out[static_cast<long long>(r) * k + round] = idx;
+    if (bi[0] == idx) {  // the winning lane pops its head
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        bv[i] = bv[i + 1];
+        bi[i] = bi[i + 1];
+      }
+      bv[7] = -INFINITY;
+      bi[7] = 0x7fffffff;
+    }
+  }
+}
+
+int launch_class_mean_renorm(const float* feat, const int* row_of, int n_classes, int n_templates, int E, float* weights,
+                             cudaStream_t stream) {
+  if (n_classes <= 0) return 0;
+  MSCLIP_REQUIRE(E % 4 == 0 && E <= 1024 && n_templates >= 1, "class_mean_renorm: width must be a multiple of 4 and <= 1024");
+  class_mean_renorm_kernel<<<(n_classes + 7) / 8, 256, 0, stream>>>(feat, row_of, n_classes, n_templates, E, weights);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_topk_rows(const float* logits, int rows, int n, int k, int* out, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  MSCLIP_REQUIRE(k >= 1 && k <= 8 && k <= n, "topk_rows: k must be in [1, min(8, n)]");
+  topk_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(logits, rows, n, k, out);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_l2norm(const float* x, float* out_f32, emb16* out_f16, int rows, int E, int normalise,
                   cudaStream_t stream) {
   if (rows <= 0) return 0;

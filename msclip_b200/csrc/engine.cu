@@ -1186,6 +1186,91 @@ int engine_similarity_logits(msclip_ctx* h, const float* img, int n_img, const f
   return 0;
 }
 
+// Zero-shot classifier in one call (tools/zero_shot.py:121-132 builds it with one encode_text call per class): all
+// n_classes * n_templates prompts are sorted by live length (position of the EOT token) on the host, encoded in
+// length-ordered chunks - each chunk runs the causal tower only over ITS longest live prefix, bit-identical embeddings -
+// and reduced per class (mean over templates, re-normalised) by one kernel.
+int engine_zeroshot_classifier(msclip_ctx* h, const int64_t* tokens, int n_classes, int n_templates, float* weights_out,
+                               cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  MSCLIP_REQUIRE(tokens && weights_out && n_classes >= 1 && n_templates >= 1, "zeroshot_classifier: bad arguments");
+  const msclip_config& c = h->cfg;
+  const int Lt = c.context_length, E = c.embed_dim;
+  const long long n = static_cast<long long>(n_classes) * n_templates;
+  MSCLIP_REQUIRE(n < (1ll << 31), "zeroshot_classifier: too many prompts");
+  // tokens on the host (to sort) ...
+  std::vector<int64_t> host_tok;
+  const int64_t* tok_h = tokens;
+  if (is_device_pointer(tokens)) {
+    host_tok.resize(static_cast<size_t>(n) * Lt);
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(host_tok.data(), tokens, host_tok.size() * 8, cudaMemcpyDeviceToHost, s));
+    MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+    tok_h = host_tok.data();
+  }
+  // live length = argmax(token ids) + 1 (first occurrence, M.py:3059); counting sort by length keeps the order stable
+  std::vector<int> len(n), order(n), row_of(n);
+  std::vector<int> count(Lt + 2, 0);
+  for (long long i = 0; i < n; ++i) {
+    const int64_t* t = tok_h + i * Lt;
+    int best = 0;
+    for (int j = 1; j < Lt; ++j)
+      if (t[j] > t[best]) best = j;
+    len[i] = best + 1;
+    ++count[len[i] + 1];
+    for (int j = 0; j < Lt; ++j)
+      MSCLIP_REQUIRE(t[j] >= 0 && t[j] < c.vocab_size, "zeroshot_classifier: token id out of range");
+  }
+  for (int l = 1; l <= Lt + 1; ++l) count[l] += count[l - 1];
+  for (long long i = 0; i < n; ++i) order[count[len[i]]++] = static_cast<int>(i);
+  for (long long pos = 0; pos < n; ++pos) row_of[order[pos]] = static_cast<int>(pos);
+  // ... and back on the device in sorted order
+  std::vector<int64_t> sorted(static_cast<size_t>(n) * Lt);
+  for (long long pos = 0; pos < n; ++pos) memcpy(&sorted[pos * Lt], tok_h + static_cast<long long>(order[pos]) * Lt, Lt * 8);
+  WS(tok_dev, int64_t, "zs_tokens", n * Lt);
+  WS(row_dev, int, "zs_rows", n);
+  WS(feat, float, "zs_feat", n * E);
+  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(tok_dev, sorted.data(), sorted.size() * 8, cudaMemcpyHostToDevice, s));
+  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(row_dev, row_of.data(), row_of.size() * 4, cudaMemcpyHostToDevice, s));
+  for (long long b0 = 0; b0 < n; b0 += kTowerChunk) {
+    const int nb = static_cast<int>(std::min<long long>(kTowerChunk, n - b0));
+    const int live = std::min(Lt, std::max(len[order[b0 + nb - 1]], 16));  // sorted: the chunk's last prompt is its longest
+    MSCLIP_TRY(text_tower(h, tok_dev + b0 * Lt, nb, live, feat + b0 * E, 1, nullptr, s));
+  }
+  h->txt_rows = 0;
+  const bool out_dev_ptr = is_device_pointer(weights_out);
+  float* w_dev = weights_out;
+  if (!out_dev_ptr) {
+    WS(wo, float, "zs_weights", static_cast<size_t>(n_classes) * E);
+    w_dev = wo;
+  }
+  MSCLIP_TRY(launch_class_mean_renorm(feat, row_dev, n_classes, n_templates, E, w_dev, s));
+  count_launch(1);
+  // the host vectors above must outlive the copies that read them
+  MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+  if (!out_dev_ptr)
+    MSCLIP_CHECK_CUDA(cudaMemcpy(weights_out, w_dev, static_cast<size_t>(n_classes) * E * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// logits = scale * img_feat . weights^T (tools/zero_shot.py:266) and the top-k classes per image (:150-163) without a host
+// round trip per batch; logits_out may be null
+int engine_zeroshot_predict(msclip_ctx* h, const float* img_feat, int n_img, const float* weights, int n_classes, float scale,
+                            int topk, int32_t* topk_out, float* logits_out, cudaStream_t s) {
+  MSCLIP_REQUIRE(h && img_feat && weights && topk_out && n_img >= 1 && n_classes >= 1, "zeroshot_predict: bad arguments");
+  MSCLIP_REQUIRE(is_device_pointer(img_feat) && is_device_pointer(weights) && is_device_pointer(topk_out) &&
+                     (logits_out == nullptr || is_device_pointer(logits_out)),
+                 "zeroshot_predict: device pointers only");
+  float* lg = logits_out;
+  if (lg == nullptr) {
+    WS(l, float, "zs_logits", static_cast<size_t>(n_img) * n_classes);
+    lg = l;
+  }
+  MSCLIP_TRY(engine_similarity_logits(h, img_feat, n_img, weights, n_classes, scale, lg, s));
+  MSCLIP_TRY(launch_topk_rows(lg, n_img, n_classes, topk, topk_out, s));
+  count_launch(1);
+  return 0;
+}
+
 int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int batch, float* logits,
                    cudaStream_t s) {
   MSCLIP_TRY(require_ready(h));

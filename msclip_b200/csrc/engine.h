@@ -118,6 +118,10 @@ int engine_encode_text(msclip_ctx* h, const int64_t* tokens, int batch, float* o
                        cudaStream_t stream);
 int engine_similarity_logits(msclip_ctx* h, const float* img, int n_img, const float* txt, int n_txt, float scale,
                              float* logits, cudaStream_t stream);
+int engine_zeroshot_classifier(msclip_ctx* h, const int64_t* tokens, int n_classes, int n_templates, float* weights_out,
+                               cudaStream_t stream);
+int engine_zeroshot_predict(msclip_ctx* h, const float* img_feat, int n_img, const float* weights, int n_classes, float scale,
+                            int topk, int32_t* topk_out, float* logits_out, cudaStream_t stream);
 int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int batch, float* logits,
                    cudaStream_t stream);
 int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* partial_out, float* loss_out,

@@ -116,6 +116,12 @@ int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, c
 int check_token_error(cudaStream_t stream);  // synchronises; non-zero if an out-of-range token id was seen
 int launch_l2norm(const float* x, float* out_f32, emb16* out_f16, int rows, int E, int normalise, cudaStream_t stream);
 
+// zero-shot head (tools/zero_shot.py:125-131, 150-163): weights[c] = normalise(mean over templates of feat[row_of[c*T + t]])
+// (row_of null = identity); top-k (k <= 8) column indices of every row of logits [rows, n], best first
+int launch_class_mean_renorm(const float* feat, const int* row_of, int n_classes, int n_templates, int E, float* weights,
+                             cudaStream_t stream);
+int launch_topk_rows(const float* logits, int rows, int n, int k, int* out, cudaStream_t stream);
+
 // ---- conv helpers (conv.cu) -------------------------------------------------------------------
 // NCHW fp32 image -> im2col rows [B*Ho*Wo, 32] op16 for the 3x3 stride-2 pad-1 first convs; k = c*9+ky*3+kx
 int launch_im2col_first(const void* img, int img_dtype, op16* out, int batch, int H, int W, cudaStream_t stream);

@@ -251,6 +251,42 @@ class CLIP(nn.Module):
         return out
 
     @torch.no_grad()
+    def zeroshot_classifier(self, tokens: torch.Tensor) -> torch.Tensor:
+        """The tool's ``zeroshot_classifier`` (tools/zero_shot.py:121-132) in one call: ``tokens`` [n_classes,
+        n_templates, context_length] -> ``zeroshot_weights`` [embed_dim, n_classes] (a transposed view of the
+        [n_classes, embed_dim] result), per class the re-normalised mean of the normalised prompt embeddings."""
+        c = self.cfg
+        if tokens.dim() != 3 or tokens.shape[2] != c.context_length:
+            raise ValueError(f"expected [n_classes, n_templates, {c.context_length}] token ids, got {tuple(tokens.shape)}")
+        tokens = tokens.to(torch.long).contiguous()
+        n_cls, n_tpl = int(tokens.shape[0]), int(tokens.shape[1])
+        with self._on_device():
+            self._sync_weights()
+            out = torch.empty((n_cls, c.embed_dim), dtype=torch.float32, device=self.device)
+            self._check(self._library().msclip_zeroshot_classifier(self._handle, C.c_void_p(tokens.data_ptr()), n_cls, n_tpl,
+                                                                  C.c_void_p(out.data_ptr()), self._stream()),
+                        "msclip_zeroshot_classifier")
+        return out.t()
+
+    @torch.no_grad()
+    def zeroshot_predict(self, image_features: torch.Tensor, zeroshot_weights: torch.Tensor, topk: int = 1,
+                         scale: float = 100.0, return_logits: bool = False):
+        """``scale * features @ zeroshot_weights`` and the top-k classes per image (tools/zero_shot.py:266, 150-163),
+        entirely on the device.  ``zeroshot_weights`` is [embed_dim, n_classes] as the tool stacks it."""
+        fi = image_features.float().contiguous()
+        w = zeroshot_weights.t().float().contiguous()           # [n_classes, embed_dim]
+        with self._on_device():
+            self._ensure_handle()
+            idx = torch.empty((fi.shape[0], topk), dtype=torch.int32, device=fi.device)
+            logits = torch.empty((fi.shape[0], w.shape[0]), dtype=torch.float32, device=fi.device) if return_logits else None
+            self._check(self._library().msclip_zeroshot_predict(self._handle, C.c_void_p(fi.data_ptr()), fi.shape[0],
+                                                               C.c_void_p(w.data_ptr()), w.shape[0], float(scale), int(topk),
+                                                               C.c_void_p(idx.data_ptr()),
+                                                               C.c_void_p(logits.data_ptr()) if return_logits else None,
+                                                               self._stream()), "msclip_zeroshot_predict")
+        return (idx, logits) if return_logits else idx
+
+    @torch.no_grad()
     def forward(self, image: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
         """CLIP.forward (M.py:3126-3155): logits over the (gathered) batch.  With gather_tensors and an
         initialised process group the features are all-gathered in rank order exactly like

@@ -227,6 +227,40 @@ def test_zero_shot_path_config5_small():
     assert mx <= COS_TOL * 100.0 and bool(agree.all())
 
 
+def test_fused_zeroshot_classifier_and_predict_match_the_tool_formulas():
+    """msclip_zeroshot_classifier (all prompts in one call, sorted by live length, per-class mean +
+    renormalisation in one kernel) against the tool's per-class loop (tools/zero_shot.py:125-131) built from
+    encode_text, and msclip_zeroshot_predict (logits + top-k on the device) against `100 * feats @ W` + torch.topk
+    (tools/zero_shot.py:266, 150-163)."""
+    cfg = MSCLIPConfig(layers=3)
+    sd_np = synth.synth_state_dict(cfg, seed=9)
+    model = build_model(cfg, sd_np)
+    n_cls, n_tpl, n_img = 37, 5, 19                     # 185 prompts with ragged lengths, odd sizes everywhere
+    toks = torch.from_numpy(np.stack([synth.synth_tokens(n_tpl, 300 + c, ragged=True) for c in range(n_cls)])).cuda()
+    ws = []
+    for c in range(n_cls):                              # the tool's loop
+        e = model.encode_text(toks[c]).mean(dim=0)
+        e /= e.norm()
+        ws.append(e)
+    w_loop = torch.stack(ws, dim=1)                     # [512, n_cls], tools/zero_shot.py:132
+    w_fused = model.zeroshot_classifier(toks)
+    assert w_fused.shape == w_loop.shape == (512, n_cls)
+    # identical embeddings (the towers are row-independent, trimming is exact); only the fp32 order of the mean differs
+    assert float((w_fused - w_loop).abs().max()) <= 2e-7
+    w_host = model.zeroshot_classifier(toks.cpu())      # host tokens: same result
+    assert torch.equal(w_host, w_fused)
+    feats = model.encode_image(torch.from_numpy(synth.synth_images(n_img, 5)).cuda())
+    idx, logits = model.zeroshot_predict(feats, w_fused, topk=5, return_logits=True)
+    ref = 100.0 * feats.double() @ w_fused.double()
+    assert float((logits.double() - ref).abs().max()) <= 2e-4           # split-operand tensor-core product: fp32 grade
+    tv, ti = logits.topk(5, dim=1)
+    assert torch.equal(idx.long(), ti) or torch.equal(torch.gather(logits, 1, idx.long()), tv)
+    assert torch.equal(model.zeroshot_predict(feats, w_fused, topk=1)[:, 0].long(), logits.argmax(dim=1))
+    with pytest.raises(Exception):
+        model.zeroshot_predict(feats, w_fused, topk=9)
+    _record("zero_shot_fused", {"classes": n_cls, "templates": n_tpl, "max_abs_w_diff": float((w_fused - w_loop).abs().max())})
+
+
 def test_get_clip_model_accepts_reference_config():
     ns = lambda **k: type("N", (), k)()
     cu = dict(CUSTOM_ATTN=True, SHARE_MODULES=["attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj", "mlp"],

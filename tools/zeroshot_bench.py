@@ -75,14 +75,29 @@ def main():
     torch.cuda.synchronize()
     t_loop_trim = time.perf_counter() - t0
 
+    # fused fast path (msclip_zeroshot_classifier): one library call, sorting / bucketing / class mean inside
+    model.zeroshot_classifier(toks.view(n_cls, n_tpl, -1)[:4])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    w_fused = model.zeroshot_classifier(toks.view(n_cls, n_tpl, -1)).t().contiguous()
+    torch.cuda.synchronize()
+    t_fused = time.perf_counter() - t0
+
     t0 = time.perf_counter()
     feats = model.encode_image(img)
     logits = model.similarity_logits(feats, w_batched, 100.0)
     top1 = logits.argmax(dim=1)
     torch.cuda.synchronize()
     t_img = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    top5 = model.zeroshot_predict(model.encode_image(img), w_fused.t(), topk=5)
+    torch.cuda.synchronize()
+    t_img_fused = time.perf_counter() - t0
     out = {"classifier_loop_s": t_loop, "classifier_batched_s": t_batched, "prompts_per_s_loop": n_cls * n_tpl / t_loop,
            "prompts_per_s_batched": n_cls * n_tpl / t_batched, "image_batch_s": t_img, "images_per_s": n_img / t_img,
+           "classifier_fused_call_s": t_fused, "prompts_per_s_fused_call": n_cls * n_tpl / t_fused,
+           "fused_vs_batched_max_abs_diff": float((w_fused - w_batched).abs().max()),
+           "image_batch_fused_predict_s": t_img_fused, "fused_top1_agrees": float((top5[:, 0].long() == top1).float().mean()),
            "classifier_live_prefix_bucketed_s": t_trim, "prompts_per_s_live_prefix_bucketed": n_cls * n_tpl / t_trim,
            "classifier_loop_live_prefix_s": t_loop_trim, "mean_live_length": float(lens.float().mean()) + 1.0,
            "live_prefix_equals_full_context": bool(torch.equal(w_trim, w_batched)) and bool(torch.equal(w_loop_trim, w_loop)),
