@@ -136,6 +136,12 @@ int msclip_contrastive_loss(msclip_handle h, int b_local, float scale, float* pa
  * (what gather_tensors would be given, M.py:3139-3140); device or host pointers. */
 int msclip_contrastive_loss_features(msclip_handle h, const float* img_feat, const float* txt_feat, int b_local,
                                      float scale, float* partial_out, float* loss_out, void* stream);
+/* Backward of the LAST msclip_contrastive_loss / msclip_forward_loss call of this handle with respect to this rank's
+ * normalised embeddings (first piece): d_img_feat / d_txt_feat [b_local, embed_dim] f32 (host or
+ * device) receive d loss / d image_features and d loss / d text_features of the global symmetric cross-entropy.  Only the
+ * local shard receives a gradient, as with gather_tensors (lib/utils/comm.py:151-152); every rank must call it (the
+ * column-wise softmax needs the peers' row log-sum-exps: a second in-kernel peer read, no collective). */
+int msclip_contrastive_loss_backward(msclip_handle h, float* d_img_feat, float* d_txt_feat, void* stream);
 /* Micro-batching (BASELINE.json: global batch 32 768 on 1 / 2 / 4 GPUs): run both towers
  * for b_micro pairs and keep their normalised embeddings as rows [row_offset, row_offset + b_micro) of this rank's
  * shard of the NEXT msclip_contrastive_loss.  row_offset must be 0 (new shard) or the number of rows encoded so far;

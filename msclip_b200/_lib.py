@@ -11,7 +11,8 @@ from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 # one library per MMA operand type (same sources, -DMSCLIP_FP16 for the second): bf16 is the default
-LIB_PATHS = {"bf16": os.path.join(HERE, "libmsclip_b200.so"), "fp16": os.path.join(HERE, "libmsclip_b200_fp16.so")}
+_SUFFIX = os.environ.get("MSCLIP_LIB_SUFFIX", "")      # experimental build variants (msclip_b200/build.py)
+LIB_PATHS = {"bf16": os.path.join(HERE, f"libmsclip_b200{_SUFFIX}.so"), "fp16": os.path.join(HERE, f"libmsclip_b200_fp16{_SUFFIX}.so")}
 LIB_PATH = LIB_PATHS["bf16"]
 
 
@@ -69,6 +70,7 @@ _SIGNATURES = {
     "msclip_contrastive_loss": (_I, [_P, _I, _F, _P, _P, _P]),
     "msclip_forward_loss": (_I, [_P, _P, _I, _P, _I, _P, _P, _P]),
     "msclip_encode_pairs": (_I, [_P, _P, _I, _P, _I, _I, _P]),
+    "msclip_contrastive_loss_backward": (_I, [_P, _P, _P, _P]),
     "msclip_contrastive_loss_features": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "msclip_launch_count": (_L, [_P]),
     "msclip_device_bytes": (_L, [_P]),

@@ -16,7 +16,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
 # two builds of the same sources: MMA operands in bf16 (default) or IEEE fp16 (-DMSCLIP_FP16)
-LIB_PATHS = {"bf16": os.path.join(HERE, "libmsclip_b200.so"), "fp16": os.path.join(HERE, "libmsclip_b200_fp16.so")}
+# MSCLIP_LIB_SUFFIX: build / load an experimental variant next to the default libraries (A/B runs, e.g. "_tanh")
+SUFFIX = os.environ.get("MSCLIP_LIB_SUFFIX", "")
+LIB_PATHS = {"bf16": os.path.join(HERE, f"libmsclip_b200{SUFFIX}.so"), "fp16": os.path.join(HERE, f"libmsclip_b200_fp16{SUFFIX}.so")}
 LIB_PATH = LIB_PATHS["bf16"]
 SOURCES = ["runtime.cu", "gemm.cu", "conv_gemm.cu", "elementwise.cu", "conv.cu", "front.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu"]
 HEADERS = ["common.cuh", "gemm_common.cuh", "rowops.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
@@ -52,9 +54,11 @@ def build(force: bool = False, verbose: bool = False, precision: str = "bf16") -
     lib_path = LIB_PATHS[precision]
     if not force and not needs_build(precision):
         return lib_path
-    obj_dir = os.path.join(OBJ_DIR, precision)
+    obj_dir = os.path.join(OBJ_DIR, precision + SUFFIX)
     os.makedirs(obj_dir, exist_ok=True)
     flags = NVCC_FLAGS + (["-DMSCLIP_FP16"] if precision == "fp16" else [])
+    if os.environ.get("MSCLIP_QGELU_TANH") == "1":      # A/B build: one-MUFU QuickGELU in the fc1 epilogue
+        flags = flags + ["-DMSCLIP_QGELU_TANH"]
     nvcc = _nvcc()
     newest_header = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
 

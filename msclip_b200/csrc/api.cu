@@ -194,6 +194,11 @@ int msclip_contrastive_loss_features(msclip_handle h, const float* img_feat, con
   return engine_contrastive_loss_features(h, img_feat, txt_feat, b_local, scale, partial_out, loss_out, as_stream(stream));
 }
 
+int msclip_contrastive_loss_backward(msclip_handle h, float* d_img_feat, float* d_txt_feat, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr, "null handle");
+  return engine_contrastive_loss_backward(h, d_img_feat, d_txt_feat, as_stream(stream));
+}
+
 int msclip_encode_pairs(msclip_handle h, const void* image, int image_dtype, const int64_t* tokens, int b_micro,
                         int row_offset, void* stream) {
   MSCLIP_REQUIRE(h != nullptr, "null handle");
@@ -306,7 +311,7 @@ int msclip_op_contrastive_lse(const void* img_f16, const void* txt_f16, int b, f
   MSCLIP_CHECK_CUDA(cudaMemcpyAsync(tab, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice, as_stream(stream)));
   return launch_contrastive_loss_ex(static_cast<const emb16*>(img_f16), static_cast<const emb16*>(txt_f16),
                                     reinterpret_cast<const emb16* const*>(tab), reinterpret_cast<const emb16* const*>(tab + 1),
-                                    nullptr, 0, 1, 0, b, 512, scale, workspace, parts2, as_stream(stream));
+                                    nullptr, 0, 1, 0, b, 512, scale, workspace, parts2, nullptr, 0, as_stream(stream));
 }
 size_t msclip_op_contrastive_lse_workspace(int b) { return ((contrastive_loss_workspace_bytes(1, b) + 15) & ~size_t(15)) + 64; }
 

@@ -491,14 +491,28 @@ static emb16* xchg_slot(const msclip_ctx* h, void* base, int parity, int modalit
 static uint32_t* xchg_flags(const msclip_ctx* h, void* base) {
   return reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(base) + 4 * xchg_feat_bytes(h));
 }
+// second flag array (backward pass: "my row lse of this epoch are written") and the lse themselves:
+// [2 parity][2 direction][lse_pitch] floats, log2 domain
+static uint32_t* xchg_flags2(const msclip_ctx* h, void* base) { return xchg_flags(h, base) + kMaxWorld; }
+static int xchg_lse_pitch(const msclip_ctx* h) { return (h->max_b_local + 127) / 128 * 128; }
+static float* xchg_lse(const msclip_ctx* h, void* base, int parity, int dir) {
+  return reinterpret_cast<float*>(xchg_flags2(h, base) + kMaxWorld) + (parity * 2 + dir) * xchg_lse_pitch(h);
+}
 
 static int upload_tables(msclip_ctx* h) {
   const int W = h->world;
-  std::vector<void*> t(static_cast<size_t>(4) * W + W);
+  // [4 W] feature shards, [W] flag arrays, [W] second flag arrays, [4 W] lse arrays ([parity][direction][rank])
+  std::vector<void*> t(static_cast<size_t>(10) * W);
   for (int par = 0; par < 2; ++par)
     for (int mod = 0; mod < 2; ++mod)
-      for (int r = 0; r < W; ++r) t[(par * 2 + mod) * W + r] = xchg_slot(h, h->peer_base[r], par, mod);
-  for (int r = 0; r < W; ++r) t[4 * W + r] = xchg_flags(h, h->peer_base[r]);
+      for (int r = 0; r < W; ++r) {
+        t[(par * 2 + mod) * W + r] = xchg_slot(h, h->peer_base[r], par, mod);
+        t[6 * W + (par * 2 + mod) * W + r] = xchg_lse(h, h->peer_base[r], par, mod);
+      }
+  for (int r = 0; r < W; ++r) {
+    t[4 * W + r] = xchg_flags(h, h->peer_base[r]);
+    t[5 * W + r] = xchg_flags2(h, h->peer_base[r]);
+  }
   if (h->shard_tables) cudaFree(h->shard_tables);
   MSCLIP_CHECK_CUDA(cudaMalloc(&h->shard_tables, t.size() * sizeof(void*)));
   MSCLIP_CHECK_CUDA(cudaMemcpy(h->shard_tables, t.data(), t.size() * sizeof(void*), cudaMemcpyHostToDevice));
@@ -521,13 +535,14 @@ int comm_init(msclip_ctx* h, int rank, int world, int max_b_local) {
   h->rank = rank;
   h->world = world;
   h->max_b_local = max_b_local;
-  h->xchg_bytes = 4 * xchg_feat_bytes(h) + 256;
+  h->xchg_bytes = 4 * xchg_feat_bytes(h) + 2 * kMaxWorld * sizeof(uint32_t) + 4 * static_cast<size_t>(xchg_lse_pitch(h)) * sizeof(float);
   MSCLIP_CHECK_CUDA(cudaMalloc(&h->xchg, h->xchg_bytes));
   MSCLIP_CHECK_CUDA(cudaMemset(h->xchg, 0, h->xchg_bytes));
   h->peer_base.assign(world, nullptr);
   h->peer_base[rank] = h->xchg;
   h->epoch = 0;
   h->img_rows = h->txt_rows = 0;
+  h->loss_b = 0;
   if (world == 1) MSCLIP_TRY(upload_tables(h));
   return 0;
 }
@@ -1325,7 +1340,10 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
   MSCLIP_TRY(ws_get(h, "loss_ws", contrastive_loss_workspace_bytes(W, b_local), &wsp));
   WS(parts, float, "loss_parts", 4);
   MSCLIP_TRY(launch_contrastive_loss_ex(xchg_slot(h, h->xchg, par, 0), xchg_slot(h, h->xchg, par, 1), img_tab, txt_tab,
-                                        flags, h->epoch, W, h->rank, b_local, E, scale, wsp, parts, s));
+                                        flags, h->epoch, W, h->rank, b_local, E, scale, wsp, parts,
+                                        xchg_lse(h, h->xchg, par, 0), xchg_lse_pitch(h), s));
+  h->loss_b = b_local;  // msclip_contrastive_loss_backward may follow: features and row lse of this epoch stay in place
+  h->loss_scale = scale;
   count_launch(3);
   if (loss_out && W == 1) {
     finish_loss_kernel<<<1, 1, 0, s>>>(parts, 1.0f / (2.0f * b_local), parts + 2);
@@ -1345,6 +1363,55 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
   }
   if (need_sync) MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
   h->img_rows = h->txt_rows = 0;
+  return 0;
+}
+
+__global__ void publish2_kernel(uint32_t* const* flag_tables, int world, int rank, uint32_t epoch) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_tables[r] + rank), "r"(epoch) : "memory");
+  }
+}
+
+// d loss / d (normalised local embeddings) of the LAST msclip_contrastive_loss call (same epoch: its features and row lse
+// are still in the exchange buffer).  Every rank must call it (the column softmax needs the peers' row lse - the second
+// peer read of the step); the gradient reaches only the local shard (lib/utils/comm.py:151-152).
+int engine_contrastive_loss_backward(msclip_ctx* h, float* d_img, float* d_txt, cudaStream_t s) {
+  MSCLIP_TRY(require_ready(h));
+  MSCLIP_REQUIRE(d_img && d_txt, "contrastive_loss_backward: null output");
+  MSCLIP_REQUIRE(h->xchg != nullptr && h->loss_b > 0, "contrastive_loss_backward: no preceding msclip_contrastive_loss");
+  const int W = h->world, B = h->loss_b, E = h->cfg.embed_dim;
+  const int par = static_cast<int>(h->epoch & 1);
+  void** tables = static_cast<void**>(h->shard_tables);
+  const emb16* const* img_tab = reinterpret_cast<const emb16* const*>(tables + (par * 2 + 0) * W);
+  const emb16* const* txt_tab = reinterpret_cast<const emb16* const*>(tables + (par * 2 + 1) * W);
+  const float* const* img_lse = reinterpret_cast<const float* const*>(tables + 6 * W + (par * 2 + 0) * W);
+  const float* const* txt_lse = reinterpret_cast<const float* const*>(tables + 6 * W + (par * 2 + 1) * W);
+  if (W > 1) {
+    // the lse of this epoch were written by the forward's kernels earlier on this stream: publish, then wait for the peers
+    publish2_kernel<<<1, kMaxWorld, 0, s>>>(reinterpret_cast<uint32_t* const*>(tables + 5 * W), W, h->rank, h->epoch);
+    MSCLIP_CHECK_CUDA(cudaGetLastError());
+    count_launch(1);
+    uint32_t* f2 = xchg_flags2(h, h->xchg);
+    for (int r = 0; r < W; ++r)
+      if (r != h->rank) MSCLIP_REQUIRE(stream_wait_value_geq(s, f2 + r, h->epoch) == 0,
+                                       "contrastive_loss_backward: stream memory operations are unavailable");
+  }
+  void* wsp = nullptr;
+  MSCLIP_TRY(ws_get(h, "loss_bwd_ws", contrastive_backward_workspace_bytes(W, B), &wsp));
+  const bool dev_i = is_device_pointer(d_img), dev_t = is_device_pointer(d_txt);
+  float* gi = d_img;
+  float* gt = d_txt;
+  if (!dev_i) MSCLIP_TRY(ws_get(h, "loss_bwd_gi", static_cast<size_t>(B) * E * 4, reinterpret_cast<void**>(&gi)));
+  if (!dev_t) MSCLIP_TRY(ws_get(h, "loss_bwd_gt", static_cast<size_t>(B) * E * 4, reinterpret_cast<void**>(&gt)));
+  MSCLIP_TRY(launch_contrastive_loss_backward(xchg_slot(h, h->xchg, par, 0), xchg_slot(h, h->xchg, par, 1), img_tab, txt_tab,
+                                              xchg_lse(h, h->xchg, par, 0), xchg_lse_pitch(h), img_lse, txt_lse, W, h->rank, B,
+                                              h->loss_scale, wsp, gi, gt, s));
+  count_launch(7);
+  if (!dev_i) MSCLIP_CHECK_CUDA(cudaMemcpyAsync(d_img, gi, static_cast<size_t>(B) * E * 4, cudaMemcpyDeviceToHost, s));
+  if (!dev_t) MSCLIP_CHECK_CUDA(cudaMemcpyAsync(d_txt, gt, static_cast<size_t>(B) * E * 4, cudaMemcpyDeviceToHost, s));
+  if (!dev_i || !dev_t) MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

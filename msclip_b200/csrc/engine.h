@@ -93,7 +93,7 @@ struct msclip_ctx {
 
   // embedding exchange (data-parallel contrastive loss)
   int rank = 0, world = 1, max_b_local = 0;
-  void* xchg = nullptr;  // [2 parity][2 modality][max_b_local, E] op16, then uint32 flags[world]
+  void* xchg = nullptr;  // [2 parity][2 modality][max_b_local, E] fp16, flags[64], flags2[64], lse [2 parity][2 dir][pitch] f32
   size_t xchg_bytes = 0;
   std::vector<void*> peer_base;    // imported peer bases (own base at [rank])
   bool peers_borrowed = false;     // peer bases are same-process device pointers (not IPC mappings to close)
@@ -103,6 +103,8 @@ struct msclip_ctx {
   // rows of this rank's shard (exchange slot of the NEXT loss) filled so far by encode_image / encode_text: one call
   // with the whole local batch, or several micro-batches appended back to back (msclip_encode_pairs)
   int img_rows = 0, txt_rows = 0;
+  int loss_b = 0;          // local batch of the last contrastive loss (0 = none): what msclip_contrastive_loss_backward uses
+  float loss_scale = 0.f;
 
   ~msclip_ctx();
 };
@@ -128,6 +130,7 @@ int engine_contrastive_loss(msclip_ctx* h, int b_local, float scale, float* part
                             cudaStream_t stream);
 int engine_contrastive_loss_features(msclip_ctx* h, const float* img_feat, const float* txt_feat, int b_local, float scale,
                                      float* partial_out, float* loss_out, cudaStream_t stream);
+int engine_contrastive_loss_backward(msclip_ctx* h, float* d_img, float* d_txt, cudaStream_t stream);
 int engine_encode_pairs(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_micro, int row_offset,
                         cudaStream_t stream);
 int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,

@@ -178,8 +178,18 @@ int launch_attention(const op16* qkv, op16* out, int batch, int L, int heads, in
 int launch_contrastive_loss_ex(const emb16* img_local, const emb16* txt_local, const emb16* const* img_shards,
                                const emb16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
                                int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
-                               cudaStream_t stream);
+                               float* lse_out, int lse_pitch, cudaStream_t stream);
 size_t contrastive_loss_workspace_bytes(int world, int b_local);
+// Backward of that loss with respect to this rank's normalised embeddings (only the local shard receives a gradient,
+// like gather_tensors, comm.py:151-152).  row_lse: the [2][lse_pitch] log2-domain lse the forward wrote (lse_out);
+// img_lse_shards / txt_lse_shards: device tables of `world` pointers to every rank's image-row / text-row lse (peer
+// pointers allowed).  d_img / d_txt: [b_local, 512] f32.
+int launch_contrastive_loss_backward(const emb16* img_local, const emb16* txt_local, const emb16* const* img_shards,
+                                     const emb16* const* txt_shards, const float* row_lse, int lse_pitch,
+                                     const float* const* img_lse_shards, const float* const* txt_lse_shards, int world,
+                                     int rank, int b_local, float scale, void* workspace, float* d_img, float* d_txt,
+                                     cudaStream_t stream);
+size_t contrastive_backward_workspace_bytes(int world, int b_local);
 // ---- weight packing (pack.cu) -------------------------------------------------------------------
 // dst[n, k] (op16, pitch ldd) = src[n*sn + k*sk] * (row_scale ? row_scale[n] : 1)
 int launch_pack_op16(const float* src, int64_t sn, int64_t sk, const float* row_scale, op16* dst, int64_t ldd, int N,

@@ -11,6 +11,8 @@
 // (L2-resident) through tcgen05.mma into double-buffered TMEM accumulators.  The epilogue warps turn
 // each 128x128 score tile into per-row (max, sum-exp) partials in registers; a second tiny kernel merges
 // the partials across column tiles, subtracts the diagonal and reduces deterministically.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -37,6 +39,12 @@ struct LossParams {
   float scale_log2;                  // exp(logit_scale) * log2(e): scores are kept in the log2 domain
   float2* ws;                        // [2][n_col_tiles][b_pad] (max, sum) partials, log2 domain
   float* diag;                       // [2][b_pad] the diagonal scores s_ii taken from the same accumulators
+  // MODE 1 (backward): instead of the partials the epilogue writes w_ij = exp(s_ij - lse_row_i) + exp(s_ij - lse_col_j)
+  const float* row_lse;              // [2][b_pad] log2-domain lse of this rank's rows (image rows | text rows)
+  const float* const* col_lse[2];    // [dir] -> device table of `world` pointers: the column owners' row lse of the OTHER direction
+  op16* wout[2];                     // [dir] -> [b_local][ldw] probabilities, column = owner * b_local + local column
+  long long ldw;
+  int lse_pitch;                     // floats between the two directions of row_lse
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -45,6 +53,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kLossThreads, 1)
 contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const __grid_constant__ CUtensorMap tmap_rows_txt,
                        const LossParams p) {
@@ -172,6 +181,46 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
       mbar_wait(&tfull_bar[as], aph, 14);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kLossBN;
+      if (MODE == 1) {
+        // backward: softmax probabilities of both directions for this 128 x 128 tile of (local rows) x (gathered columns)
+        const int row = rb * 128 + q * 32 + lane;
+        const float lse_r = row < p.b_local ? p.row_lse[dir * p.lse_pitch + row] : 0.f;
+        const float* lse_c = p.col_lse[dir][owner] + c0;
+        op16* wrow = p.wout[dir] + static_cast<long long>(row) * p.ldw + static_cast<long long>(owner) * p.b_local + c0;
+        // the positive pair of a row: its "- 2 x_i" term is folded into the matrix in fp32 (w_ii - 2 is small when the
+        // softmax is peaked; rounding w_ii ~ 2 to 16 bits first would swamp the gradient)
+        const int diag_col = (owner == p.rank) ? row - c0 : -1;
+#pragma unroll 1
+        for (int c = 0; c < kLossBN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (row < p.b_local) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const int col = c * 32 + j;
+              float w0 = 0.f, w1 = 0.f;
+              if (col < valid_cols) {
+                const float v = __uint_as_float(r[j]) * p.scale_log2;
+                w0 = exp2f(v - lse_r) + exp2f(v - __ldg(lse_c + col));
+                if (col == diag_col) w0 = (exp2f(v - lse_r) - 1.0f) + (exp2f(v - __ldg(lse_c + col)) - 1.0f);
+              }
+              if (col + 1 < valid_cols) {
+                const float v = __uint_as_float(r[j + 1]) * p.scale_log2;
+                w1 = exp2f(v - lse_r) + exp2f(v - __ldg(lse_c + col + 1));
+                if (col + 1 == diag_col) w1 = (exp2f(v - lse_r) - 1.0f) + (exp2f(v - __ldg(lse_c + col + 1)) - 1.0f);
+              }
+              // element-wise stores: b_local (hence the column offset of a shard) need not be even
+              if (col < valid_cols) wrow[col] = to_op16(w0);
+              if (col + 1 < valid_cols) wrow[col + 1] = to_op16(w1);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
       float m = -INFINITY, l = 0.f;
       // the tile that holds the positives of these rows: row i of the block meets column i of the tile.
       // Taking s_ii from the very accumulator that also enters the log-sum-exp keeps lse_i - s_ii free of
@@ -223,7 +272,7 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
 // per local row and direction: merge the column-tile partials, subtract the diagonal score
 __global__ void __launch_bounds__(256)
 lse_combine_kernel(const float2* __restrict__ ws, const float* __restrict__ diag, int b_local, int b_pad,
-                   int n_col_tiles, float* __restrict__ row_loss) {
+                   int n_col_tiles, float* __restrict__ row_loss, float* __restrict__ lse_out, int lse_pitch) {
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= 2 * b_local) return;
   const int dir = idx / b_local, row = idx % b_local;
@@ -237,6 +286,34 @@ lse_combine_kernel(const float2* __restrict__ ws, const float* __restrict__ diag
   }
   // scores are in log2 units (scale * log2 e folded in): lse_i - s_ii = ln2 * ((m - d) + log2 l)
   row_loss[idx] = kLn2 * ((m - diag[dir * b_pad + row]) + log2f(l));
+  if (lse_out != nullptr) lse_out[dir * lse_pitch + row] = m + log2f(l);  // log2 domain; the backward pass reads it
+}
+
+// out[k][owner * b_local + r] = op16(shards[owner][r][k]): the gathered embeddings, transposed, as the K-major B operand
+// of the gradient GEMM (K = global batch); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+gather_transpose_kernel(const emb16* const* __restrict__ shards, int world, int b_local, int E, op16* __restrict__ out,
+                        long long ld) {
+  __shared__ float tile[32][33];
+  const int owner = blockIdx.z;
+  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const emb16* src = shards[owner];
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i;
+    tile[i][tx] = (r < b_local && k0 + tx < E) ? __half2float(src[static_cast<long long>(r) * E + k0 + tx]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, r = r0 + tx;
+    if (k < E && r < b_local) out[static_cast<long long>(k) * ld + static_cast<long long>(owner) * b_local + r] = to_op16(tile[tx][i]);
+  }
+}
+
+// grad = coef * raw: d loss / d (normalised embedding), see launch_contrastive_loss_backward
+__global__ void __launch_bounds__(256)
+loss_grad_finish_kernel(const float* __restrict__ raw, float coef, float* __restrict__ grad, long long total) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) grad[i] = coef * raw[i];
 }
 
 // deterministic reduction: out[dir] = sum_row row_loss[dir][row]
@@ -265,19 +342,24 @@ size_t contrastive_loss_workspace_bytes(int world, int b_local) {
          2 * static_cast<size_t>(b_local) * sizeof(float);
 }
 
+static int configure_loss_kernels() {
+  static bool configured = false;
+  if (!configured) {
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(contrastive_lse_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
+    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(contrastive_lse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLossSmem));
+    configured = true;
+  }
+  return 0;
+}
+
 int launch_contrastive_loss_ex(const emb16* img_local, const emb16* txt_local, const emb16* const* img_shards,
                                const emb16* const* txt_shards, const uint32_t* flags, uint32_t epoch, int world,
                                int rank, int b_local, int E, float scale, void* workspace, float* loss_parts,
-                               cudaStream_t stream) {
+                               float* lse_out, int lse_pitch, cudaStream_t stream) {
   MSCLIP_REQUIRE(E == kLossE, "contrastive loss: embedding width must be 512");
   MSCLIP_REQUIRE(world >= 1 && b_local >= 1, "contrastive loss: empty problem");
-  static bool configured = false;
-  if (!configured) {
-    MSCLIP_CHECK_CUDA(cudaFuncSetAttribute(contrastive_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kLossSmem));
-    configured = true;
-  }
-  LossParams p;
+  MSCLIP_TRY(configure_loss_kernels());
+  LossParams p = {};
   p.col_shards[0] = txt_shards;  // image rows see text columns
   p.col_shards[1] = img_shards;  // text rows see image columns
   p.flags = world > 1 ? flags : nullptr;
@@ -296,12 +378,83 @@ int launch_contrastive_loss_ex(const emb16* img_local, const emb16* txt_local, c
   CUtensorMap ti, tt;
   MSCLIP_TRY(make_tmap_op16_2d(&ti, img_local, b_local, kLossE, kLossE, 128));
   MSCLIP_TRY(make_tmap_op16_2d(&tt, txt_local, b_local, kLossE, kLossE, 128));
-  contrastive_lse_kernel<<<dim3(p.n_col_tiles, 2), kLossThreads, kLossSmem, stream>>>(ti, tt, p);
+  contrastive_lse_kernel<0><<<dim3(p.n_col_tiles, 2), kLossThreads, kLossSmem, stream>>>(ti, tt, p);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   lse_combine_kernel<<<(2 * b_local + 255) / 256, 256, 0, stream>>>(p.ws, p.diag, b_local, p.b_pad, p.n_col_tiles,
-                                                                    row_loss);
+                                                                    row_loss, lse_out, lse_pitch);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   loss_reduce_kernel<<<2, 1024, 0, stream>>>(row_loss, b_local, loss_parts);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- backward of the contrastive loss with respect to this rank's (normalised) embeddings --------------------------------
+// loss = (1 / 2G) sum_i [lse_j s_ij - s_ii] + (1 / 2G) sum_j [lse_i s_ij - s_jj], s = scale * I . T^T.  With
+// w_ij = softmax_j(s_i.)_j + softmax_i(s_.j)_i - 2 [i == j]:   dL/dI_i = scale / 2G * sum_j w_ij T_j   (i local, j global)
+//                                                              dL/dT_j = scale / 2G * sum_i w_ij I_i   (j local, i global)
+// - the gradient reaches only the local shard, exactly as with gather_tensors (lib/utils/comm.py:151-152).  The column
+// softmax needs the row lse of the columns' owners: a second peer read (col_lse tables).  Three steps: (1) the forward
+// kernel re-run in MODE 1 writes w for (local rows) x (all columns) in both directions, (2) the gathered embeddings are
+// transposed into K-major operands, (3) two tcgen05 GEMMs over K = G and a scaling pass.
+// Workspace: contrastive_backward_workspace_bytes(world, b_local).
+static long long padded_g(int world, int b_local) { return (static_cast<long long>(world) * b_local + 63) / 64 * 64; }
+
+size_t contrastive_backward_workspace_bytes(int world, int b_local) {
+  const long long ldg = padded_g(world, b_local);
+  return static_cast<size_t>(2 * (static_cast<long long>(b_local) + kLossE) * ldg * 2 + 2ll * b_local * kLossE * 4 + 256);
+}
+
+int launch_contrastive_loss_backward(const emb16* img_local, const emb16* txt_local, const emb16* const* img_shards,
+                                     const emb16* const* txt_shards, const float* row_lse, int lse_pitch,
+                                     const float* const* img_lse_shards, const float* const* txt_lse_shards, int world,
+                                     int rank, int b_local, float scale, void* workspace, float* d_img, float* d_txt,
+                                     cudaStream_t stream) {
+  MSCLIP_REQUIRE(world >= 1 && b_local >= 1 && d_img && d_txt, "contrastive loss backward: bad arguments");
+  MSCLIP_REQUIRE(lse_pitch >= b_local, "contrastive loss backward: lse pitch smaller than the local batch");
+  MSCLIP_TRY(configure_loss_kernels());
+  const long long G = static_cast<long long>(world) * b_local, ldg = padded_g(world, b_local);
+  uint8_t* w8 = static_cast<uint8_t*>(workspace);
+  op16* wprob[2] = {reinterpret_cast<op16*>(w8), reinterpret_cast<op16*>(w8) + static_cast<long long>(b_local) * ldg};
+  op16* xt[2] = {wprob[1] + static_cast<long long>(b_local) * ldg, wprob[1] + static_cast<long long>(b_local) * ldg + kLossE * ldg};
+  float* raw = reinterpret_cast<float*>(xt[1] + kLossE * ldg);
+  // zero padding columns (K of the GEMMs is ldg): clear the operands once per call
+  MSCLIP_CHECK_CUDA(cudaMemsetAsync(w8, 0, static_cast<size_t>(2 * (static_cast<long long>(b_local) + kLossE) * ldg * 2), stream));
+  LossParams p = {};
+  p.col_shards[0] = txt_shards;
+  p.col_shards[1] = img_shards;
+  p.world = world;
+  p.rank = rank;
+  p.b_local = b_local;
+  p.tiles_per_shard = (b_local + kLossBN - 1) / kLossBN;
+  p.n_col_tiles = world * p.tiles_per_shard;
+  p.n_row_blocks = (b_local + 127) / 128;
+  p.b_pad = pad128(b_local);
+  p.scale_log2 = scale * kLog2e;
+  p.row_lse = row_lse;
+  p.lse_pitch = lse_pitch;
+  p.col_lse[0] = txt_lse_shards;  // image rows x text columns: the columns' lse is the text rows' lse of their owner
+  p.col_lse[1] = img_lse_shards;
+  p.wout[0] = wprob[0];
+  p.wout[1] = wprob[1];
+  p.ldw = ldg;
+  CUtensorMap ti, tt;
+  MSCLIP_TRY(make_tmap_op16_2d(&ti, img_local, b_local, kLossE, kLossE, 128));
+  MSCLIP_TRY(make_tmap_op16_2d(&tt, txt_local, b_local, kLossE, kLossE, 128));
+  contrastive_lse_kernel<1><<<dim3(p.n_col_tiles, 2), kLossThreads, kLossSmem, stream>>>(ti, tt, p);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  const dim3 tg((b_local + 31) / 32, kLossE / 32, world);
+  gather_transpose_kernel<<<tg, 256, 0, stream>>>(txt_shards, world, b_local, kLossE, xt[0], ldg);
+  gather_transpose_kernel<<<tg, 256, 0, stream>>>(img_shards, world, b_local, kLossE, xt[1], ldg);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  // raw_img = w[0] . T_all, raw_txt = w[1] . I_all   (K = padded global batch)
+  MSCLIP_TRY(launch_gemm(wprob[0], ldg, xt[0], ldg, b_local, kLossE, static_cast<int>(ldg), nullptr, raw, kLossE, nullptr, 0, EPI_F32, stream));
+  MSCLIP_TRY(launch_gemm(wprob[1], ldg, xt[1], ldg, b_local, kLossE, static_cast<int>(ldg), nullptr, raw + static_cast<long long>(b_local) * kLossE,
+                         kLossE, nullptr, 0, EPI_F32, stream));
+  const float coef = scale / (2.0f * static_cast<float>(G));
+  const long long total = static_cast<long long>(b_local) * kLossE;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  loss_grad_finish_kernel<<<grid, 256, 0, stream>>>(raw, coef, d_img, total);
+  loss_grad_finish_kernel<<<grid, 256, 0, stream>>>(raw + total, coef, d_txt, total);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

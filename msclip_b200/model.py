@@ -99,6 +99,7 @@ class CLIP(nn.Module):
         self._comm = None           # (rank, world, max_b_local) once the peer exchange is set up
         self._comm_mode = "p2p"     # "p2p": in-kernel NVLink gather; "gather": gather_tensors fallback (multi-node)
         self._checked_b = set()     # local batch sizes already verified to be equal on every rank
+        self._last_loss_b = 0       # local batch of the last loss call (contrastive_loss_backward)
 
     # ---- reference attributes -----------------------------------------------------------------------
     @property
@@ -348,6 +349,7 @@ class CLIP(nn.Module):
         """Symmetric cross-entropy over the rows retained by ``encode_pairs`` (b_local per rank)."""
         world = self._comm[1] if self._comm else 1
         self._require_equal_shards(b_local)
+        self._last_loss_b = int(b_local)
         with self._on_device():
             parts = torch.empty(2, dtype=torch.float32, device=self.device)
             loss = torch.empty((), dtype=torch.float32, device=self.device)
@@ -387,6 +389,7 @@ class CLIP(nn.Module):
             image = image.float()
         image, text = image.contiguous(), text.to(torch.long).contiguous()
         self._require_equal_shards(b)
+        self._last_loss_b = int(b)
         with self._on_device():
             self._sync_weights()
             dev = self.device
@@ -401,6 +404,20 @@ class CLIP(nn.Module):
         if reduce:
             torch.distributed.all_reduce(parts, group=getattr(self, "_group", None))
         return parts.sum() / (2.0 * world * b)
+
+    @torch.no_grad()
+    def contrastive_loss_backward(self):
+        """(d loss / d image_features, d loss / d text_features) [b_local, embed_dim] of the last ``contrastive_loss`` /
+        ``loss_of_encoded`` call - the first piece of the training backward.  Every rank must
+        call it; like ``gather_tensors`` (lib/utils/comm.py:151-152) the gradient reaches only the local shard."""
+        with self._on_device():
+            b = self._last_loss_b
+            gi = torch.empty((b, self.cfg.embed_dim), dtype=torch.float32, device=self.device)
+            gt = torch.empty_like(gi)
+            self._check(self._library().msclip_contrastive_loss_backward(self._handle, C.c_void_p(gi.data_ptr()),
+                                                                        C.c_void_p(gt.data_ptr()), self._stream()),
+                        "msclip_contrastive_loss_backward")
+        return gi, gt
 
     def launch_count(self) -> int:
         return int(self._library().msclip_launch_count(self._handle)) if self._handle else 0

@@ -45,6 +45,8 @@ def main():
     for it in range(3):                               # several epochs: exercises the double-buffered exchange
         loss = float(model.contrastive_loss(img, tok))
         out[f"fused_p2p_{it}"] = loss
+    # backward of the last step: this rank's gradient rows (second peer read inside the kernels)
+    gi, gt = model.contrastive_loss_backward()
     # micro-batched shard (msclip_encode_pairs x n + one loss): bit-identical to the one-shot call
     out["fused_p2p_micro"] = float(model.contrastive_loss(img, tok, micro_batch=max(8, b_local // 3)))
     # (b) NCCL comparator with the same per-rank features
@@ -63,6 +65,20 @@ def main():
         img_all = torch.from_numpy(synth.synth_images(G, 21)).to(dev)
         tok_all = torch.from_numpy(synth.synth_tokens(G, 21, ragged=True)).to(dev)
         out["single_process"] = float(solo.contrastive_loss(img_all, tok_all))
+        gi_all, gt_all = solo.contrastive_loss_backward()
+        grads = [torch.empty(world, b_local, 512, device=dev) for _ in range(2)]
+    else:
+        gi_all = gt_all = grads = None
+    # gather every rank's gradient shard on rank 0 and compare with the single-process gradient
+    parts_i = [torch.empty_like(gi) for _ in range(world)] if rank == 0 else None
+    parts_t = [torch.empty_like(gt) for _ in range(world)] if rank == 0 else None
+    dist.gather(gi, parts_i, dst=0)
+    dist.gather(gt, parts_t, dst=0)
+    if rank == 0:
+        di = torch.cat(parts_i) - gi_all
+        dt = torch.cat(parts_t) - gt_all
+        out["grad_image_rel"] = float(di.norm() / gi_all.norm())
+        out["grad_text_rel"] = float(dt.norm() / gt_all.norm())
     dist.barrier()
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(out), flush=True)

@@ -394,6 +394,7 @@ def test_two_ranks_on_one_gpu_run_the_p2p_protocol():
     tok = torch.from_numpy(synth.synth_tokens(2 * b, 31, ragged=True)).cuda()
     solo = build_model(cfg, sd_np)
     truth = float(solo.contrastive_loss(img, tok))
+    gi_solo, gt_solo = solo.contrastive_loss_backward()
     L = _lib.lib("bf16")
     ranks = [build_model(cfg, sd_np) for _ in range(2)]
     bases = (C.c_void_p * 2)()
@@ -418,3 +419,47 @@ def test_two_ranks_on_one_gpu_run_the_p2p_protocol():
         torch.cuda.synchronize()
         got = float(parts.sum()) / (2.0 * 2 * b)
         assert abs(got - truth) <= 2e-6 * abs(truth), (epoch, got, truth)
+        # backward of the same step: each rank gets the gradient rows of ITS shard (second peer read: the peers' row lse)
+        grads = [(torch.empty(b, 512, device="cuda"), torch.empty(b, 512, device="cuda")) for _ in range(2)]
+        for r, m in enumerate(ranks):
+            sp = C.c_void_p(streams[r].cuda_stream)
+            _lib.check(L.msclip_contrastive_loss_backward(m._handle, C.c_void_p(grads[r][0].data_ptr()),
+                                                          C.c_void_p(grads[r][1].data_ptr()), sp), "loss_backward")
+        torch.cuda.synchronize()
+        gi = torch.cat([grads[0][0], grads[1][0]])
+        gt = torch.cat([grads[0][1], grads[1][1]])
+        assert rel_err(gi.cpu().numpy(), gi_solo.cpu().numpy()) <= 1e-5 and rel_err(gt.cpu().numpy(), gt_solo.cpu().numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("b,scale", [(40, 1 / 0.07), (300, 100.0), (129, math.e)])
+def test_contrastive_loss_backward_matches_autograd(b, scale, precision):
+    """SURVEY.md 8f-1, first piece: d loss / d (normalised embeddings) from msclip_contrastive_loss_backward against
+    torch.autograd (float64) on the symmetric cross-entropy of the same fp16-rounded embeddings.  The probabilities
+    and the transposed embeddings enter the gradient GEMM as 16-bit operands: <= 1e-2 (bf16) / 2e-3 (fp16) relative."""
+    import ctypes as C
+    from msclip_b200 import _lib
+    cfg = MSCLIPConfig(layers=2)
+    model = build_model(cfg, synth.synth_state_dict(cfg, seed=3), precision)
+    model._sync_weights()
+    g = torch.Generator(device="cuda").manual_seed(b)
+    fi = torch.nn.functional.normalize(torch.randn(b, 512, device="cuda", generator=g), dim=-1)
+    ft = torch.nn.functional.normalize(fi * 0.6 + 0.1 * torch.randn(b, 512, device="cuda", generator=g), dim=-1)
+    L = _lib.lib(precision)
+    parts, loss = torch.zeros(2, device="cuda"), torch.zeros((), device="cuda")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.msclip_contrastive_loss_features(model._handle, C.c_void_p(fi.data_ptr()), C.c_void_p(ft.data_ptr()), b, scale,
+                                                  C.c_void_p(parts.data_ptr()), C.c_void_p(loss.data_ptr()), sp), "loss", precision)
+    model._last_loss_b = b
+    gi, gt = model.contrastive_loss_backward()
+    a = fi.half().double().requires_grad_(True)
+    t = ft.half().double().requires_grad_(True)
+    logits = scale * a @ t.t()
+    tgt = torch.arange(b, device="cuda")
+    ref = 0.5 * (torch.nn.functional.cross_entropy(logits, tgt) + torch.nn.functional.cross_entropy(logits.t(), tgt))
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-6
+    ei, et = rel_err(gi.cpu().numpy(), a.grad.float().cpu().numpy()), rel_err(gt.cpu().numpy(), t.grad.float().cpu().numpy())
+    _record(f"loss_backward/{precision}/b{b}", {"d_image_features": ei, "d_text_features": et})
+    tol = 1e-2 if precision == "bf16" else 2e-3
+    assert ei <= tol and et <= tol, (ei, et)

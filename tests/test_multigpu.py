@@ -41,5 +41,6 @@ def test_fused_p2p_loss_equals_single_process_and_nccl(b_local):
         # identical bf16 embeddings and identical tile arithmetic: only the reduction tree over ranks differs
         assert abs(out[f"fused_p2p_{it}"] - ref) <= 2e-6 * abs(ref), out
     assert out["fused_p2p_0"] == out["fused_p2p_1"] == out["fused_p2p_2"] == out["fused_p2p_micro"]
+    assert out["grad_image_rel"] <= 1e-5 and out["grad_text_rel"] <= 1e-5, out   # sharded backward = single-process backward
     assert abs(out["nccl_gather_fp64"] - ref) <= 1e-3 * abs(ref), out      # fp32 vs bf16-rounded embeddings
     assert abs(out["forward_logits_loss"] - ref) <= 1e-3 * abs(ref), out
