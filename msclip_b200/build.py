@@ -57,8 +57,8 @@ def build(force: bool = False, verbose: bool = False, precision: str = "bf16") -
     obj_dir = os.path.join(OBJ_DIR, precision + SUFFIX)
     os.makedirs(obj_dir, exist_ok=True)
     flags = NVCC_FLAGS + (["-DMSCLIP_FP16"] if precision == "fp16" else [])
-    if os.environ.get("MSCLIP_QGELU_TANH") == "1":      # A/B build: one-MUFU QuickGELU in the fc1 epilogue
-        flags = flags + ["-DMSCLIP_QGELU_TANH"]
+    if os.environ.get("MSCLIP_QGELU_EXP") == "1":       # A/B build: two-MUFU (ex2 + rcp) QuickGELU in the fc1 epilogue
+        flags = flags + ["-DMSCLIP_QGELU_EXP"]
     nvcc = _nvcc()
     newest_header = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
 
