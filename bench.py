@@ -526,7 +526,7 @@ def run_ours(args, cfg, rank, world, local):
                 "peak_source": pk["source"] + ", burst (kernel timed alone)",
                 "us_per_launch": gemm_s * 1e6,
                 "whole_step": {"achieved": step_tf, "peak": pk["sustained"], "frac": step_tf / pk["sustained"],
-                               "note": "per-GPU pairs/s x 23.549 GFLOP/pair against the sustained cuBLAS peak"}}
+                               "note": f"per-GPU pairs/s x {GF_PER_PAIR[cfg.patch_size] / 1e9:.3f} GFLOP/pair against the sustained cuBLAS peak"}}
     del a, w, o
 
     # ---- comparators: the reference forward run eagerly on this GPU; NCCL exchange + logits + CE

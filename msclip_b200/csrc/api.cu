@@ -300,7 +300,8 @@ int msclip_op_front_conv(const void* img, int dtype, int batch, int height, int 
 }
 int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
                               const float* b, float* x_out, int batch, int grid, void* stream) {
-  return launch_adapter_fuse_ln(x, t, dw_w9, dw_bias, w, b, x_out, batch, grid, nullptr, nullptr, as_stream(stream));
+  return launch_adapter_fuse_ln(x, t, dw_w9, dw_bias, w, b, x_out, batch, grid, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                as_stream(stream));
 }
 int msclip_op_contrastive_lse(const void* img_f16, const void* txt_f16, int b, float scale, void* workspace,
                               float* parts2, void* stream) {

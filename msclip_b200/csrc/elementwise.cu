@@ -116,10 +116,24 @@ text_max_len_kernel(const int64_t* __restrict__ tok, int L, int batch, int* __re
   if (lane == 0) atomicMax(out_max, best_i + 1);
 }
 
+// The producers of the residual stream can also emit the LayerNorm the next GEMM consumes (ln_1 of the block that
+// follows): the row is in registers anyway, so the separate LayerNorm launch (one more read of the fp32 row) disappears.
+// Same row arithmetic as layernorm_kernel -> bit-identical h.
+struct NextLn {
+  const float* w;
+  const float* b;
+  op16* h;  // null: not requested
+};
+__device__ __forceinline__ void emit_next_ln(float4 (&v)[kVec], const NextLn& nl, long long r, int lane) {
+  if (nl.h == nullptr) return;
+  layer_norm_row(v, nl.w, nl.b, lane);
+  store_row_bf16(nl.h + r * kD, lane, v);
+}
+
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 text_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb, const float* __restrict__ pos,
                   float* __restrict__ x, long long rows, int L, int Ltok, int vocab, int* __restrict__ err,
-                  op16* __restrict__ xc, float* __restrict__ rec) {
+                  op16* __restrict__ xc, float* __restrict__ rec, NextLn nl) {
   const int lane = threadIdx.x & 31;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
        r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
@@ -141,13 +155,14 @@ text_embed_kernel(const int64_t* __restrict__ tok, const float* __restrict__ emb
     }
     store_row_f32(x + r * kD, lane, v);
     if (xc != nullptr) emit_centred_row(v, lane, xc + r * kD, rec + r * kLnRecordFloats);
+    emit_next_ln(v, nl, r, lane);
   }
 }
 
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 image_embed_ln_pre_kernel(const float* __restrict__ grid, const float* __restrict__ cls, const float* __restrict__ pos,
                           const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ x,
-                          long long rows, int L, op16* __restrict__ xc, float* __restrict__ rec) {
+                          long long rows, int L, op16* __restrict__ xc, float* __restrict__ rec, NextLn nl) {
   const int lane = threadIdx.x & 31;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
        r += static_cast<long long>(gridDim.x) * kRowsPerBlock) {
@@ -166,6 +181,7 @@ image_embed_ln_pre_kernel(const float* __restrict__ grid, const float* __restric
     layer_norm_row(v, w, b, lane);
     store_row_f32(x + r * kD, lane, v);
     if (xc != nullptr) emit_centred_row(v, lane, xc + r * kD, rec + r * kLnRecordFloats);
+    emit_next_ln(v, nl, r, lane);
   }
 }
 
@@ -173,7 +189,8 @@ image_embed_ln_pre_kernel(const float* __restrict__ grid, const float* __restric
 __global__ void __launch_bounds__(32 * kRowsPerBlock)
 adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t, const float* __restrict__ dw_w9,
                        const float* __restrict__ dw_bias, const float* __restrict__ w, const float* __restrict__ b,
-                       float* __restrict__ x_out, long long rows, int g, op16* __restrict__ xc, float* __restrict__ rec) {
+                       float* __restrict__ x_out, long long rows, int g, op16* __restrict__ xc, float* __restrict__ rec,
+                       NextLn nl) {
   const int lane = threadIdx.x & 31;
   const int L = g * g + 1;
   for (long long r = static_cast<long long>(blockIdx.x) * kRowsPerBlock + (threadIdx.x >> 5); r < rows;
@@ -229,6 +246,7 @@ adapter_fuse_ln_kernel(const float* __restrict__ x, const float* __restrict__ t,
     layer_norm_row(v, w, b, lane);
     store_row_f32(x_out + r * kD, lane, v);
     if (xc != nullptr) emit_centred_row(v, lane, xc + r * kD, rec + r * kLnRecordFloats);
+    emit_next_ln(v, nl, r, lane);
   }
 }
 
@@ -306,13 +324,14 @@ static int* token_error_flag() {
 }
 
 int launch_text_embed(const int64_t* tok, int tok_pitch, const float* tok_emb, const float* pos, float* x, int batch, int L,
-                      int vocab, op16* xc, float* rec, cudaStream_t stream) {
+                      int vocab, op16* xc, float* rec, const float* next_ln_w, const float* next_ln_b, op16* next_h,
+                      cudaStream_t stream) {
   if (batch <= 0) return 0;
   int* flag = token_error_flag();
   MSCLIP_REQUIRE(flag != nullptr, "cudaMalloc of the token error flag failed");
   const long long rows = static_cast<long long>(batch) * L;
   text_embed_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(tok, tok_emb, pos, x, rows, L, tok_pitch, vocab, flag,
-                                                                       xc, xc ? rec : nullptr);
+                                                                       xc, xc ? rec : nullptr, NextLn{next_ln_w, next_ln_b, next_h});
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -332,21 +351,24 @@ int check_token_error(cudaStream_t stream) {
 }
 
 int launch_image_embed_ln_pre(const float* grid, const float* cls, const float* pos, const float* w, const float* b,
-                              float* x, int batch, int L, op16* xc, float* rec, cudaStream_t stream) {
+                              float* x, int batch, int L, op16* xc, float* rec, const float* next_ln_w,
+                              const float* next_ln_b, op16* next_h, cudaStream_t stream) {
   if (batch <= 0) return 0;
   const long long rows = static_cast<long long>(batch) * L;
-  image_embed_ln_pre_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(grid, cls, pos, w, b, x, rows, L, xc, rec);
+  image_embed_ln_pre_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(grid, cls, pos, w, b, x, rows, L, xc, rec,
+                                                                               NextLn{next_ln_w, next_ln_b, next_h});
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
-                           const float* b, float* x_out, int batch, int g, op16* xc, float* rec, cudaStream_t stream) {
+                           const float* b, float* x_out, int batch, int g, op16* xc, float* rec, const float* next_ln_w,
+                           const float* next_ln_b, op16* next_h, cudaStream_t stream) {
   if (batch <= 0) return 0;
   MSCLIP_REQUIRE(x != x_out, "adapter tail cannot run in place (3x3 neighbourhood reads)");
   const long long rows = static_cast<long long>(batch) * (g * g + 1);
   adapter_fuse_ln_kernel<<<row_grid(rows), 32 * kRowsPerBlock, 0, stream>>>(x, t, dw_w9, dw_bias, w, b, x_out, rows, g, xc,
-                                                                            rec);
+                                                                            rec, NextLn{next_ln_w, next_ln_b, next_h});
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -636,6 +636,7 @@ static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch,
     count_launch(launches);
     return 0;
   }
+  const bool have_h = *h_ready && !g_ln_fold;  // ln_1(x) already in hbuf (emitted by the kernel that produced x)
   *h_ready = false;
   if (g_ln_fold) {
     MSCLIP_TRY(launch_gemm_ln(hbuf, w, bw.w_qkv_ln, w, M, 3 * w, w, bw.b_qkv_ln, qkv, 3 * w, nullptr, 0, EPI_BF16, 1, rec[0],
@@ -650,14 +651,14 @@ static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch,
     count_launch(5);
     return 0;
   }
-  MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
+  if (!have_h) MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
   MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, qkv, 3 * w, nullptr, 0, EPI_BF16, s));
   MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
   MSCLIP_TRY(launch_gemm(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, x, w, EPI_RESID_F32, s));
   MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln2_w, bw.ln2_b, hbuf, M, s));
   MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
   MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, x, w, EPI_RESID_F32, s));
-  count_launch(7);
+  count_launch(have_h ? 6 : 7);
   return 0;
 }
 
@@ -875,9 +876,15 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     float* xc = x;
     float* xo = x2;
     float* gt = gridtmp + static_cast<size_t>(b0) * g * g * w;
-    MSCLIP_TRY(launch_image_embed_ln_pre(gt, h->cls, h->vpos, h->ln_pre_w, h->ln_pre_b, xc, nb, L, xcen, rec[0], s));
+    // the kernels that produce the residual stream also emit ln_1 of the block that consumes it next
+    bool adapter_first = false;
+    for (int j = 0; j < n_active; ++j) adapter_first |= kLateral[j] == 1;
+    const bool emit1 = !g_ln_fold && c.layers > 1 && !adapter_first;
+    MSCLIP_TRY(launch_image_embed_ln_pre(gt, h->cls, h->vpos, h->ln_pre_w, h->ln_pre_b, xc, nb, L, xcen, rec[0],
+                                         emit1 ? h->vblocks[1].ln1_w : nullptr, emit1 ? h->vblocks[1].ln1_b : nullptr,
+                                         emit1 ? hbuf : nullptr, s));
     count_launch(1);
-    bool h_ready = false;
+    bool h_ready = emit1;
     for (int idx = 1; idx < c.layers; ++idx) {
       for (int j = 0; j < n_active; ++j) {
         if (kLateral[j] != idx) continue;
@@ -885,10 +892,13 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         // t = pw_conv(BN(dw_conv(top)))  (M.py:1756-1759); the stem output in gridtmp is dead by now
         MSCLIP_TRY(launch_gemm(pooled[j] + static_cast<size_t>(b0) * g * g * a.C, a.C, a.pw, a.C, nb * g * g, w, a.C,
                                nullptr, gt, w, nullptr, 0, EPI_F32, s));
-        MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, xcen, rec[0], s));
+        const bool emit = !g_ln_fold;
+        MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, xcen, rec[0],
+                                          emit ? h->vblocks[idx].ln1_w : nullptr, emit ? h->vblocks[idx].ln1_b : nullptr,
+                                          emit ? hbuf : nullptr, s));
         count_launch(2);
         std::swap(xc, xo);
-        h_ready = false;
+        h_ready = emit;
       }
       // the next block's ln_1 can ride on this block's fc2 unless a lateral adapter rewrites x in between
       bool adapter_next = false;
@@ -931,9 +941,12 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
   for (int b0 = 0; b0 < batch; b0 += kTowerChunk) {
     const int nb = std::min(kTowerChunk, batch - b0);
     const int64_t* tk = tok + static_cast<size_t>(b0) * Lt;
-    MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0], s));
+    const bool emit0 = !g_ln_fold;
+    MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0],
+                                 emit0 ? h->tblocks[0].ln1_w : nullptr, emit0 ? h->tblocks[0].ln1_b : nullptr,
+                                 emit0 ? hbuf : nullptr, s));
     count_launch(1);
-    bool h_ready = false;
+    bool h_ready = emit0;
     for (int idx = 0; idx < c.layers; ++idx)
       MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, rec, &h_ready,
                            idx + 1 < c.layers ? &h->tblocks[idx + 1] : nullptr, s));

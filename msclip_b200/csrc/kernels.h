@@ -103,15 +103,20 @@ int launch_eot_layernorm_op16(const float* x, int x_len, const int64_t* tok, int
 // *out_max = max(*out_max, max_b argmax_j tok[b, j] + 1): the longest live prefix of the batch
 int launch_text_max_len(const int64_t* tok, int L, int batch, int* out_max, cudaStream_t stream);
 // x[b*L+l] = tok_emb[tok[b*tok_pitch + l]] + pos[l], l < L <= tok_pitch   (M.py:3047-3048)
-// xc / rec (optional, all three producers of the residual stream): op16(x - mean) and the row record for the LN fold
+// xc / rec (optional, all three producers of the residual stream): op16(x - mean) and the row record for the LN fold.
+// next_h (optional, all three): also emit LayerNorm(x) * next_ln_w + next_ln_b as op16 - ln_1 of the block that follows -
+// so that block needs no separate LayerNorm launch (bit-identical to launch_layernorm_op16 on the same x).
 int launch_text_embed(const int64_t* tok, int tok_pitch, const float* tok_emb, const float* pos, float* x, int batch, int L,
-                      int vocab, op16* xc, float* rec, cudaStream_t stream);
+                      int vocab, op16* xc, float* rec, const float* next_ln_w, const float* next_ln_b, op16* next_h,
+                      cudaStream_t stream);
 // x[b*L+l] = ln_pre((l == 0 ? cls : grid[b*(L-1)+l-1]) + pos[l])   (M.py:2418-2426)
 int launch_image_embed_ln_pre(const float* grid, const float* cls, const float* pos, const float* w, const float* b,
-                              float* x, int batch, int L, op16* xc, float* rec, cudaStream_t stream);
+                              float* x, int batch, int L, op16* xc, float* rec, const float* next_ln_w,
+                              const float* next_ln_b, op16* next_h, cudaStream_t stream);
 // Lateral adapter tail (M.py:1760-1777): x_out = ln_adapt(concat(2*cls, BN(dw3x3(grid(x))) + t))
 int launch_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9, const float* dw_bias, const float* w,
-                           const float* b, float* x_out, int batch, int g, op16* xc, float* rec, cudaStream_t stream);
+                           const float* b, float* x_out, int batch, int g, op16* xc, float* rec, const float* next_ln_w,
+                           const float* next_ln_b, op16* next_h, cudaStream_t stream);
 // out[r] = x[r] / ||x[r]|| (optional) as f32 and op16 copies; width E (<= 1024, multiple of 4)
 int check_token_error(cudaStream_t stream);  // synchronises; non-zero if an out-of-range token id was seen
 int launch_l2norm(const float* x, float* out_f32, emb16* out_f16, int rows, int E, int normalise, cudaStream_t stream);
