@@ -529,6 +529,34 @@ def run_ours(args, cfg, rank, world, local):
                                "note": f"per-GPU pairs/s x {GF_PER_PAIR[cfg.patch_size] / 1e9:.3f} GFLOP/pair against the sustained cuBLAS peak"}}
     del a, w, o
 
+    # ---- where a multi-GPU step spends its time: towers vs loss stage (peer wait + fused kernel), per rank, device-timed
+    phases = None
+    if world > 1:
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        barrier()
+        for k in range(args.steps):
+            ev[k][0].record(stream)
+            for m in range(n_micro):
+                _lib.check(L.msclip_encode_pairs(h, C.c_void_p(img_dev.data_ptr() + m * img_micro_bytes), _lib.F32,
+                                                 C.c_void_p(tok_dev.data_ptr() + m * tok_micro_bytes), micro, m * micro, sp),
+                           "msclip_encode_pairs")
+            ev[k][1].record(stream)
+            _lib.check(L.msclip_contrastive_loss(h, B, scale.value, C.c_void_p(parts.data_ptr()), None, sp), "msclip_contrastive_loss")
+            ev[k][2].record(stream)
+        barrier()
+        enc = torch.tensor([sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps], device=dev)
+        los = torch.tensor([sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps], device=dev)
+        enc_all = [torch.empty_like(enc) for _ in range(world)]
+        los_all = [torch.empty_like(los) for _ in range(world)]
+        torch.distributed.all_gather(enc_all, enc)
+        torch.distributed.all_gather(los_all, los)
+        phases = {"encode_ms_per_rank": [round(float(x), 3) for x in enc_all],
+                  "loss_stage_ms_per_rank": [round(float(x), 3) for x in los_all],
+                  "what": "mean over the timed steps, CUDA events on each rank's stream: encode = both towers; loss stage = publish + "
+                          "stream wait for the peers' flags (absorbs the skew between ranks: a rank whose towers finish early "
+                          "waits here for the slowest one) + fused similarity / cross-entropy kernels; compare with "
+                          "comparators.loss_stage_vs_nccl.fused_p2p_loss_ms (the same stage with ranks aligned by a barrier)"}
+
     # ---- comparators: the reference forward run eagerly on this GPU; NCCL exchange + logits + CE
     comparators = {}
     if world > 1 and not args.no_comparators:
@@ -550,7 +578,7 @@ def run_ours(args, cfg, rank, world, local):
         "dtype": args.precision, "data": "synthetic", "config": workload_config(args, cfg, world), "impl": "ours",
         "loss": loss_value, "loss_expected_ln_G": math.log(B * world),
         "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary, "roofline": roofline, "cpu_baseline": cpu,
-        "device_bytes": int(L.msclip_device_bytes(h)), "comparators": comparators or None,
+        "device_bytes": int(L.msclip_device_bytes(h)), "comparators": comparators or None, "phases": phases,
     }
     emit(line)
 

@@ -11,4 +11,4 @@ import json;d=json.load(open('gpurun_out/bench_n$N.json'));print(round(d['value'
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --global-batch 32768 --steps 3 --warmup 3 --no-cpu --no-comparators > gpurun_out/bench_g32k_n$N.json 2> gpurun_out/bench_g32k_n$N.err
 echo "bench global-32768 N=$N exit $?"; python -c "
 import json;d=json.load(open('gpurun_out/bench_g32k_n$N.json'));print(round(d['value']), round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), d['gpu_launches'], 'loss', d['loss'], d['loss_expected_ln_G'])"
-tail -3 gpurun_out/bench_n$N.err gpurun_out/bench_g32k_n$N.err
+tail -n 3 gpurun_out/bench_n$N.err
