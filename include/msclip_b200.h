@@ -142,6 +142,32 @@ int msclip_contrastive_loss_features(msclip_handle h, const float* img_feat, con
  * local shard receives a gradient, as with gather_tensors (lib/utils/comm.py:151-152); every rank must call it (the
  * column-wise softmax needs the peers' row log-sum-exps: a second in-kernel peer read, no collective). */
 int msclip_contrastive_loss_backward(msclip_handle h, float* d_img_feat, float* d_txt_feat, void* stream);
+/* ---- training (the reference ships no backward - what a training loop around CLIP.forward would get
+ * from torch.autograd: loss.backward() through lib/utils/comm.py:151-152, M.py:3126-3155, 3043-3079, 2621-2697) ------------
+ * msclip_train_enable(h, 1), called BEFORE msclip_finalize_weights (a finalized handle must be re-sent its weights),
+ * makes the handle (i) keep transposed copies of the block weights, (ii) allocate one fp32 gradient buffer per trainable
+ * state-dict key (aliased keys share a buffer, like the parameters, M.py:2786-2830) and (iii) keep the fp32 input of
+ * every block during encode_image / encode_text (calls of at most 4096 rows).  bf16 build only.
+ * Trainable: both heads, every ResidualAttentionBlock, ln_pre / ln_post / ln_final / ln_adapt, token / positional / class
+ * embeddings.  The convolutional front (stem, parallel branch, adapter convolutions, BatchNorms) is frozen: the gradient
+ * flows THROUGH the adapters' bottom path but their convolution parameters receive none. */
+int msclip_train_enable(msclip_handle h, int enable);
+/* Accumulate d loss / d parameter for the LAST taped msclip_encode_image / msclip_encode_text (or msclip_forward_loss /
+ * msclip_encode_pairs) call into the gradient buffers, given d loss / d features [batch, embed_dim] f32 on the device
+ * (of the normalised features when the call normalised) - e.g. the output of msclip_contrastive_loss_backward.
+ * Either gradient may be NULL (that tower is skipped). */
+int msclip_backward(msclip_handle h, const float* d_img_feat, const float* d_txt_feat, void* stream);
+int msclip_zero_grad(msclip_handle h, void* stream);
+/* Normalised features [b, embed_dim] f32 of the last taped tower call (modality 0 = image, 1 = text), re-read from the
+ * tape - e.g. for d loss / d logit_scale = sum_i I_i . dI_i after msclip_forward_loss, which returns no features. */
+int msclip_taped_features(msclip_handle h, int modality, float* out, int b, void* stream);
+/* The gradient buffers: count, and key / device pointer / element count of entry i (layout = the parameter's). */
+int msclip_num_grads(msclip_handle h);
+int msclip_grad_info(msclip_handle h, int index, const char** key, float** dev_ptr, int64_t* numel);
+/* Re-pack ONE trainable parameter from its updated fp32 master copy `dev_ptr` (after an optimiser step): no allocation,
+ * no host round trip; keys of the frozen front are rejected. */
+int msclip_update_weight(msclip_handle h, const char* key, const float* dev_ptr, void* stream);
+
 /* Micro-batching (BASELINE.json: global batch 32 768 on 1 / 2 / 4 GPUs): run both towers
  * for b_micro pairs and keep their normalised embeddings as rows [row_offset, row_offset + b_micro) of this rank's
  * shard of the NEXT msclip_contrastive_loss.  row_offset must be 0 (new shard) or the number of rows encoded so far;

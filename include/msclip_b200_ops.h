@@ -17,6 +17,8 @@
  *                             bottleneck entry, adapter-0 pooling (one fused pass over the image)
  *   msclip_op_adapter_fuse_ln Lateral_Adapter tail                  M.py:1760-1777
  *   msclip_op_contrastive_lse similarity + symmetric CE partials    M.py:3141 + north-star loss
+ *   msclip_op_wgrad / _attention_bwd / _layernorm_bwd / _qgelu_bwd   backward of the ops above (section 8f-1)
+ *   msclip_op_adamw           fused multi-tensor AdamW              experiments/model/b32.yaml:32-53
  *   msclip_num_keys / msclip_key_info   the state-dict contract     SURVEY.md section 8c
  */
 #ifndef MSCLIP_B200_OPS_H_
@@ -107,6 +109,30 @@ int msclip_op_adapter_fuse_ln(const float* x, const float* t, const float* dw_w9
 int msclip_op_contrastive_lse(const void* img_f16, const void* txt_f16, int b, float scale, void* workspace,
                               float* parts2, void* stream);
 size_t msclip_op_contrastive_lse_workspace(int b);
+
+/* ---- backward kernels (oracle = torch.autograd of the forward op) -------------------------------
+ * dw[n, k] (f32, dense) (+)= sum_t dy[t, n] * x[t, k]: weight gradient of F.linear (M.py:612, 747, 794-798) by tcgen05 with
+ * MN-major operands (no transposes); n % 128 == 0, k % 256 == 0; workspace = msclip_op_wgrad_workspace(tokens, n, k) bytes. */
+int msclip_op_wgrad(const void* dy_bf16, int64_t ldy, const void* x_bf16, int64_t ldx, int tokens, int n, int k, float* dw,
+                    int accumulate, void* workspace, void* stream);
+size_t msclip_op_wgrad_workspace(int tokens, int n, int k);
+void msclip_op_set_wgrad_desc(unsigned lbo_bytes, unsigned sbo_bytes); /* bring-up knob; 0 = default */
+/* backward of msclip_op_attention: dqkv = gradient of the UNSCALED (q | k | v) given qkv (q pre-scaled) and the gradient of
+ * the attention output; seq_len <= 80 */
+int msclip_op_attention_bwd(const void* qkv_bf16, const void* dctx_bf16, void* dqkv_bf16, int batch, int seq_len, int heads,
+                            int causal, void* stream);
+/* dx (+)= LayerNorm_backward(dy; x, gamma) over 768 columns; dx16 (optional) = bf16(dx after the update); dgamma / dbeta /
+ * dcolsum [768] (+)= sum_rows dy*xhat / dy / updated dx (each may be NULL); workspace = msclip_op_bwd_workspace(rows) bytes */
+int msclip_op_layernorm_bwd(const float* x, const float* dy, const float* gamma, float* dx, void* dx16, float* dgamma, float* dbeta,
+                            float* dcolsum, int rows, int accumulate, void* workspace, void* stream);
+/* da <- da * quickgelu'(u) (bf16, in place); dbias [width] (+)= column sums of the result; width % 256 == 0 */
+int msclip_op_qgelu_bwd(void* da_bf16, const void* u_bf16, float* dbias, int rows, int width, void* workspace, void* stream);
+size_t msclip_op_bwd_workspace(int rows);
+/* Fused multi-tensor AdamW (torch.optim.AdamW semantics; optimiser of experiments/model/b32.yaml:32-53): host arrays of n
+ * device pointers / element counts / per-tensor lr and weight decay; `step` >= 1 (bias correction). */
+int msclip_op_adamw(int n, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                    const int64_t* numel, const float* lr, const float* weight_decay, float beta1, float beta2, float eps,
+                    int step, void* stream);
 
 /* state-dict contract of a handle: number of keys, and key / rank / shape (up to 4 dims) of entry i. */
 int msclip_num_keys(msclip_handle h);

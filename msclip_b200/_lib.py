@@ -72,6 +72,13 @@ _SIGNATURES = {
     "msclip_encode_pairs": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "msclip_contrastive_loss_backward": (_I, [_P, _P, _P, _P]),
     "msclip_contrastive_loss_features": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
+    "msclip_train_enable": (_I, [_P, _I]),
+    "msclip_backward": (_I, [_P, _P, _P, _P]),
+    "msclip_zero_grad": (_I, [_P, _P]),
+    "msclip_taped_features": (_I, [_P, _I, _P, _I, _P]),
+    "msclip_num_grads": (_I, [_P]),
+    "msclip_grad_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(_L)]),
+    "msclip_update_weight": (_I, [_P, C.c_char_p, _P, _P]),
     "msclip_launch_count": (_L, [_P]),
     "msclip_device_bytes": (_L, [_P]),
     # include/msclip_b200_ops.h
@@ -95,6 +102,14 @@ _SIGNATURES = {
     "msclip_op_adapter_fuse_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "msclip_op_contrastive_lse": (_I, [_P, _P, _I, _F, _P, _P, _P]),
     "msclip_op_contrastive_lse_workspace": (C.c_size_t, [_I]),
+    "msclip_op_wgrad": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _P]),
+    "msclip_op_wgrad_workspace": (C.c_size_t, [_I, _I, _I]),
+    "msclip_op_set_wgrad_desc": (None, [C.c_uint, C.c_uint]),
+    "msclip_op_attention_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "msclip_op_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "msclip_op_qgelu_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "msclip_op_bwd_workspace": (C.c_size_t, [_I]),
+    "msclip_op_adamw": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _I, _P]),
     "msclip_num_keys": (_I, [_P]),
     "msclip_key_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I), C.POINTER(_L)]),
 }

@@ -2,6 +2,8 @@
 #include "engine.h"
 
 #include <new>
+#include <cstring>
+#include <vector>
 
 #include "../../include/msclip_b200_ops.h"
 #include "common.cuh"
@@ -66,6 +68,78 @@ int msclip_create(const msclip_config* cfg, msclip_handle* out) {
 int msclip_destroy(msclip_handle h) {
   delete h;
   return 0;
+}
+
+// ---- backward kernels ----------------------------------------------------------------------------------------------
+int msclip_op_wgrad(const void* dy, int64_t ldy, const void* x, int64_t ldx, int tokens, int n, int k, float* dw, int accumulate,
+                    void* workspace, void* stream) {
+  return launch_wgrad(static_cast<const op16*>(dy), ldy, static_cast<const op16*>(x), ldx, tokens, n, k, dw, accumulate, workspace,
+                      as_stream(stream));
+}
+size_t msclip_op_wgrad_workspace(int tokens, int n, int k) { return wgrad_workspace_bytes(tokens, n, k); }
+void msclip_op_set_wgrad_desc(unsigned lbo, unsigned sbo) { wgrad_set_desc(lbo, sbo); }
+int msclip_op_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int batch, int seq_len, int heads, int causal,
+                            void* stream) {
+  return launch_attention_bwd(static_cast<const op16*>(qkv), static_cast<const op16*>(dctx), static_cast<op16*>(dqkv), batch, seq_len,
+                              heads, causal, as_stream(stream));
+}
+size_t msclip_op_bwd_workspace(int rows) {
+  const size_t a = static_cast<size_t>(bwd_row_parts(rows)) * 3 * 768, b = static_cast<size_t>(bwd_slab_parts(rows)) * 4 * 768;
+  return (a > b ? a : b) * sizeof(float);
+}
+int msclip_op_layernorm_bwd(const float* x, const float* dy, const float* gamma, float* dx, void* dx16, float* dgamma, float* dbeta,
+                            float* dcolsum, int rows, int accumulate, void* workspace, void* stream) {
+  MSCLIP_REQUIRE(workspace != nullptr && rows > 0, "msclip_op_layernorm_bwd: bad arguments");
+  float* part = static_cast<float*>(workspace);
+  cudaStream_t s = as_stream(stream);
+  MSCLIP_TRY(launch_ln_bwd(x, dy, gamma, dx, static_cast<op16*>(dx16), part, rows, accumulate, s));
+  const int rp = bwd_row_parts(rows);
+  float* dst[3] = {dgamma, dbeta, dcolsum};
+  for (int i = 0; i < 3; ++i)
+    if (dst[i]) MSCLIP_TRY(launch_reduce_partials(part + i * 768, rp, 3 * 768, dst[i], 768, 1, 0, 1.0f, s));
+  return 0;
+}
+int msclip_op_qgelu_bwd(void* da, const void* u, float* dbias, int rows, int width, void* workspace, void* stream) {
+  MSCLIP_REQUIRE(workspace != nullptr && rows > 0 && width <= 4 * 768, "msclip_op_qgelu_bwd: bad arguments");
+  float* part = static_cast<float*>(workspace);
+  cudaStream_t s = as_stream(stream);
+  MSCLIP_TRY(launch_qgelu_bwd(static_cast<op16*>(da), static_cast<const op16*>(u), part, rows, width, s));
+  if (dbias) MSCLIP_TRY(launch_reduce_partials(part, bwd_slab_parts(rows), width, dbias, width, 1, 0, 1.0f, s));
+  return 0;
+}
+int msclip_op_adamw(int n, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                    const int64_t* numel, const float* lr, const float* weight_decay, float beta1, float beta2, float eps, int step,
+                    void* stream) {
+  MSCLIP_REQUIRE(n >= 0 && step >= 1, "msclip_op_adamw: bad arguments");
+  if (n == 0) return 0;
+  // tensor table + chunk map (64 Ki elements per chunk) staged through one stream-ordered device allocation
+  constexpr int kChunk = 65536;
+  std::vector<AdamwTensor> tab(n);
+  std::vector<int> ct;
+  std::vector<long long> co;
+  for (int i = 0; i < n; ++i) {
+    tab[i] = {params[i], grads[i], exp_avg[i], exp_avg_sq[i], static_cast<long long>(numel[i]), lr[i], weight_decay[i]};
+    for (long long o = 0; o < numel[i]; o += kChunk) {
+      ct.push_back(i);
+      co.push_back(o);
+    }
+  }
+  const size_t b0 = tab.size() * sizeof(AdamwTensor), b1 = ct.size() * sizeof(int), b2 = co.size() * sizeof(long long);
+  const size_t o1 = (b0 + 15) & ~size_t(15), o2 = (o1 + b1 + 15) & ~size_t(15);
+  std::vector<uint8_t> host(o2 + b2);
+  memcpy(host.data(), tab.data(), b0);
+  memcpy(host.data() + o1, ct.data(), b1);
+  memcpy(host.data() + o2, co.data(), b2);
+  cudaStream_t s = as_stream(stream);
+  uint8_t* dev = nullptr;
+  MSCLIP_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), host.size(), s));
+  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, s));
+  MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));  // the pageable host table must outlive the copy
+  const int rc = launch_adamw(reinterpret_cast<const AdamwTensor*>(dev), reinterpret_cast<const int*>(dev + o1),
+                              reinterpret_cast<const long long*>(dev + o2), static_cast<int>(ct.size()), kChunk, beta1, beta2, eps,
+                              step, s);
+  MSCLIP_CHECK_CUDA(cudaFreeAsync(dev, s));
+  return rc;
 }
 
 int msclip_num_keys(msclip_handle h) { return h ? static_cast<int>(h->spec.size()) : -1; }
@@ -209,6 +283,31 @@ int msclip_forward_loss(msclip_handle h, const void* image, int image_dtype, con
                         float* partial_out, float* loss_out, void* stream) {
   MSCLIP_REQUIRE(h != nullptr, "null handle");
   return engine_forward_loss(h, image, image_dtype, tokens, b_local, partial_out, loss_out, as_stream(stream));
+}
+
+int msclip_train_enable(msclip_handle h, int enable) { return train_enable(h, enable); }
+int msclip_backward(msclip_handle h, const float* d_img_feat, const float* d_txt_feat, void* stream) {
+  return engine_backward(h, d_img_feat, d_txt_feat, as_stream(stream));
+}
+int msclip_zero_grad(msclip_handle h, void* stream) { return engine_zero_grad(h, as_stream(stream)); }
+int msclip_taped_features(msclip_handle h, int modality, float* out, int b, void* stream) {
+  MSCLIP_REQUIRE(h != nullptr && out != nullptr && (modality == 0 || modality == 1), "msclip_taped_features: bad arguments");
+  const msclip_ctx::TapeInfo& t = modality == 0 ? h->tape_img : h->tape_txt;
+  MSCLIP_REQUIRE(t.valid && b == t.batch, "msclip_taped_features: no taped call with that batch size");
+  const float* raw = static_cast<const float*>(tape_get(h, modality == 0 ? "v_feat" : "t_feat"));
+  MSCLIP_REQUIRE(raw != nullptr, "msclip_taped_features: incomplete tape");
+  return launch_l2norm(raw, out, nullptr, b, h->cfg.embed_dim, 1, as_stream(stream));
+}
+int msclip_num_grads(msclip_handle h) { return h ? static_cast<int>(h->grad_list.size()) : 0; }
+int msclip_grad_info(msclip_handle h, int index, const char** key, float** dev_ptr, int64_t* numel) {
+  MSCLIP_REQUIRE(h != nullptr && index >= 0 && index < static_cast<int>(h->grad_list.size()), "msclip_grad_info: index out of range");
+  if (key) *key = h->grad_list[index].first.c_str();
+  if (dev_ptr) *dev_ptr = h->grad_list[index].second;
+  if (numel) *numel = h->grad_numel[index];
+  return 0;
+}
+int msclip_update_weight(msclip_handle h, const char* key, const float* dev_ptr, void* stream) {
+  return engine_update_weight(h, key, dev_ptr, as_stream(stream));
 }
 
 int64_t msclip_launch_count(msclip_handle) { return launch_count(); }

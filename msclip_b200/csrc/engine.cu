@@ -193,6 +193,14 @@ struct Packer {
     if (d && launch_pack_op16(t.dev, 1, N, nullptr, d, K, N, K, stream)) rc = 1;
     return d;
   }
+  // nn.Linear weight [N,K] -> its transpose op16 [K,N] (rows = input features): B operand of dX = dY . W
+  op16* transposed_linear(const std::string& k) {
+    const RawTensor& t = raw(k);
+    const int N = static_cast<int>(t.shape[0]), K = static_cast<int>(t.shape[1]);
+    op16* d = static_cast<op16*>(dalloc(static_cast<size_t>(N) * K * 2));
+    if (d && launch_pack_op16(t.dev, 1, K, nullptr, d, N, K, N, stream)) rc = 1;
+    return d;
+  }
   // W [N,K] with LayerNorm `ln` in front of it -> W * diag(gamma) (op16), its column sums, bias + W . beta
   void ln_fold(const std::string& wk, const std::string& bk, const float* row_scale, const std::string& ln, op16** w_out,
                float** cs_out, float** b_out) {
@@ -294,6 +302,7 @@ int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
   std::vector<float> qs(3 * w, 1.0f);
   for (int i = 0; i < w; ++i) qs[i] = 0.125f;
   float* qscale = P.up_f32(qs);
+  h->qscale_dev = qscale;
 
   // ---- transformer blocks
   h->vblocks.assign(c.layers, BlockWeights());
@@ -432,6 +441,22 @@ int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
     a.ln_w = P.keep_f32(p + "ln_adapt.weight");
     a.ln_b = P.keep_f32(p + "ln_adapt.bias");
   }
+  if (h->train) {
+    // transposed copies of the block weights / un-transposed projections for the input-gradient GEMMs
+    h->vblocks_t.assign(c.layers, BlockWeightsT());
+    h->tblocks_t.assign(c.layers, BlockWeightsT());
+    auto pack_t = [&](const std::string& p, BlockWeightsT& t) {
+      t.w_qkv_t = P.transposed_linear(p + ".attn.in_proj_weight");
+      t.w_o_t = P.transposed_linear(p + ".attn.out_proj.weight");
+      t.w_fc1_t = P.transposed_linear(p + ".mlp.c_fc.weight");
+      t.w_fc2_t = P.transposed_linear(p + ".mlp.c_proj.weight");
+    };
+    for (int i = 1; i < c.layers; ++i) pack_t("visual.transformer.resblocks." + std::to_string(i), h->vblocks_t[i]);
+    pack_t("transformer.resblocks.0", h->tblocks_t[0]);
+    for (int i = 1; i < c.layers; ++i) h->tblocks_t[i] = h->vblocks_t[i];
+    h->vproj_n = P.linear("visual.proj", nullptr);
+    h->tproj_n = P.linear("text_projection", nullptr);
+  }
   MSCLIP_CHECK_CUDA(cudaStreamSynchronize(stream));
   if (P.rc) return P.rc;
   for (auto& kv : h->raw) cudaFree(kv.second.dev);
@@ -441,7 +466,7 @@ int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------ workspace
-static int ws_get(msclip_ctx* h, const char* name, size_t bytes, void** out) {
+int ws_get(msclip_ctx* h, const char* name, size_t bytes, void** out) {
   DevBuf& b = h->ws[name];
   if (b.bytes < bytes) {
     if (b.p) {
@@ -463,9 +488,17 @@ static int ws_get(msclip_ctx* h, const char* name, size_t bytes, void** out) {
   *out = b.p;
   return 0;
 }
-#define WS(var, type, name, count) \
-  type* var = nullptr;             \
-  MSCLIP_TRY(ws_get(h, name, static_cast<size_t>(count) * sizeof(type), reinterpret_cast<void**>(&var)))
+
+int tape_save(msclip_ctx* h, const std::string& name, const void* src, size_t bytes, cudaStream_t s) {
+  void* dst = nullptr;
+  MSCLIP_TRY(ws_get(h, ("tape:" + name).c_str(), bytes, &dst));
+  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+void* tape_get(msclip_ctx* h, const std::string& name) {
+  auto it = h->ws.find("tape:" + name);
+  return it == h->ws.end() ? nullptr : it->second.p;
+}
 
 static int ensure_streams(msclip_ctx* h) {
   if (!h->copy_stream) {
@@ -884,6 +917,12 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
                                          emit1 ? h->vblocks[1].ln1_w : nullptr, emit1 ? h->vblocks[1].ln1_b : nullptr,
                                          emit1 ? hbuf : nullptr, s));
     count_launch(1);
+    // training: keep what the backward pass re-reads (engine_train.cu) - the stem output, every block's input, every
+    // adapter's input and top-path term, the final stream and the un-normalised features
+    const bool tape = h->train && batch <= kTrainMaxBatch;
+    const size_t xbytes = static_cast<size_t>(nb) * L * w * sizeof(float), gbytes = static_cast<size_t>(nb) * g * g * w * sizeof(float);
+    h->tape_img.valid = false;
+    if (tape) MSCLIP_TRY(tape_save(h, "v_grid", gt, gbytes, s));
     bool h_ready = emit1;
     for (int idx = 1; idx < c.layers; ++idx) {
       for (int j = 0; j < n_active; ++j) {
@@ -892,6 +931,10 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         // t = pw_conv(BN(dw_conv(top)))  (M.py:1756-1759); the stem output in gridtmp is dead by now
         MSCLIP_TRY(launch_gemm(pooled[j] + static_cast<size_t>(b0) * g * g * a.C, a.C, a.pw, a.C, nb * g * g, w, a.C,
                                nullptr, gt, w, nullptr, 0, EPI_F32, s));
+        if (tape) {
+          MSCLIP_TRY(tape_save(h, "v_ax" + std::to_string(j), xc, xbytes, s));
+          MSCLIP_TRY(tape_save(h, "v_at" + std::to_string(j), gt, gbytes, s));
+        }
         const bool emit = !g_ln_fold;
         MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, xcen, rec[0],
                                           emit ? h->vblocks[idx].ln1_w : nullptr, emit ? h->vblocks[idx].ln1_b : nullptr,
@@ -904,12 +947,21 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
       bool adapter_next = false;
       for (int j = 0; j < n_active; ++j) adapter_next |= kLateral[j] == idx + 1;
       const BlockWeights* next = (idx + 1 < c.layers && !adapter_next) ? &h->vblocks[idx + 1] : nullptr;
+      if (tape) MSCLIP_TRY(tape_save(h, "v_x" + std::to_string(idx), xc, xbytes, s));
       MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, rec, &h_ready, next, s));
     }
+    if (tape) MSCLIP_TRY(tape_save(h, "v_x" + std::to_string(c.layers), xc, xbytes, s));
     // CLS -> ln_post -> proj -> L2 norm (M.py:2685-2690, 2982-2983)
     MSCLIP_TRY(launch_layernorm_op16(xc, L, h->ln_post_w, h->ln_post_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->vproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));
+    if (tape) {
+      MSCLIP_TRY(tape_save(h, "v_feat", feat_raw, static_cast<size_t>(nb) * c.embed_dim * sizeof(float), s));
+      h->tape_img.batch = nb;
+      h->tape_img.L = L;
+      h->tape_img.normalize = normalize;
+      h->tape_img.valid = true;
+    }
     MSCLIP_TRY(launch_l2norm(feat_raw, out_dev + static_cast<size_t>(b0) * c.embed_dim,
                              feat_bf16 ? feat_bf16 + static_cast<size_t>(b0) * c.embed_dim : nullptr, nb, c.embed_dim,
                              normalize, s));
@@ -947,12 +999,28 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
                                  emit0 ? hbuf : nullptr, s));
     count_launch(1);
     bool h_ready = emit0;
-    for (int idx = 0; idx < c.layers; ++idx)
+    const bool tape = h->train && batch <= kTrainMaxBatch;  // see vision_tower
+    const size_t xbytes = static_cast<size_t>(nb) * L * w * sizeof(float);
+    h->tape_txt.valid = false;
+    for (int idx = 0; idx < c.layers; ++idx) {
+      if (tape) MSCLIP_TRY(tape_save(h, "t_x" + std::to_string(idx), x, xbytes, s));
       MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, rec, &h_ready,
                            idx + 1 < c.layers ? &h->tblocks[idx + 1] : nullptr, s));
+    }
+    if (tape) {
+      MSCLIP_TRY(tape_save(h, "t_x" + std::to_string(c.layers), x, xbytes, s));
+      MSCLIP_TRY(tape_save(h, "t_tok", tk, static_cast<size_t>(nb) * Lt * sizeof(int64_t), s));
+    }
     MSCLIP_TRY(launch_eot_layernorm_op16(x, L, tk, Lt, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->tproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));
+    if (tape) {
+      MSCLIP_TRY(tape_save(h, "t_feat", feat_raw, static_cast<size_t>(nb) * c.embed_dim * sizeof(float), s));
+      h->tape_txt.batch = nb;
+      h->tape_txt.L = L;
+      h->tape_txt.normalize = normalize;
+      h->tape_txt.valid = true;
+    }
     MSCLIP_TRY(launch_l2norm(feat_raw, out_dev + static_cast<size_t>(b0) * c.embed_dim,
                              feat_bf16 ? feat_bf16 + static_cast<size_t>(b0) * c.embed_dim : nullptr, nb, c.embed_dim,
                              normalize, s));
@@ -1497,6 +1565,7 @@ msclip_ctx::~msclip_ctx() {
   for (auto& kv : raw) cudaFree(kv.second.dev);
   for (void* p : weight_allocs) cudaFree(p);
   for (auto& kv : ws) cudaFree(kv.second.p);
+  msclip::train_free(this);
   for (int r = 0; r < static_cast<int>(peer_base.size()); ++r)
     if (r != rank && peer_base[r] && !peers_borrowed) cudaIpcCloseMemHandle(peer_base[r]);
   for (auto& st : staged) {

@@ -36,6 +36,17 @@ struct BlockWeights {
   float *cs_qkv = nullptr, *cs_fc1 = nullptr, *b_qkv_ln = nullptr, *b_fc1_ln = nullptr;
 };
 
+// transposed copies of the block's linear weights: the B operand of the input-gradient GEMMs (dX = dY . W needs W^T
+// K-major); w_qkv_t is packed from the UNSCALED in_proj weight (attention_bwd emits the gradient of the unscaled q)
+struct BlockWeightsT {
+  op16 *w_qkv_t = nullptr, *w_o_t = nullptr, *w_fc1_t = nullptr, *w_fc2_t = nullptr;  // [768,2304] [768,768] [768,3072] [3072,768]
+};
+// fp32 gradient buffers of one block (text blocks 1.. share the linear-layer buffers of the vision block, like the weights)
+struct BlockGrads {
+  float *w_qkv = nullptr, *b_qkv = nullptr, *w_o = nullptr, *b_o = nullptr, *w_fc1 = nullptr, *b_fc1 = nullptr, *w_fc2 = nullptr,
+        *b_fc2 = nullptr, *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+};
+
 struct ConvWeights {
   op16* w = nullptr;   // [N, K] op16, BN scale folded
   float* b = nullptr;  // [N] BN shift (null = no bias)
@@ -62,6 +73,7 @@ struct msclip_ctx {
   bool finalized = false;
   bool text_trim = true;  // encode_text runs the causal tower only over the longest live prefix (<= EOT) of the batch
   float logit_scale = 0.f;
+  float* qscale_dev = nullptr;  // [3 * width]: 1/8 for the q rows of in_proj (M.py:707), 1 elsewhere
 
   // packed weights
   std::vector<msclip::BlockWeights> vblocks, tblocks;  // index = block id (vblocks[0] unused: it is the stem)
@@ -106,6 +118,20 @@ struct msclip_ctx {
   int loss_b = 0;          // local batch of the last contrastive loss (0 = none): what msclip_contrastive_loss_backward uses
   float loss_scale = 0.f;
 
+  // ---- training (engine_train.cu): backward of heads, transformer blocks, adapter bottom paths and
+  // embeddings.  `train` makes finalize keep transposed weight copies and makes the towers keep their per-block inputs.
+  bool train = false;
+  std::vector<msclip::BlockWeightsT> vblocks_t, tblocks_t;
+  msclip::op16 *vproj_n = nullptr, *tproj_n = nullptr;  // projections as [width, embed] K-major (dgrad operand)
+  std::vector<msclip::BlockGrads> vgrads, tgrads;
+  std::vector<std::pair<std::string, float*>> grad_list;  // state-dict key -> gradient buffer (aliased keys share one buffer)
+  std::vector<int64_t> grad_numel;
+  std::vector<std::pair<float*, size_t>> grad_allocs;     // unique allocations (pointer, bytes)
+  struct TapeInfo {
+    int batch = 0, L = 0, normalize = 1;
+    bool valid = false;
+  } tape_txt, tape_img;
+
   ~msclip_ctx();
 };
 
@@ -140,6 +166,24 @@ int comm_init(msclip_ctx* h, int rank, int world, int max_b_local);
 int comm_export(msclip_ctx* h, void* handle_out);
 int comm_import(msclip_ctx* h, const void* handles);
 int comm_import_pointers(msclip_ctx* h, void* const* bases);
+
+// workspace buffers are named and grow on demand (engine.cu)
+int ws_get(msclip_ctx* h, const char* name, size_t bytes, void** out);
+#define WS(var, type, name, count) \
+  type* var = nullptr;             \
+  MSCLIP_TRY(::msclip::ws_get(h, name, static_cast<size_t>(count) * sizeof(type), reinterpret_cast<void**>(&var)))
+// tape of the training forward: named copies of activations the backward pass needs ("tape:" + name)
+int tape_save(msclip_ctx* h, const std::string& name, const void* src, size_t bytes, cudaStream_t s);
+void* tape_get(msclip_ctx* h, const std::string& name);
+constexpr int kLateralLayers[5] = {2, 4, 6, 8, 10};  // PARALLEL_LATERAL_LAYER, b32-yfcc-msclips.yaml:18
+constexpr int kTrainMaxBatch = 4096;                 // one transformer chunk per tower call
+
+int train_enable(msclip_ctx* h, int enable);
+int train_pack_transposed(msclip_ctx* h, cudaStream_t stream);   // called by engine_finalize while the raw tensors exist
+int engine_backward(msclip_ctx* h, const float* d_img, const float* d_txt, cudaStream_t stream);
+int engine_zero_grad(msclip_ctx* h, cudaStream_t stream);
+int engine_update_weight(msclip_ctx* h, const char* key, const float* src, cudaStream_t stream);
+void train_free(msclip_ctx* h);
 
 int64_t launch_count();
 void count_launch(int n);

@@ -195,6 +195,58 @@ int launch_contrastive_loss_backward(const emb16* img_local, const emb16* txt_lo
                                      int rank, int b_local, float scale, void* workspace, float* d_img, float* d_txt,
                                      cudaStream_t stream);
 size_t contrastive_backward_workspace_bytes(int world, int b_local);
+// ---- backward pass: wgrad.cu, attention_bwd.cu, backward.cu ----------------------------
+// dW [N, K] f32 (+)= dY[tokens, N]^T . X[tokens, K]  (tcgen05 with MN-major operands, token range split S ways,
+// deterministic reduction of the S partial matrices).  N % 128 == 0, K % 256 == 0.
+int launch_wgrad(const op16* dY, int64_t ldy, const op16* X, int64_t ldx, int tokens, int N, int K, float* dW, int accumulate,
+                 void* workspace, cudaStream_t stream);
+size_t wgrad_workspace_bytes(int tokens, int N, int K);
+int wgrad_pick_splits(int tokens, int N, int K);
+void wgrad_set_desc(uint32_t lbo, uint32_t sbo);  // bring-up knob (0 = default)
+// qkv [B*L, 3*64*heads] (q pre-scaled), dctx [B*L, 64*heads] -> dqkv = gradient of the unscaled (q | k | v); L <= 80
+int launch_attention_bwd(const op16* qkv, const op16* dctx, op16* dqkv, int batch, int L, int heads, int causal,
+                         cudaStream_t stream);
+// Row kernels write per-CTA partial column sums ([parts][slots * 768] / [parts][width]); launch_reduce_partials folds them:
+// dst[j] (+)= (j < head_n ? head_scale : 1) * sum_p part[p * pitch + j]
+int bwd_row_parts(long long rows);   // CTAs (= partial rows) of the 768-wide row kernels below
+int bwd_slab_parts(long long rows);  // partial rows of the 16-bit slab kernels (qgelu_bwd, colsum16)
+int launch_reduce_partials(const float* part, int nparts, long long pitch, float* dst, long long n, int accumulate,
+                           long long head_n, float head_scale, cudaStream_t stream);
+// dx (+)= LN_backward(dy; x, gamma); g16 (optional) = op16(dx); part [bwd_row_parts][3 * 768] = dgamma | dbeta | colsum(dx)
+int launch_ln_bwd(const float* x, const float* dy, const float* gamma, float* dx, op16* g16, float* part, long long rows,
+                  int accumulate, cudaStream_t stream);
+// g16 = op16(dx); part [bwd_row_parts][768] = colsum(dx)
+int launch_cast_colsum(const float* dx, op16* g16, float* part, long long rows, cudaStream_t stream);
+int launch_qgelu_fwd(const op16* u, op16* a, long long n, cudaStream_t stream);
+// da <- da * quickgelu'(u); part [bwd_slab_parts][width] = colsum
+int launch_qgelu_bwd(op16* da, const op16* u, float* part, long long rows, int width, cudaStream_t stream);
+int launch_colsum16(const op16* g, float* part, long long rows, int width, cudaStream_t stream);
+int launch_l2norm_bwd(const float* g, const float* df, float* dg, op16* dg16, int rows, int E, int normalise, cudaStream_t stream);
+// pooled rows (tok != null: EOT position of tok [batch, Ltok]; null: row 0 = CLS): dx[b * Lx + pos_b] = LN_backward(dz[b]);
+// part [bwd_row_parts(batch)][2 * 768] = dgamma | dbeta
+int launch_pooled_ln_bwd(const float* x, int Lx, const int64_t* tok, int Ltok, const float* dz, const float* gamma, float* dx,
+                         float* part, int batch, cudaStream_t stream);
+int launch_text_embed_bwd(const float* dx, const int64_t* tok, int Ltok, int L, int batch, int vocab, float* dpos, float* demb,
+                          cudaStream_t stream);
+// dx <- LN_backward(dx; e) with e recomputed from (grid, cls, pos); part [bwd_row_parts][2 * 768]; dpos / dcls accumulate
+int launch_image_embed_bwd(const float* grid, const float* cls, const float* pos, const float* gamma, float* dx, float* part,
+                           int batch, int L, float* dpos, float* dcls, cudaStream_t stream);
+// lateral adapter, bottom path: dxo (gradient of the adapter output, overwritten with ds = gradient of the pre-LayerNorm sum,
+// whose grid rows are also the gradient of the top path's t) -> dx = gradient of the adapter input; part [..][2 * 768]
+int launch_adapter_bwd(const float* x, const float* t, const float* w9, const float* bias, const float* gamma, float* dxo,
+                       float* dx, float* part, int batch, int gsz, cudaStream_t stream);
+// fused multi-tensor AdamW (torch.optim.AdamW semantics)
+struct AdamwTensor {
+  float* param;
+  const float* grad;
+  float* m;
+  float* v;
+  long long numel;
+  float lr, wd;
+};
+int launch_adamw(const AdamwTensor* tab_dev, const int* chunk_tensor_dev, const long long* chunk_off_dev, int nchunks, int chunk,
+                 float beta1, float beta2, float eps, int step, cudaStream_t stream);
+
 // ---- weight packing (pack.cu) -------------------------------------------------------------------
 // dst[n, k] (op16, pitch ldd) = src[n*sn + k*sk] * (row_scale ? row_scale[n] : 1)
 int launch_pack_op16(const float* src, int64_t sn, int64_t sk, const float* row_scale, op16* dst, int64_t ldd, int N,

@@ -73,6 +73,13 @@ def _init_tensor(key: str, shape) -> torch.Tensor:
     return t
 
 
+class _DeviceArray:
+    """A raw device pointer as a CUDA-array-interface object (zero-copy torch view of a library-owned buffer)."""
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape) if len(shape) else (1,), "typestr": "<f4",
+                                         "data": (int(ptr), False), "version": 2}
+
+
 class CLIP(nn.Module):
     def __init__(self, cfg: MSCLIPConfig, precision: Optional[str] = None):
         """``precision``: MMA operand type of the library build to use - "bf16" (default, the north star's
@@ -418,6 +425,111 @@ class CLIP(nn.Module):
                                                                         C.c_void_p(gt.data_ptr()), self._stream()),
                         "msclip_contrastive_loss_backward")
         return gi, gt
+
+    # ---- training: backward + optimiser hooks -----------------------------------
+    def enable_training(self, enable: bool = True) -> None:
+        """Make the library keep what the backward pass needs (transposed weight copies, per-block inputs of the
+        towers, one fp32 gradient buffer per trainable key) - see include/msclip_b200.h.  The gradient buffers are
+        attached zero-copy as ``.grad`` of the corresponding parameters (aliased text / vision parameters are one
+        Parameter and one buffer, M.py:2786-2830), so ``torch.optim`` optimisers work unchanged and
+        ``msclip_b200.optim.AdamW`` updates them with one fused kernel.  The convolutional front stays frozen."""
+        with self._on_device():
+            self._ensure_handle()
+            self._check(self._library().msclip_train_enable(self._handle, int(bool(enable))), "msclip_train_enable")
+            self._synced = None                       # re-send the weights: transposed copies are packed at finalize
+            self._train_keys = {}
+            if enable:
+                self._sync_weights()
+                self._attach_grads()
+
+    def _attach_grads(self) -> None:
+        L = self._library()
+        params = dict(self.named_parameters(remove_duplicate=False))
+        seen = {}
+        for i in range(L.msclip_num_grads(self._handle)):
+            key, ptr, numel = C.c_char_p(), C.c_void_p(), C.c_int64()
+            self._check(L.msclip_grad_info(self._handle, i, C.byref(key), C.byref(ptr), C.byref(numel)), "msclip_grad_info")
+            name = key.value.decode()
+            p = params[name]
+            if p.numel() != numel.value or p.dtype != torch.float32:
+                raise _lib.MsclipError(f"gradient buffer of {name} does not match the fp32 parameter")
+            if ptr.value not in seen:
+                seen[ptr.value] = torch.as_tensor(_DeviceArray(ptr.value, (p.numel(),)), device=self.device).view(p.shape)
+            p.grad = seen[ptr.value]
+            self._train_keys[name] = p
+        ls = self.logit_scale
+        if ls.grad is None:
+            ls.grad = torch.zeros_like(ls)
+        self._train_keys["logit_scale"] = ls
+
+    def trainable_parameters(self):
+        """{state-dict key: Parameter} of everything that receives a gradient (one entry per key; aliased keys map to
+        the same Parameter)."""
+        if not getattr(self, "_train_keys", None):
+            raise _lib.MsclipError("call enable_training() first")
+        return dict(self._train_keys)
+
+    def zero_grad(self, set_to_none: bool = False):             # the buffers belong to the library: always zero in place
+        if getattr(self, "_train_keys", None):
+            with self._on_device():
+                self._check(self._library().msclip_zero_grad(self._handle, self._stream()), "msclip_zero_grad")
+            self.logit_scale.grad.zero_()
+            return
+        return super().zero_grad(set_to_none)
+
+    @torch.no_grad()
+    def backward_features(self, d_image_features: Optional[torch.Tensor], d_text_features: Optional[torch.Tensor]) -> None:
+        """Accumulate d loss / d parameter for the last ``encode_image`` / ``encode_text`` (or ``contrastive_loss``) call,
+        given d loss / d features [B, embed_dim] of the features those calls returned (msclip_backward)."""
+        gi = d_image_features.float().contiguous() if d_image_features is not None else None
+        gt = d_text_features.float().contiguous() if d_text_features is not None else None
+        with self._on_device():
+            self._check(self._library().msclip_backward(self._handle, C.c_void_p(gi.data_ptr()) if gi is not None else None,
+                                                       C.c_void_p(gt.data_ptr()) if gt is not None else None, self._stream()),
+                        "msclip_backward")
+
+    @torch.no_grad()
+    def loss_and_backward(self, image: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+        """One training forward + backward: the fused global-batch loss (``contrastive_loss``), its backward to the local
+        embeddings (second in-kernel peer pass) and the backward of both towers.  Gradients accumulate in ``.grad``;
+        with more than one rank they are LOCAL (all-reduce them like DDP would).  Returns the loss."""
+        loss = self.contrastive_loss(image, text)
+        gi, gt = self.contrastive_loss_backward()
+        self.backward_features(gi, gt)
+        # d loss / d logit_scale = s * d loss / d s = sum_i I_i . dI_i  (dI_i = s / 2G * sum_j w_ij T_j)
+        fi = self.last_image_features()
+        self.logit_scale.grad += (gi * fi).sum().to(self.logit_scale.dtype)
+        return loss
+
+    @torch.no_grad()
+    def last_image_features(self) -> torch.Tensor:
+        """Normalised image features of the last taped image-tower call (read back from the library's tape)."""
+        if not getattr(self, "_train_keys", None):
+            raise _lib.MsclipError("call enable_training() first")
+        with self._on_device():
+            b = self._last_loss_b
+            out = torch.empty((b, self.cfg.embed_dim), dtype=torch.float32, device=self.device)
+            self._check(self._library().msclip_taped_features(self._handle, 0, C.c_void_p(out.data_ptr()), b, self._stream()),
+                        "msclip_taped_features")
+        return out
+
+    @torch.no_grad()
+    def refresh_weights(self, keys=None) -> None:
+        """Re-pack trainable parameters from their (updated) fp32 masters - device-side, no allocation
+        (msclip_update_weight).  ``keys``: state-dict keys to refresh; default all trainable ones."""
+        todo = self.trainable_parameters()
+        if keys is not None:
+            todo = {k: todo[k] for k in keys}
+        done = set()
+        with self._on_device():
+            for key, p in todo.items():
+                if p.data_ptr() in done:
+                    continue
+                done.add(p.data_ptr())
+                self._check(self._library().msclip_update_weight(self._handle, key.encode(), C.c_void_p(p.data_ptr()),
+                                                                self._stream()), f"msclip_update_weight({key})")
+        if self._tensors is not None:       # the packed copies are current: do not trigger a full re-upload
+            self._synced = tuple((t.data_ptr(), t._version) for _, t in self._tensors)
 
     def launch_count(self) -> int:
         return int(self._library().msclip_launch_count(self._handle)) if self._handle else 0
