@@ -25,24 +25,40 @@ from oracle.make_golden import case_inputs       # noqa: E402
 from golden_util import GOLDEN_DIR, GRAD_CASES, grad_sample, trainable_keys   # noqa: E402
 
 
-def run_case(name):
-    cfg, sd, img, tok = case_inputs(name)
+def reference_grads(cfg, sd, img, tok, autocast):
     model = ref_shim.build_reference_model(cfg, sd)
     model.eval()
     for p in model.parameters():
         p.requires_grad_(True)
-    logits = model(torch.from_numpy(img), torch.from_numpy(tok))
+    if autocast:
+        # the reference's own bf16 mode (as in make_golden.py): the yardstick for a bf16-operand backward
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            logits = model(torch.from_numpy(img), torch.from_numpy(tok)).float()
+    else:
+        logits = model(torch.from_numpy(img), torch.from_numpy(tok))
     tgt = torch.arange(logits.shape[0])
     loss = 0.5 * (F.cross_entropy(logits, tgt) + F.cross_entropy(logits.t(), tgt))
     loss.backward()
     params = dict(model.named_parameters(remove_duplicate=False))
-    out = {"meta": json.dumps({"case": name, "loss": float(loss), "torch": torch.__version__})}
+    return {k: params[k].grad.detach().numpy().copy() for k in trainable_keys(cfg)}, float(loss.detach())
+
+
+def run_case(name):
+    cfg, sd, img, tok = case_inputs(name)
+    grads, loss = reference_grads(cfg, sd, img, tok, False)
+    grads_ac, _ = reference_grads(cfg, sd, img, tok, True)
+    out = {}
+    num = den = 0.0
     for key in trainable_keys(cfg):
-        g = params[key].grad
-        assert g is not None, key
-        g = g.detach().numpy()
+        g = grads[key]
         out["norm/" + key] = np.float64(np.linalg.norm(g.astype(np.float64)))
         out["sample/" + key] = grad_sample(g, key, tok)
+        out["sample_autocast/" + key] = grad_sample(grads_ac[key], key, tok)
+        num += float(np.linalg.norm(out["sample_autocast/" + key].astype(np.float64) - out["sample/" + key]) ** 2)
+        den += float(np.linalg.norm(out["sample/" + key].astype(np.float64)) ** 2)
+    out["meta"] = json.dumps({"case": name, "loss": loss, "torch": torch.__version__,
+                              "autocast_aggregate": (num / den) ** 0.5})
+    print(f"  reference autocast(bf16) backward vs fp32, sample aggregate: {(num / den) ** 0.5:.4f}")
     np.savez_compressed(os.path.join(GOLDEN_DIR, "grad_" + name + ".npz"), **out)
     print(f"{name}: loss {float(loss):.6f}, {len(trainable_keys(cfg))} gradient tensors")
 
