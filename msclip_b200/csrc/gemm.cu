@@ -229,7 +229,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = umma_idesc_f32acc(kBM * CG, BN);
+      const uint32_t idesc = umma_idesc_f32acc_fmt(kBM * CG, BN, p.operand_fmt);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -598,7 +598,14 @@ int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, i
 
 static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                             const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
-                            int split_cols, cudaStream_t stream);
+                            int split_cols, cudaStream_t stream, uint32_t operand_fmt = kUmmaOperandFormat);
+
+// the same GEMM on IEEE fp16 operands whatever the build's operand type (16-bit payloads are moved as opaque words)
+int launch_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, float alpha, void* out, int64_t ldo,
+                    int epi, cudaStream_t stream) {
+  return launch_gemm_impl(static_cast<const op16*>(A), lda, static_cast<const op16*>(W), ldw, M, N, K, alpha, nullptr, out, ldo, nullptr,
+                          0, epi, 0, stream, kUmmaFormatF16);
+}
 
 int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
@@ -643,6 +650,7 @@ int launch_gemm_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M
   MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
                                static_cast<uint32_t>(256 / cg)));
   GemmParams p = {};
+  p.operand_fmt = kUmmaOperandFormat;
   p.M = M;
   p.N = N;
   p.K = K;
@@ -686,6 +694,7 @@ int launch_gemm_resid_ln(const op16* A, int64_t lda, const op16* W, int64_t ldw,
   MSCLIP_TRY(make_tmap_op16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM));
   MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw), 128));
   GemmParams p = {};
+  p.operand_fmt = kUmmaOperandFormat;
   p.M = M;
   p.N = N;
   p.K = K;
@@ -711,7 +720,7 @@ size_t gemm_resid_ln_counters(int M) { return 2 * static_cast<size_t>((M + 2 * k
 
 static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                             const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
-                            int split_cols, cudaStream_t stream) {
+                            int split_cols, cudaStream_t stream, uint32_t operand_fmt) {
   MSCLIP_REQUIRE(M > 0 && N > 0 && K > 0, "launch_gemm: empty problem");
   MSCLIP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "launch_gemm: K and operand pitches must be multiples of 8");
   const int bn = split_cols ? split_cols : gemm_pick_bn(N);
@@ -730,6 +739,7 @@ static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t l
   MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
                                static_cast<uint32_t>(bn / cg / np)));
   GemmParams p = {};
+  p.operand_fmt = kUmmaOperandFormat;
   p.M = M;
   p.N = N;
   p.K = K;
@@ -737,6 +747,7 @@ static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t l
   p.alpha = alpha;
   p.vec_ok = vec_ok ? 1 : 0;
   p.split_stride = split_cols ? static_cast<long long>(M) * split_cols : 0;
+  p.operand_fmt = operand_fmt;
   p.total_tiles = ((M + kBM * cg * np - 1) / (kBM * cg * np)) * p.tiles_n;
   p.bias = bias;
   p.out = out;
@@ -803,6 +814,7 @@ int launch_conv_tma(const ConvSource* src, int nsrc, int batch, int Ho, int Wo, 
                       (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   MSCLIP_REQUIRE(vec_ok, "conv_tma: output rows and bias must be 16-byte aligned");
   GemmParams p = {};
+  p.operand_fmt = kUmmaOperandFormat;
   CUtensorMap ta[2], tb;
   int kb = 0;
   for (int i = 0; i < nsrc; ++i) {

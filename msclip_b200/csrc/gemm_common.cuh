@@ -51,6 +51,7 @@ struct GemmParams {
   long long ldo, ldr;
   float alpha;  // acc is scaled by alpha before the bias (similarity logits: exp(logit_scale))
   int vec_ok;   // rows of out / resid keep 16-byte alignment -> vector stores
+  uint32_t operand_fmt;  // kind::f16 A/B format field (0 = F16, 1 = BF16): the loss backward runs fp16 operands in both builds
   long long split_stride;  // != 0: column tile j writes a separate [M, BN] matrix at out + j * split_stride (elements)
   // LayerNorm folded into the GEMMs around it (kernel template parameter LN, see below)
   const float* ln_in;    // LN = 1: row records of A's rows; LN = 2: records of the residual input (its mean = new shift)

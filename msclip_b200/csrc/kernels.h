@@ -65,6 +65,9 @@ int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, i
 
 int launch_gemm_split(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
                       void* out, int split_cols, int epi, cudaStream_t stream);
+// fp16 operands in either build (only 16-bit-out / f32-out epilogues without bias or residual): the loss backward
+int launch_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, float alpha, void* out, int64_t ldo,
+                    int epi, cudaStream_t stream);
 void gemm_set_pair_mode(int mode);  // 0: 1 CTA per tile, 1: CTA pairs, 2|4: multicast clusters of 2|4 pairs
 int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,

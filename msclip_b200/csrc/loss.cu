@@ -42,7 +42,8 @@ struct LossParams {
   // MODE 1 (backward): instead of the partials the epilogue writes w_ij = exp(s_ij - lse_row_i) + exp(s_ij - lse_col_j)
   const float* row_lse;              // [2][b_pad] log2-domain lse of this rank's rows (image rows | text rows)
   const float* const* col_lse[2];    // [dir] -> device table of `world` pointers: the column owners' row lse of the OTHER direction
-  op16* wout[2];                     // [dir] -> [b_local][ldw] probabilities, column = owner * b_local + local column
+  emb16* wout[2];                    // [dir] -> [b_local][ldw] probabilities * wscale (fp16), column = owner * b_local + local column
+  float wscale;                      // power of two that lifts probabilities of order 1 / G out of fp16's subnormal range
   long long ldw;
   int lse_pitch;                     // floats between the two directions of row_lse
 };
@@ -186,7 +187,7 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
         const int row = rb * 128 + q * 32 + lane;
         const float lse_r = row < p.b_local ? p.row_lse[dir * p.lse_pitch + row] : 0.f;
         const float* lse_c = p.col_lse[dir][owner] + c0;
-        op16* wrow = p.wout[dir] + static_cast<long long>(row) * p.ldw + static_cast<long long>(owner) * p.b_local + c0;
+        emb16* wrow = p.wout[dir] + static_cast<long long>(row) * p.ldw + static_cast<long long>(owner) * p.b_local + c0;
         // the positive pair of a row: its "- 2 x_i" term is folded into the matrix in fp32 (w_ii - 2 is small when the
         // softmax is peaked; rounding w_ii ~ 2 to 16 bits first would swamp the gradient)
         const int diag_col = (owner == p.rank) ? row - c0 : -1;
@@ -211,8 +212,8 @@ contrastive_lse_kernel(const __grid_constant__ CUtensorMap tmap_rows_img, const 
                 if (col + 1 == diag_col) w1 = (exp2f(v - lse_r) - 1.0f) + (exp2f(v - __ldg(lse_c + col + 1)) - 1.0f);
               }
               // element-wise stores: b_local (hence the column offset of a shard) need not be even
-              if (col < valid_cols) wrow[col] = to_op16(w0);
-              if (col + 1 < valid_cols) wrow[col + 1] = to_op16(w1);
+              if (col < valid_cols) wrow[col] = __float2half_rn(w0 * p.wscale);
+              if (col + 1 < valid_cols) wrow[col + 1] = __float2half_rn(w1 * p.wscale);
             }
           }
         }
@@ -289,24 +290,24 @@ lse_combine_kernel(const float2* __restrict__ ws, const float* __restrict__ diag
   if (lse_out != nullptr) lse_out[dir * lse_pitch + row] = m + log2f(l);  // log2 domain; the backward pass reads it
 }
 
-// out[k][owner * b_local + r] = op16(shards[owner][r][k]): the gathered embeddings, transposed, as the K-major B operand
+// out[k][owner * b_local + r] = shards[owner][r][k] (fp16, exactly as exchanged): the gathered embeddings, transposed, as the K-major B operand
 // of the gradient GEMM (K = global batch); 32 x 32 tiles through shared memory
 __global__ void __launch_bounds__(256)
-gather_transpose_kernel(const emb16* const* __restrict__ shards, int world, int b_local, int E, op16* __restrict__ out,
+gather_transpose_kernel(const emb16* const* __restrict__ shards, int world, int b_local, int E, emb16* __restrict__ out,
                         long long ld) {
-  __shared__ float tile[32][33];
+  __shared__ emb16 tile[32][34];
   const int owner = blockIdx.z;
   const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const emb16* src = shards[owner];
   for (int i = ty; i < 32; i += 8) {
     const int r = r0 + i;
-    tile[i][tx] = (r < b_local && k0 + tx < E) ? __half2float(src[static_cast<long long>(r) * E + k0 + tx]) : 0.f;
+    tile[i][tx] = (r < b_local && k0 + tx < E) ? src[static_cast<long long>(r) * E + k0 + tx] : __float2half_rn(0.f);
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int k = k0 + i, r = r0 + tx;
-    if (k < E && r < b_local) out[static_cast<long long>(k) * ld + static_cast<long long>(owner) * b_local + r] = to_op16(tile[tx][i]);
+    if (k < E && r < b_local) out[static_cast<long long>(k) * ld + static_cast<long long>(owner) * b_local + r] = tile[tx][i];
   }
 }
 
@@ -414,8 +415,15 @@ int launch_contrastive_loss_backward(const emb16* img_local, const emb16* txt_lo
   MSCLIP_TRY(configure_loss_kernels());
   const long long G = static_cast<long long>(world) * b_local, ldg = padded_g(world, b_local);
   uint8_t* w8 = static_cast<uint8_t*>(workspace);
-  op16* wprob[2] = {reinterpret_cast<op16*>(w8), reinterpret_cast<op16*>(w8) + static_cast<long long>(b_local) * ldg};
-  op16* xt[2] = {wprob[1] + static_cast<long long>(b_local) * ldg, wprob[1] + static_cast<long long>(b_local) * ldg + kLossE * ldg};
+  // 16-bit operands of the two gradient GEMMs are IEEE fp16 in BOTH builds: the embeddings are used exactly as exchanged, and
+  // w (|w| <= 2, typical magnitude 1 / G) is stored times 2^k, k = floor(log2 G) - 1, so that it keeps fp16's 11 significant
+  // bits (8 x less rounding error than bf16) instead of sinking into the subnormals; 2^-k is folded into the final coefficient.
+  emb16* wprob[2] = {reinterpret_cast<emb16*>(w8), reinterpret_cast<emb16*>(w8) + static_cast<long long>(b_local) * ldg};
+  emb16* xt[2] = {wprob[1] + static_cast<long long>(b_local) * ldg, wprob[1] + static_cast<long long>(b_local) * ldg + kLossE * ldg};
+  int wexp = 0;
+  while ((2ll << (wexp + 1)) <= G) ++wexp;   // 2 * 2^wexp <= G < 4 * 2^wexp  ->  |w| * 2^wexp <= G <= fp16 max for G <= 65504
+  if (wexp > 14) wexp = 14;
+  const float wscale = static_cast<float>(1 << wexp);
   float* raw = reinterpret_cast<float*>(xt[1] + kLossE * ldg);
   // zero padding columns (K of the GEMMs is ldg): clear the operands once per call
   MSCLIP_CHECK_CUDA(cudaMemsetAsync(w8, 0, static_cast<size_t>(2 * (static_cast<long long>(b_local) + kLossE) * ldg * 2), stream));
@@ -437,6 +445,7 @@ int launch_contrastive_loss_backward(const emb16* img_local, const emb16* txt_lo
   p.wout[0] = wprob[0];
   p.wout[1] = wprob[1];
   p.ldw = ldg;
+  p.wscale = wscale;
   CUtensorMap ti, tt;
   MSCLIP_TRY(make_tmap_op16_2d(&ti, img_local, b_local, kLossE, kLossE, 128));
   MSCLIP_TRY(make_tmap_op16_2d(&tt, txt_local, b_local, kLossE, kLossE, 128));
@@ -447,10 +456,10 @@ int launch_contrastive_loss_backward(const emb16* img_local, const emb16* txt_lo
   gather_transpose_kernel<<<tg, 256, 0, stream>>>(img_shards, world, b_local, kLossE, xt[1], ldg);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   // raw_img = w[0] . T_all, raw_txt = w[1] . I_all   (K = padded global batch)
-  MSCLIP_TRY(launch_gemm(wprob[0], ldg, xt[0], ldg, b_local, kLossE, static_cast<int>(ldg), nullptr, raw, kLossE, nullptr, 0, EPI_F32, stream));
-  MSCLIP_TRY(launch_gemm(wprob[1], ldg, xt[1], ldg, b_local, kLossE, static_cast<int>(ldg), nullptr, raw + static_cast<long long>(b_local) * kLossE,
-                         kLossE, nullptr, 0, EPI_F32, stream));
-  const float coef = scale / (2.0f * static_cast<float>(G));
+  MSCLIP_TRY(launch_gemm_f16(wprob[0], ldg, xt[0], ldg, b_local, kLossE, static_cast<int>(ldg), 1.0f, raw, kLossE, EPI_F32, stream));
+  MSCLIP_TRY(launch_gemm_f16(wprob[1], ldg, xt[1], ldg, b_local, kLossE, static_cast<int>(ldg), 1.0f, raw + static_cast<long long>(b_local) * kLossE,
+                             kLossE, EPI_F32, stream));
+  const float coef = scale / (2.0f * static_cast<float>(G) * wscale);
   const long long total = static_cast<long long>(b_local) * kLossE;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
   loss_grad_finish_kernel<<<grid, 256, 0, stream>>>(raw, coef, d_img, total);
