@@ -168,6 +168,18 @@ int msclip_grad_info(msclip_handle h, int index, const char** key, float** dev_p
  * no host round trip; keys of the frozen front are rejected. */
 int msclip_update_weight(msclip_handle h, const char* key, const float* dev_ptr, void* stream);
 
+/* ---- input pipeline on the GPU ---------------------------------------------------------------
+ * The tool's transform, tools/zero_shot.py:202-207: Resize(out_size, BICUBIC) -> CenterCrop(out_size) -> ToTensor ->
+ * Normalize(mean, std), for n decoded RGB images (uint8, HWC) of arbitrary sizes, BIT-EXACT with torchvision on PIL images
+ * (Pillow's two-pass 22-bit fixed-point resampling, restated in csrc/preprocess.cu).  `pixels`: the images back to back in
+ * host or device memory, image i at byte offset offsets[i] with heights[i] x widths[i] x 3 bytes (offsets / heights /
+ * widths are host arrays).  `out` [n, 3, out_size, out_size] in out_dtype (MSCLIP_F32 / _BF16 / _F16) - ready for
+ * msclip_encode_image - and / or `out_u8` [n, out_size, out_size, 3] (the resized, cropped bytes); device memory; either
+ * may be NULL. */
+int msclip_preprocess_images(msclip_handle h, const uint8_t* pixels, const int64_t* offsets, const int* heights, const int* widths,
+                             int n, int out_size, const float* mean3, const float* std3, void* out, int out_dtype, uint8_t* out_u8,
+                             void* stream);
+
 /* Micro-batching (BASELINE.json: global batch 32 768 on 1 / 2 / 4 GPUs): run both towers
  * for b_micro pairs and keep their normalised embeddings as rows [row_offset, row_offset + b_micro) of this rank's
  * shard of the NEXT msclip_contrastive_loss.  row_offset must be 0 (new shard) or the number of rows encoded so far;

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "msclip_encode_pairs": (_I, [_P, _P, _I, _P, _I, _I, _P]),
     "msclip_contrastive_loss_backward": (_I, [_P, _P, _P, _P]),
     "msclip_contrastive_loss_features": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
+    "msclip_preprocess_images": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
     "msclip_train_enable": (_I, [_P, _I]),
     "msclip_backward": (_I, [_P, _P, _P, _P]),
     "msclip_zero_grad": (_I, [_P, _P]),

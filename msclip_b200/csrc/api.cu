@@ -285,6 +285,10 @@ int msclip_forward_loss(msclip_handle h, const void* image, int image_dtype, con
   return engine_forward_loss(h, image, image_dtype, tokens, b_local, partial_out, loss_out, as_stream(stream));
 }
 
+int msclip_preprocess_images(msclip_handle h, const uint8_t* pixels, const int64_t* offsets, const int* heights, const int* widths, int n,
+                             int out_size, const float* mean3, const float* std3, void* out, int out_dtype, uint8_t* out_u8, void* stream) {
+  return engine_preprocess(h, pixels, offsets, heights, widths, n, out_size, mean3, std3, out, out_dtype, out_u8, as_stream(stream));
+}
 int msclip_train_enable(msclip_handle h, int enable) { return train_enable(h, enable); }
 int msclip_backward(msclip_handle h, const float* d_img_feat, const float* d_txt_feat, void* stream) {
   return engine_backward(h, d_img_feat, d_txt_feat, as_stream(stream));

@@ -185,6 +185,9 @@ int engine_zero_grad(msclip_ctx* h, cudaStream_t stream);
 int engine_update_weight(msclip_ctx* h, const char* key, const float* src, cudaStream_t stream);
 void train_free(msclip_ctx* h);
 
+int engine_preprocess(msclip_ctx* h, const uint8_t* pixels, const int64_t* offsets, const int* heights, const int* widths, int n, int S,
+                      const float* mean, const float* stdv, void* out, int out_dtype, uint8_t* out_u8, cudaStream_t s);
+
 int64_t launch_count();
 void count_launch(int n);
 bool is_device_pointer(const void* p);

@@ -217,19 +217,22 @@ int wgrad_pick_splits(int tokens, int N, int K) {
   const int tiles = (N / kWM) * (K / kWN);
   const int num_kb = (tokens + kWK - 1) / kWK;
   const int sms = num_sms();
-  int best = 1;
+  // wave efficiency of every candidate; take the SMALLEST split count within 3 % of the best (fewer partial matrices to write
+  // and reduce: 30 splits of the QKV gradient wrote 200 MB of partials for a 1 % better tail, profiles/r02_backward_ncu.md)
+  double eff[33] = {0.0};
   double best_eff = 0.0;
+  int smax = 1;
   for (int s = 1; s <= 32; ++s) {
     if (s > 1 && num_kb / s < 4) break;
     const int units = tiles * s;
     const int waves = (units + sms - 1) / sms;
-    const double eff = static_cast<double>(units) / (static_cast<double>(waves) * sms);
-    if (eff > best_eff + 0.02) {
-      best_eff = eff;
-      best = s;
-    }
+    eff[s] = static_cast<double>(units) / (static_cast<double>(waves) * sms);
+    if (eff[s] > best_eff) best_eff = eff[s];
+    smax = s;
   }
-  return best;
+  for (int s = 1; s <= smax; ++s)
+    if (eff[s] >= best_eff - 0.03) return s;
+  return 1;
 }
 
 size_t wgrad_workspace_bytes(int tokens, int N, int K) {

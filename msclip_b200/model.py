@@ -426,6 +426,44 @@ class CLIP(nn.Module):
                         "msclip_contrastive_loss_backward")
         return gi, gt
 
+    # ---- input pipeline on the GPU ------------------------------------------------
+    @torch.no_grad()
+    def preprocess(self, images, size: Optional[int] = None, mean=(0.48145466, 0.4578275, 0.40821073),
+                   std=(0.26862954, 0.26130258, 0.27577711), dtype: torch.dtype = torch.float32, source_on_device: bool = False,
+                   return_u8: bool = False):
+        """The tool's ``transform_CLIP`` (tools/zero_shot.py:202-207: Resize(size, BICUBIC), CenterCrop, ToTensor, Normalize
+        with lib/config/default.py:84-85) for a list of decoded RGB images - uint8 [H, W, 3] numpy arrays or tensors of any
+        sizes - in two kernel launches, bit-exact with torchvision on PIL images.  Returns ([n, 3, size, size] tensor on the
+        model's device ready for ``encode_image``, and with ``return_u8`` the resized + cropped bytes [n, size, size, 3])."""
+        import numpy as np
+        size = int(size or self.cfg.image_resolution)
+        arrs = [im.cpu().numpy() if isinstance(im, torch.Tensor) else np.asarray(im) for im in images]
+        for a in arrs:
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError("preprocess expects uint8 [H, W, 3] RGB images")
+        n = len(arrs)
+        offs, total = [], 0
+        for a in arrs:
+            offs.append(total)
+            total += a.size
+        packed = torch.empty(total, dtype=torch.uint8, pin_memory=not source_on_device)
+        flat = packed.numpy()
+        for a, o in zip(arrs, offs):
+            flat[o:o + a.size] = a.reshape(-1)
+        with self._on_device():
+            self._ensure_handle()
+            if source_on_device:
+                packed = packed.to(self.device)
+            out = torch.empty((n, 3, size, size), dtype=dtype, device=self.device)
+            u8 = torch.empty((n, size, size, 3), dtype=torch.uint8, device=self.device) if return_u8 else None
+            self._check(self._library().msclip_preprocess_images(
+                self._handle, C.c_void_p(packed.data_ptr()), (C.c_int64 * n)(*offs), (C.c_int * n)(*[a.shape[0] for a in arrs]),
+                (C.c_int * n)(*[a.shape[1] for a in arrs]), n, size, (C.c_float * 3)(*mean), (C.c_float * 3)(*std),
+                C.c_void_p(out.data_ptr()), _IMAGE_DTYPES[dtype], C.c_void_p(u8.data_ptr()) if return_u8 else None, self._stream()),
+                "msclip_preprocess_images")
+            torch.cuda.current_stream(self.device).synchronize()      # the pinned staging buffer is released on return
+        return out, u8
+
     # ---- training: backward + optimiser hooks (SURVEY.md section 8f-1) -----------------------------------
     def enable_training(self, enable: bool = True) -> None:
         """Make the library keep what the backward pass needs (transposed weight copies, per-block inputs of the
