@@ -301,6 +301,46 @@ def nccl_loss_comparator(model, L, h, dev, B, world, sp, scale):
                     "gather + fused similarity/CE); comparator = 2 x dist.all_gather + [G,G] logits + 2 x F.cross_entropy"}
 
 
+def train_step_block(model, img_dev, tok_dev, B, cfg, steps: int = 3, warmup: int = 1):
+    """Device-timed training step (secondary figure, not the headline metric): pairs/s and the tensor-roofline fraction with
+    3 x the transformer FLOPs of the forward (forward + dgrad + wgrad) + 1 x the frozen convolutional front."""
+    try:
+        from msclip_b200.optim import AdamW
+        torch.cuda.empty_cache()
+        model.enable_training()
+        opt = AdamW(model, lr=1e-4, weight_decay=0.05, lr_share=1e-4, wd_share=0.2)      # b32.yaml:32-53, b32-yfcc-msclips.yaml:13-14
+        losses = []
+
+        def step():
+            opt.zero_grad()
+            losses.append(model.loss_and_backward(img_dev, tok_dev))
+            opt.step()
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        gf = (3.0 * (23.549 - 2.379) + 2.379) if cfg.patch_size == 32 else None      # GFLOP: BASELINE.md section 3 (pair 23.549, convs 2.379)
+        pk = peaks()
+        pairs_s = B / ms * 1e3
+        out = {"ms_per_step": ms, "value": pairs_s, "unit": "pairs/s", "steps": steps, "warmup": warmup,
+               "what": "msclip_forward_loss (taped) + msclip_contrastive_loss_backward + msclip_backward + msclip_op_adamw + msclip_update_weight",
+               "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+               "device_bytes": int(model._library().msclip_device_bytes(model._handle))}
+        if gf:
+            out.update({"gflop_per_pair": gf, "tflops": pairs_s * gf / 1e3,
+                        "frac_of_sustained_tensor_peak": pairs_s * gf / 1e3 / pk["sustained"]})
+        return out
+    except Exception as exc:          # noqa: BLE001 - a secondary figure must never take the headline line down
+        return {"error": repr(exc)[:300]}
+
+
 def workload_config(args, cfg, world):
     if args.global_batch:
         b_local = args.global_batch // world
@@ -567,6 +607,11 @@ def run_ours(args, cfg, rank, world, local):
         free_before = torch.cuda.mem_get_info()[0]
         comparators["reference_eager_b200"] = eager_reference_on_gpu(cfg, sd_np, dev, min(micro, 4096))
         comparators["reference_eager_b200"]["free_hbm_gb_before"] = free_before / 1e9
+    # ---- secondary: one TRAINING step of the same workload (forward + loss + backward of loss, heads,
+    # all transformer blocks, adapter bottom paths and embeddings + fused AdamW + weight re-pack; convolutional front frozen)
+    train = None
+    if world == 1 and n_micro == 1 and args.precision == "bf16" and not args.no_train:
+        train = train_step_block(model, img_dev, tok_dev, B, cfg)
     cpu = None
     if not args.no_cpu:
         v, sec_step, cores, kind, desc = cpu_baseline(cfg, sd_np, args.cpu_sample, 3, 1)
@@ -579,6 +624,7 @@ def run_ours(args, cfg, rank, world, local):
         "loss": loss_value, "loss_expected_ln_G": math.log(B * world),
         "e2e": e2e, "gpu_launches": launches, "clocks": clock_summary, "roofline": roofline, "cpu_baseline": cpu,
         "device_bytes": int(L.msclip_device_bytes(h)), "comparators": comparators or None, "phases": phases,
+        "train_step": train,
     }
     emit(line)
 
@@ -620,6 +666,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"], help="MMA operand type (library build)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step figure")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if world != args.gpus and world == 1 and args.gpus > 1:

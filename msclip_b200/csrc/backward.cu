@@ -276,6 +276,20 @@ reduce_partials_kernel(const float* __restrict__ part, int nparts, long long pit
   }
 }
 
+// up to three destinations of width n from one partial buffer whose rows hold them side by side (dgamma | dbeta | colsum)
+__global__ void __launch_bounds__(256)
+reduce_partials3_kernel(const float* __restrict__ part, int nparts, long long pitch, float* __restrict__ d0, float* __restrict__ d1,
+                        float* __restrict__ d2, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 3 * n) return;
+  const int slot = j / n;
+  float* dst = slot == 0 ? d0 : (slot == 1 ? d1 : d2);
+  if (dst == nullptr) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[p * pitch + j];
+  dst[j - slot * n] += s;
+}
+
 // ---- heads ---------------------------------------------------------------------------------------------------------
 // dg = (df - f (f . df)) / ||g||, f = g / ||g||   (normalise = 0: dg = df); also the 16-bit copy for the projection GEMMs
 __global__ void __launch_bounds__(32 * kWarps)
@@ -594,6 +608,13 @@ int launch_reduce_partials(const float* part, int nparts, long long pitch, float
   if (n <= 0) return 0;
   const int grid = static_cast<int>((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
   reduce_partials_kernel<<<grid, 256, 0, stream>>>(part, nparts, pitch, dst, n, accumulate, head_n, head_scale);
+  MSCLIP_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// d0 / d1 / d2 [n] += column sums of part[:, 0:n] / [:, n:2n] / [:, 2n:3n] (null destinations are skipped)
+int launch_reduce_partials3(const float* part, int nparts, long long pitch, float* d0, float* d1, float* d2, int n, cudaStream_t stream) {
+  reduce_partials3_kernel<<<(3 * n + 255) / 256, 256, 0, stream>>>(part, nparts, pitch, d0, d1, d2, n);
   MSCLIP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

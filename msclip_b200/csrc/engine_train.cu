@@ -27,6 +27,13 @@ namespace {
 
 constexpr int kW = 768;
 
+// MSCLIP_BWD_FUSED_GELU=0: separate QuickGELU forward / backward kernels around a plain dgrad GEMM (A/B timing and the
+// comparator of the fused epilogue's parity test)
+const bool g_fused_dgelu = [] {
+  const char* e = getenv("MSCLIP_BWD_FUSED_GELU");
+  return e == nullptr || e[0] != '0';
+}();
+
 float* grad_find(msclip_ctx* h, const std::string& key) {
   for (auto& kv : h->grad_list)
     if (kv.first == key) return kv.second;
@@ -118,9 +125,13 @@ int get_scratch(msclip_ctx* h, int M, BwdScratch& b) {
   return 0;
 }
 
-// dx (gradient of the block output, fp32 [M, 768]) -> gradient of the block input (in place); parameter gradients accumulate
+// dx (gradient of the block output, fp32 [M, 768]) -> gradient of the block input (in place); parameter gradients accumulate.
+// g16_ready: b.g16 already holds op16(dx) and the fc2 bias gradient of this block has been taken (both were emitted by the
+// LayerNorm backward that ended the block above).  below: the block that consumes this block's dx next with nothing in
+// between (its fc2 bias gradient = column sums of our final dx), or null.
 int block_backward(msclip_ctx* h, const BlockWeights& bw, const BlockWeightsT& bt, const BlockGrads& bg, const float* x_in,
-                   float* dx, int batch, int L, int causal, const BwdScratch& b, cudaStream_t s) {
+                   float* dx, int batch, int L, int causal, const BwdScratch& b, bool g16_ready, const BlockGrads* below,
+                   cudaStream_t s) {
   const int w = kW, M = batch * L;
   const int rp = bwd_row_parts(M), sp = bwd_slab_parts(M);
   // ---- recompute the block's intermediates (the forward's kernels; fc1 keeps the pre-activation u)
@@ -130,21 +141,27 @@ int block_backward(msclip_ctx* h, const BlockWeights& bw, const BlockWeightsT& b
   MSCLIP_TRY(launch_gemm(b.ctx, w, bw.w_o, w, M, w, w, bw.b_o, b.x1, w, x_in, w, EPI_RESID_F32, s));
   MSCLIP_TRY(launch_layernorm_op16(b.x1, 1, bw.ln2_w, bw.ln2_b, b.h2, M, s));
   MSCLIP_TRY(launch_gemm(b.h2, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, b.u, 4 * w, nullptr, 0, EPI_BF16, s));
-  MSCLIP_TRY(launch_qgelu_fwd(b.u, b.a, static_cast<long long>(M) * 4 * w, s));
   // ---- MLP (M.py:794-798, 1028)
-  MSCLIP_TRY(launch_cast_colsum(dx, b.g16, b.part, M, s));
-  MSCLIP_TRY(fold(b.part, rp, w, bg.b_fc2, w, s));
-  MSCLIP_TRY(launch_gemm(b.g16, w, bt.w_fc2_t, w, M, 4 * w, w, nullptr, b.da, 4 * w, nullptr, 0, EPI_BF16, s));
-  MSCLIP_TRY(launch_wgrad(b.g16, w, b.a, 4 * w, M, w, 4 * w, bg.w_fc2, 1, b.wg, s));
-  MSCLIP_TRY(launch_qgelu_bwd(b.da, b.u, b.part, M, 4 * w, s));
+  if (!g16_ready) {
+    MSCLIP_TRY(launch_cast_colsum(dx, b.g16, b.part, M, s));
+    MSCLIP_TRY(fold(b.part, rp, w, bg.b_fc2, w, s));
+  }
+  if (g_fused_dgelu) {
+    // d u = (d x2 . W2) * quickgelu'(u) and a = quickgelu(u) from ONE kernel: the dgrad GEMM's epilogue reads u
+    MSCLIP_TRY(launch_gemm_dgelu(b.g16, w, bt.w_fc2_t, w, M, 4 * w, w, b.u, b.da, b.a, s));
+    MSCLIP_TRY(launch_colsum16(b.da, b.part, M, 4 * w, s));
+  } else {
+    MSCLIP_TRY(launch_qgelu_fwd(b.u, b.a, static_cast<long long>(M) * 4 * w, s));
+    MSCLIP_TRY(launch_gemm(b.g16, w, bt.w_fc2_t, w, M, 4 * w, w, nullptr, b.da, 4 * w, nullptr, 0, EPI_BF16, s));
+    MSCLIP_TRY(launch_qgelu_bwd(b.da, b.u, b.part, M, 4 * w, s));
+  }
   MSCLIP_TRY(fold(b.part, sp, 4 * w, bg.b_fc1, 4 * w, s));
+  MSCLIP_TRY(launch_wgrad(b.g16, w, b.a, 4 * w, M, w, 4 * w, bg.w_fc2, 1, b.wg, s));
   MSCLIP_TRY(launch_wgrad(b.da, 4 * w, b.h2, w, M, 4 * w, w, bg.w_fc1, 1, b.wg, s));
   MSCLIP_TRY(launch_gemm(b.da, 4 * w, bt.w_fc1_t, 4 * w, M, w, 4 * w, nullptr, b.tmp32, w, nullptr, 0, EPI_F32, s));
   // dx1 = dx2 + LN2'(dh2); its 16-bit copy feeds out-proj's dgrad / wgrad, its column sums are out-proj's bias gradient
   MSCLIP_TRY(launch_ln_bwd(b.x1, b.tmp32, bw.ln2_w, dx, b.g16, b.part, M, 1, s));
-  MSCLIP_TRY(fold(b.part, rp, 3 * w, bg.ln2_w, w, s));
-  MSCLIP_TRY(fold(b.part + w, rp, 3 * w, bg.ln2_b, w, s));
-  MSCLIP_TRY(fold(b.part + 2 * w, rp, 3 * w, bg.b_o, w, s));
+  MSCLIP_TRY(launch_reduce_partials3(b.part, rp, 3 * w, bg.ln2_w, bg.ln2_b, bg.b_o, w, s));
   // ---- attention (M.py:612, 707-747, 1027)
   MSCLIP_TRY(launch_gemm(b.g16, w, bt.w_o_t, w, M, w, w, nullptr, b.dctx, w, nullptr, 0, EPI_BF16, s));
   MSCLIP_TRY(launch_wgrad(b.g16, w, b.ctx, w, M, w, w, bg.w_o, 1, b.wg, s));
@@ -153,10 +170,10 @@ int block_backward(msclip_ctx* h, const BlockWeights& bw, const BlockWeightsT& b
   MSCLIP_TRY(fold(b.part, sp, 3 * w, bg.b_qkv, 3 * w, s));
   MSCLIP_TRY(launch_wgrad(b.dqkv, 3 * w, b.h1, w, M, 3 * w, w, bg.w_qkv, 1, b.wg, s));
   MSCLIP_TRY(launch_gemm(b.dqkv, 3 * w, bt.w_qkv_t, 3 * w, M, w, 3 * w, nullptr, b.tmp32, w, nullptr, 0, EPI_F32, s));
-  MSCLIP_TRY(launch_ln_bwd(x_in, b.tmp32, bw.ln1_w, dx, nullptr, b.part, M, 1, s));
-  MSCLIP_TRY(fold(b.part, rp, 3 * w, bg.ln1_w, w, s));
-  MSCLIP_TRY(fold(b.part + w, rp, 3 * w, bg.ln1_b, w, s));
-  count_launch(7 + 2 + 1 + 2 + 2 + 2 + 1 + 4 + 1 + 2 + 1 + 2 + 2 + 1 + 3);
+  // the block below starts from this dx: hand it the 16-bit copy and its fc2 bias gradient now
+  MSCLIP_TRY(launch_ln_bwd(x_in, b.tmp32, bw.ln1_w, dx, below ? b.g16 : nullptr, b.part, M, 1, s));
+  MSCLIP_TRY(launch_reduce_partials3(b.part, rp, 3 * w, bg.ln1_w, bg.ln1_b, below ? below->b_fc2 : nullptr, w, s));
+  count_launch(6 + (g16_ready ? 0 : 2) + (g_fused_dgelu ? 2 : 3) + 1 + 4 + 1 + 2 + 2 + 2 + 1 + 2 + 2 + 1 + 2);
   return 0;
 }
 
@@ -202,7 +219,8 @@ int text_backward(msclip_ctx* h, const float* d_txt, cudaStream_t s) {
   for (int idx = c.layers - 1; idx >= 0; --idx) {
     const float* xin = static_cast<const float*>(tape_get(h, "t_x" + std::to_string(idx)));
     MSCLIP_REQUIRE(xin != nullptr, "backward: incomplete text tape");
-    MSCLIP_TRY(block_backward(h, h->tblocks[idx], h->tblocks_t[idx], h->tgrads[idx], xin, dx, B, L, 1, b, s));
+    MSCLIP_TRY(block_backward(h, h->tblocks[idx], h->tblocks_t[idx], h->tgrads[idx], xin, dx, B, L, 1, b, idx != c.layers - 1,
+                              idx > 0 ? &h->tgrads[idx - 1] : nullptr, s));
   }
   MSCLIP_TRY(launch_text_embed_bwd(dx, tok, c.context_length, L, B, c.vocab_size, grad_find(h, "positional_embedding"),
                                    grad_find(h, "token_embedding.weight"), s));
@@ -227,10 +245,15 @@ int image_backward(msclip_ctx* h, const float* d_img, cudaStream_t s) {
                            grad_find(h, "visual.proj"), grad_find(h, "visual.ln_post.weight"), grad_find(h, "visual.ln_post.bias"), dx,
                            b, s));
   const int n_active = active_adapters(h);
+  bool g16_ready = false;
   for (int idx = c.layers - 1; idx >= 1; --idx) {
     const float* xin = static_cast<const float*>(tape_get(h, "v_x" + std::to_string(idx)));
     MSCLIP_REQUIRE(xin != nullptr, "backward: incomplete image tape");
-    MSCLIP_TRY(block_backward(h, h->vblocks[idx], h->vblocks_t[idx], h->vgrads[idx], xin, dx, B, L, 0, b, s));
+    bool adapter_here = false;
+    for (int j = 0; j < n_active; ++j) adapter_here |= kLateralLayers[j] == idx;
+    MSCLIP_TRY(block_backward(h, h->vblocks[idx], h->vblocks_t[idx], h->vgrads[idx], xin, dx, B, L, 0, b, g16_ready,
+                              (idx > 1 && !adapter_here) ? &h->vgrads[idx - 1] : nullptr, s));
+    g16_ready = idx > 1 && !adapter_here;
     for (int j = 0; j < n_active; ++j) {
       if (kLateralLayers[j] != idx) continue;
       // lateral adapter in front of this block: x_in = ln_adapt(2 cls | dw3x3(x) + t)  (M.py:1760-1777)

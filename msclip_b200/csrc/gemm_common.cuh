@@ -51,6 +51,8 @@ struct GemmParams {
   long long ldo, ldr;
   float alpha;  // acc is scaled by alpha before the bias (similarity logits: exp(logit_scale))
   int vec_ok;   // rows of out / resid keep 16-byte alignment -> vector stores
+  const op16* aux16;     // EPI_DGELU_BF16: u (fc1 pre-activation), pitch ldo
+  op16* out2;            // EPI_DGELU_BF16: quickgelu(u), pitch ldo
   uint32_t operand_fmt;  // kind::f16 A/B format field (0 = F16, 1 = BF16): the loss backward runs fp16 operands in both builds
   long long split_stride;  // != 0: column tile j writes a separate [M, BN] matrix at out + j * split_stride (elements)
   // LayerNorm folded into the GEMMs around it (kernel template parameter LN, see below)
@@ -133,6 +135,7 @@ struct EpiOperands {
   float4 resid_even[(EPI == EPI_RESID_F32) ? CH / 8 : 1];  // even row of the lane pair, pieces 2j + (lane & 1)
   float4 resid_odd[(EPI == EPI_RESID_F32) ? CH / 8 : 1];   // odd row of the lane pair
   float4 colsum[(LN == 1) ? CH / 4 : 1];
+  uint4 aux[(EPI == EPI_DGELU_BF16) ? CH / 8 : 1];  // this thread's own row of u, CH consecutive columns
 };
 
 template <int EPI, int CH, int LN = 0>
@@ -152,6 +155,16 @@ __device__ __forceinline__ void epilogue_prefetch(EpiOperands<EPI, CH, LN>& o, c
 #pragma unroll
     for (int j = 0; j < CH / 4; ++j) o.bias[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (EPI == EPI_DGELU_BF16) {
+    if (row < p.M) {
+      const uint4* up = reinterpret_cast<const uint4*>(p.aux16 + static_cast<long long>(row) * p.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < CH / 8; ++j) o.aux[j] = __ldg(up + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH / 8; ++j) o.aux[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   if (EPI == EPI_RESID_F32) {
     const int par = threadIdx.x & 1;
     const int row_e = row & ~1, row_o = row | 1;
@@ -163,6 +176,28 @@ __device__ __forceinline__ void epilogue_prefetch(EpiOperands<EPI, CH, LN>& o, c
       o.resid_even[j] = row_e < p.M ? xe[2 * j + par] : z;
       o.resid_odd[j] = row_o < p.M ? xo[2 * j + par] : z;
     }
+  }
+}
+
+// 16-bit results of a lane's own row (CH columns as CH / 2 packed words) -> global memory through the lane-pair swap
+template <int CH>
+__device__ __forceinline__ void store16_swapped(const uint32_t (&u)[CH / 2], op16* base, long long ld, int row_e, int row_o, int col0,
+                                                bool ok_e, bool ok_o, bool par) {
+  uint4* oe = reinterpret_cast<uint4*>(base + static_cast<long long>(row_e) * ld + col0);
+  uint4* oo = reinterpret_cast<uint4*>(base + static_cast<long long>(row_o) * ld + col0);
+#pragma unroll
+  for (int j = 0; j < CH / 16; ++j) {
+    uint32_t e[4], d[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t lo = u[8 * j + t], hi = u[8 * j + 4 + t];
+      const uint32_t keep = par ? hi : lo;
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, par ? lo : hi, 1);
+      e[t] = par ? recv : keep;
+      d[t] = par ? keep : recv;
+    }
+    if (ok_e) oe[2 * j + par] = make_uint4(e[0], e[1], e[2], e[3]);
+    if (ok_o) oo[2 * j + par] = make_uint4(d[0], d[1], d[2], d[3]);
   }
 }
 
@@ -263,24 +298,26 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
   } else {
     // pieces = uint4 (8 columns of 16-bit values)
     uint32_t u[CH / 2];
+    if (EPI == EPI_DGELU_BF16) {
+      // v = d a (gradient of the fc2 input); aux = u.  sigmoid with one MUFU op as in quick_gelu()
+      uint32_t act[CH / 2];
+      const op162* uu = reinterpret_cast<const op162*>(o.aux);
 #pragma unroll
-    for (int j = 0; j < CH / 2; ++j) u[j] = pack16(v[2 * j], v[2 * j + 1]);
-    uint4* oe = reinterpret_cast<uint4*>(reinterpret_cast<op16*>(p.out) + static_cast<long long>(row_e) * p.ldo + col0);
-    uint4* oo = reinterpret_cast<uint4*>(reinterpret_cast<op16*>(p.out) + static_cast<long long>(row_o) * p.ldo + col0);
-#pragma unroll
-    for (int j = 0; j < CH / 16; ++j) {
-      uint32_t e[4], d[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const uint32_t lo = u[8 * j + t], hi = u[8 * j + 4 + t];
-        const uint32_t keep = par ? hi : lo;
-        const uint32_t recv = __shfl_xor_sync(0xffffffffu, par ? lo : hi, 1);
-        e[t] = par ? recv : keep;
-        d[t] = par ? keep : recv;
+      for (int j = 0; j < CH / 2; ++j) {
+        const float2 x = op162_to_float2(uu[j]);
+        float t0, t1;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.851f * x.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.851f * x.y));
+        const float s0 = fmaf(0.5f, t0, 0.5f), s1 = fmaf(0.5f, t1, 0.5f);
+        act[j] = pack16(x.x * s0, x.y * s1);
+        u[j] = pack16(v[2 * j] * s0 * fmaf(1.702f * x.x, 1.0f - s0, 1.0f), v[2 * j + 1] * s1 * fmaf(1.702f * x.y, 1.0f - s1, 1.0f));
       }
-      if (ok_e) oe[2 * j + par] = make_uint4(e[0], e[1], e[2], e[3]);
-      if (ok_o) oo[2 * j + par] = make_uint4(d[0], d[1], d[2], d[3]);
+      store16_swapped<CH>(act, p.out2, p.ldo, row_e, row_o, col0, ok_e, ok_o, par);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) u[j] = pack16(v[2 * j], v[2 * j + 1]);
     }
+    store16_swapped<CH>(u, reinterpret_cast<op16*>(p.out), p.ldo, row_e, row_o, col0, ok_e, ok_o, par);
   }
 }
 

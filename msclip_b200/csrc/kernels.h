@@ -59,6 +59,10 @@ enum GemmEpilogue {
   EPI_RELU_BF16 = 2,   // op16 out = relu(acc + bias)               (conv + folded BN + ReLU)
   EPI_RESID_F32 = 3,   // f32  out = resid + acc + bias             (residual stream, may alias out)
   EPI_F32 = 4,         // f32  out = acc + bias
+  // backward of the MLP (M.py:794-798): acc = d(fc2 input); aux = u, the fc1 pre-activation.  op16 out = acc * quickgelu'(u)
+  // (= d u) and op16 out2 = quickgelu(u) (the fc2 input the weight gradient needs): both QuickGELU passes of the backward
+  // ride on the dgrad GEMM's epilogue instead of two more trips over the [M, 3072] tensors
+  EPI_DGELU_BF16 = 5,
 };
 int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
                 void* out, int64_t ldo, const float* resid, int64_t ldr, int epi, cudaStream_t stream);
@@ -68,6 +72,9 @@ int launch_gemm_split(const op16* A, int64_t lda, const op16* W, int64_t ldw, in
 // fp16 operands in either build (only 16-bit-out / f32-out epilogues without bias or residual): the loss backward
 int launch_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, float alpha, void* out, int64_t ldo,
                     int epi, cudaStream_t stream);
+// du = (A . W^T) * quickgelu'(u), a = quickgelu(u)   (EPI_DGELU_BF16; N % 256 == 0, all pitches = N)
+int launch_gemm_dgelu(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const op16* u, op16* du, op16* a,
+                      cudaStream_t stream);
 void gemm_set_pair_mode(int mode);  // 0: 1 CTA per tile, 1: CTA pairs, 2|4: multicast clusters of 2|4 pairs
 int launch_gemm_scaled(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, float alpha,
                        const float* bias, void* out, int64_t ldo, const float* resid, int64_t ldr, int epi,
@@ -215,6 +222,7 @@ int bwd_row_parts(long long rows);   // CTAs (= partial rows) of the 768-wide ro
 int bwd_slab_parts(long long rows);  // partial rows of the 16-bit slab kernels (qgelu_bwd, colsum16)
 int launch_reduce_partials(const float* part, int nparts, long long pitch, float* dst, long long n, int accumulate,
                            long long head_n, float head_scale, cudaStream_t stream);
+int launch_reduce_partials3(const float* part, int nparts, long long pitch, float* d0, float* d1, float* d2, int n, cudaStream_t stream);
 // dx (+)= LN_backward(dy; x, gamma); g16 (optional) = op16(dx); part [bwd_row_parts][3 * 768] = dgamma | dbeta | colsum(dx)
 int launch_ln_bwd(const float* x, const float* dy, const float* gamma, float* dx, op16* g16, float* part, long long rows,
                   int accumulate, cudaStream_t stream);

@@ -79,6 +79,35 @@ def main():
         dt = torch.cat(parts_t) - gt_all
         out["grad_image_rel"] = float(di.norm() / gi_all.norm())
         out["grad_text_rel"] = float(dt.norm() / gt_all.norm())
+    # ---- training step: every rank runs loss_and_backward on its shard (the loss backward reads
+    # the peers' row lse in-kernel), the LOCAL parameter gradients are summed with one NCCL all-reduce per tensor (what DDP
+    # does), and the result must equal the single-process gradient of the global-batch loss
+    if os.environ.get("MSCLIP_PRECISION", "bf16") == "bf16":
+        model.enable_training()
+        model.zero_grad()
+        out["train_loss_p2p"] = float(model.loss_and_backward(img, tok))
+        params = model.trainable_parameters()
+        uniq = {}
+        for k, p in params.items():
+            uniq.setdefault(p.data_ptr(), (k, p))
+        for _k, p in uniq.values():
+            dist.all_reduce(p.grad)
+        if rank == 0:
+            solo.enable_training()
+            solo.zero_grad()
+            out["train_loss_single"] = float(solo.loss_and_backward(img_all, tok_all))
+            ref = solo.trainable_parameters()
+            num = den = 0.0
+            worst = ("", 0.0)
+            for k, p in uniq.values():
+                d = float((p.grad - ref[k].grad).double().norm())
+                r = float(ref[k].grad.double().norm())
+                num += d * d
+                den += r * r
+                if r > 0 and d / r > worst[1]:
+                    worst = (k, d / r)
+            out["train_grad_aggregate_rel"] = (num / max(den, 1e-300)) ** 0.5
+            out["train_grad_worst"] = list(worst)
     dist.barrier()
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(out), flush=True)
