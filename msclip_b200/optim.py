@@ -63,6 +63,22 @@ class AdamW:
     def zero_grad(self) -> None:
         self.model.zero_grad()
 
+    def state_dict(self):
+        """{'steps', 'betas', 'eps', 'state': {key: (exp_avg, exp_avg_sq)}, 'groups': {key: (lr, weight_decay)}} on the CPU."""
+        return {"steps": self.steps, "betas": tuple(self.betas), "eps": self.eps,
+                "state": {k: (m.detach().cpu().clone(), v.detach().cpu().clone()) for k, (m, v) in self.state.items()},
+                "groups": {e[0]: (e[2], e[3]) for e in self.entries}}
+
+    def load_state_dict(self, sd) -> None:
+        self.steps = int(sd["steps"])
+        self.betas, self.eps = tuple(sd["betas"]), float(sd["eps"])
+        for e in self.entries:
+            m, v = sd["state"][e[0]]
+            self.state[e[0]][0].copy_(m)
+            self.state[e[0]][1].copy_(v)
+            if e[0] in sd.get("groups", {}):
+                e[2], e[3] = (float(x) for x in sd["groups"][e[0]])
+
     @torch.no_grad()
     def step(self) -> None:
         self.steps += 1

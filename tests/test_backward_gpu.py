@@ -352,3 +352,37 @@ def test_adamw_step_trains_and_refreshes_packed_weights():
     _record("adamw_training", {"losses": losses, "final": final, "fresh_handle": ref_final})
     assert final < losses[0], (losses, final)
     assert abs(final - ref_final) <= 1e-5 * abs(ref_final) + 1e-7, (final, ref_final)
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """Training-format checkpoint of the reference (lib/utils/utils.py:157-199, with the DDP `module.` prefix): save after two
+    steps, load into a fresh model + optimiser, and the third step must produce bit-identical weights."""
+    from msclip_b200.checkpoint import load_checkpoint, save_checkpoint
+    from msclip_b200.optim import AdamW
+    cfg = MSCLIPConfig(patch_size=32, layers=2)
+    sd_np = synth.synth_state_dict(cfg, seed=12, logit_scale=math.log(10.0))
+    img, tok = synth.correlated_pair_batch(cfg, 6, seed=4)
+    timg, ttok = torch.from_numpy(img).cuda(), torch.from_numpy(tok).cuda()
+
+    def one_step(model, opt):
+        opt.zero_grad()
+        loss = float(model.loss_and_backward(timg, ttok))
+        opt.step()
+        return loss
+
+    a = build_train_model(cfg, sd_np)
+    oa = AdamW(a, lr=3e-4, weight_decay=0.05, lr_share=1e-4, wd_share=0.2)
+    for _ in range(2):
+        one_step(a, oa)
+    path = str(tmp_path / "checkpoint.pth")
+    saved = save_checkpoint(a, path, oa, epoch_or_step=1, in_epoch=False, distributed=True)
+    assert saved["step"] == 2 and all(k.startswith("module.") for k in saved["state_dict"])
+    b = build_train_model(cfg, synth.synth_state_dict(cfg, seed=99))
+    ob = AdamW(b, lr=1.0)
+    meta = load_checkpoint(b, path, ob)
+    assert meta["step"] == 2 and meta["model"] == "clip_openai_pe_res_v1"
+    la, lb = one_step(a, oa), one_step(b, ob)
+    assert la == lb, (la, lb)
+    for (k, pa), (_k, pb) in zip(a.state_dict().items(), b.state_dict().items()):
+        if pa.dtype == torch.float32 and "token_embedding" not in k:      # the embedding scatter uses fp32 atomics
+            assert torch.equal(pa, pb), k
