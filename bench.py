@@ -301,7 +301,7 @@ def nccl_loss_comparator(model, L, h, dev, B, world, sp, scale):
                     "gather + fused similarity/CE); comparator = 2 x dist.all_gather + [G,G] logits + 2 x F.cross_entropy"}
 
 
-def train_step_block(model, img_dev, tok_dev, B, cfg, steps: int = 3, warmup: int = 1):
+def train_step_block(model, img_dev, tok_dev, B, cfg, steps: int = 4, warmup: int = 2):
     """Device-timed training step (secondary figure, not the headline metric): pairs/s and the tensor-roofline fraction with
     3 x the transformer FLOPs of the forward (forward + dgrad + wgrad) + 1 x the frozen convolutional front."""
     try:
@@ -319,17 +319,18 @@ def train_step_block(model, img_dev, tok_dev, B, cfg, steps: int = 3, warmup: in
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
             step()
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        ms = evs[0].elapsed_time(evs[steps]) / steps
         gf = (3.0 * (23.549 - 2.379) + 2.379) if cfg.patch_size == 32 else None      # GFLOP: BASELINE.md section 3 (pair 23.549, convs 2.379)
         pk = peaks()
         pairs_s = B / ms * 1e3
-        out = {"ms_per_step": ms, "value": pairs_s, "unit": "pairs/s", "steps": steps, "warmup": warmup,
+        out = {"ms_per_step": ms, "ms_each_step": per_step, "value": pairs_s, "unit": "pairs/s", "steps": steps, "warmup": warmup,
                "what": "msclip_forward_loss (taped) + msclip_contrastive_loss_backward + msclip_backward + msclip_op_adamw + msclip_update_weight",
                "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
                "device_bytes": int(model._library().msclip_device_bytes(model._handle))}

@@ -107,13 +107,28 @@ int msclip_op_qgelu_bwd(void* da, const void* u, float* dbias, int rows, int wid
   if (dbias) MSCLIP_TRY(launch_reduce_partials(part, bwd_slab_parts(rows), width, dbias, width, 1, 0, 1.0f, s));
   return 0;
 }
+// Tensor table + chunk map of the last calls, kept on the device: two slots (pinned staging + device copy each).  A call
+// whose table equals the one already resident (same tensors, same lr / weight decay - every step of a constant-lr run)
+// uploads nothing; otherwise the other slot is refilled once the kernel that last read it has finished.  No stream
+// synchronisation, no allocation in the steady state: the optimiser step never stalls the host.
+namespace {
+struct AdamwSlot {
+  uint8_t* pinned = nullptr;
+  uint8_t* dev = nullptr;
+  size_t cap = 0;
+  std::vector<uint8_t> content;
+  cudaEvent_t used = nullptr;
+};
+AdamwSlot g_adamw_slot[2];
+int g_adamw_cur = 0;
+}  // namespace
+
 int msclip_op_adamw(int n, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                     const int64_t* numel, const float* lr, const float* weight_decay, float beta1, float beta2, float eps, int step,
                     void* stream) {
   MSCLIP_REQUIRE(n >= 0 && step >= 1, "msclip_op_adamw: bad arguments");
   if (n == 0) return 0;
-  // tensor table + chunk map (64 Ki elements per chunk) staged through one stream-ordered device allocation
-  constexpr int kChunk = 65536;
+  constexpr int kChunk = 65536;  // elements per work item
   std::vector<AdamwTensor> tab(n);
   std::vector<int> ct;
   std::vector<long long> co;
@@ -126,20 +141,33 @@ int msclip_op_adamw(int n, float* const* params, const float* const* grads, floa
   }
   const size_t b0 = tab.size() * sizeof(AdamwTensor), b1 = ct.size() * sizeof(int), b2 = co.size() * sizeof(long long);
   const size_t o1 = (b0 + 15) & ~size_t(15), o2 = (o1 + b1 + 15) & ~size_t(15);
-  std::vector<uint8_t> host(o2 + b2);
+  std::vector<uint8_t> host(o2 + b2, 0);
   memcpy(host.data(), tab.data(), b0);
   memcpy(host.data() + o1, ct.data(), b1);
   memcpy(host.data() + o2, co.data(), b2);
   cudaStream_t s = as_stream(stream);
-  uint8_t* dev = nullptr;
-  MSCLIP_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), host.size(), s));
-  MSCLIP_CHECK_CUDA(cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, s));
-  MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));  // the pageable host table must outlive the copy
-  const int rc = launch_adamw(reinterpret_cast<const AdamwTensor*>(dev), reinterpret_cast<const int*>(dev + o1),
-                              reinterpret_cast<const long long*>(dev + o2), static_cast<int>(ct.size()), kChunk, beta1, beta2, eps,
-                              step, s);
-  MSCLIP_CHECK_CUDA(cudaFreeAsync(dev, s));
-  return rc;
+  AdamwSlot* slot = &g_adamw_slot[g_adamw_cur];
+  if (slot->content != host) {
+    g_adamw_cur ^= 1;
+    slot = &g_adamw_slot[g_adamw_cur];
+    if (slot->used) MSCLIP_CHECK_CUDA(cudaEventSynchronize(slot->used));  // last reader of this slot (two steps ago)
+    if (slot->cap < host.size()) {
+      if (slot->pinned) cudaFreeHost(slot->pinned);
+      if (slot->dev) cudaFree(slot->dev);
+      slot->cap = host.size() * 2;
+      MSCLIP_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&slot->pinned), slot->cap, cudaHostAllocDefault));
+      MSCLIP_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&slot->dev), slot->cap));
+    }
+    if (!slot->used) MSCLIP_CHECK_CUDA(cudaEventCreateWithFlags(&slot->used, cudaEventDisableTiming));
+    memcpy(slot->pinned, host.data(), host.size());
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(slot->dev, slot->pinned, host.size(), cudaMemcpyHostToDevice, s));
+    slot->content = host;
+  }
+  const uint8_t* dev = slot->dev;
+  MSCLIP_TRY(launch_adamw(reinterpret_cast<const AdamwTensor*>(dev), reinterpret_cast<const int*>(dev + o1),
+                          reinterpret_cast<const long long*>(dev + o2), static_cast<int>(ct.size()), kChunk, beta1, beta2, eps, step, s));
+  MSCLIP_CHECK_CUDA(cudaEventRecord(slot->used, s));
+  return 0;
 }
 
 int msclip_num_keys(msclip_handle h) { return h ? static_cast<int>(h->spec.size()) : -1; }
@@ -189,7 +217,7 @@ int msclip_finalize_weights(msclip_handle h, void* stream) {
 
 int msclip_logit_scale_exp(msclip_handle h, float* out) {
   MSCLIP_REQUIRE(h != nullptr && out != nullptr && h->finalized, "msclip_logit_scale_exp: weights not finalized");
-  *out = expf(h->logit_scale);
+  *out = expf(current_logit_scale(h));
   return 0;
 }
 

@@ -298,6 +298,7 @@ int engine_finalize(msclip_ctx* h, cudaStream_t stream) {
   {
     std::vector<float> ls = P.host("logit_scale");
     h->logit_scale = ls.empty() ? 0.f : ls[0];
+    h->ls_pending = false;
   }
   std::vector<float> qs(3 * w, 1.0f);
   for (int i = 0; i < w; ++i) qs[i] = 0.125f;
@@ -487,6 +488,15 @@ int ws_get(msclip_ctx* h, const char* name, size_t bytes, void** out) {
   }
   *out = b.p;
   return 0;
+}
+
+float current_logit_scale(msclip_ctx* h) {
+  if (h->ls_pending) {
+    cudaEventSynchronize(h->ls_event);
+    h->logit_scale = *h->ls_pinned;
+    h->ls_pending = false;
+  }
+  return h->logit_scale;
 }
 
 int tape_save(msclip_ctx* h, const std::string& name, const void* src, size_t bytes, cudaStream_t s) {
@@ -1375,7 +1385,7 @@ int engine_forward(msclip_ctx* h, const void* image, int dtype, const int64_t* t
   WS(ft, float, "fwd_txt", static_cast<size_t>(std::max(batch, 1)) * E);
   MSCLIP_TRY(encode_text_impl(h, tokens, batch, ft, 1, false, 0, s));
   MSCLIP_TRY(engine_encode_image(h, image, dtype, batch, fi, 1, s));
-  return engine_similarity_logits(h, fi, batch, ft, batch, std::exp(h->logit_scale), logits, s);
+  return engine_similarity_logits(h, fi, batch, ft, batch, std::exp(current_logit_scale(h)), logits, s);
 }
 
 __global__ void publish_kernel(uint32_t* const* flag_tables, int world, int rank, uint32_t epoch) {
@@ -1555,7 +1565,7 @@ int engine_encode_pairs(msclip_ctx* h, const void* image, int dtype, const int64
 int engine_forward_loss(msclip_ctx* h, const void* image, int dtype, const int64_t* tokens, int b_local,
                         float* partial_out, float* loss_out, cudaStream_t s) {
   MSCLIP_TRY(engine_encode_pairs(h, image, dtype, tokens, b_local, 0, s));
-  return engine_contrastive_loss(h, b_local, std::exp(h->logit_scale), partial_out, loss_out, s);
+  return engine_contrastive_loss(h, b_local, std::exp(current_logit_scale(h)), partial_out, loss_out, s);
 }
 
 }  // namespace msclip

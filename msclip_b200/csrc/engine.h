@@ -73,6 +73,11 @@ struct msclip_ctx {
   bool finalized = false;
   bool text_trim = true;  // encode_text runs the causal tower only over the longest live prefix (<= EOT) of the batch
   float logit_scale = 0.f;
+  // logit_scale refreshed from the device after an optimiser step: the read-back lands in pinned memory and is waited for
+  // only when the value is next needed (no host synchronisation inside the training step)
+  float* ls_pinned = nullptr;
+  cudaEvent_t ls_event = nullptr;
+  bool ls_pending = false;
   float* qscale_dev = nullptr;  // [3 * width]: 1/8 for the q rows of in_proj (M.py:707), 1 elsewhere
 
   // packed weights
@@ -187,6 +192,8 @@ void train_free(msclip_ctx* h);
 
 int engine_preprocess(msclip_ctx* h, const uint8_t* pixels, const int64_t* offsets, const int* heights, const int* widths, int n, int S,
                       const float* mean, const float* stdv, void* out, int out_dtype, uint8_t* out_u8, cudaStream_t s);
+
+float current_logit_scale(msclip_ctx* h);  // h->logit_scale, after any pending read-back has landed
 
 int64_t launch_count();
 void count_launch(int n);

@@ -327,6 +327,11 @@ int train_enable(msclip_ctx* h, int enable) {
 }
 
 void train_free(msclip_ctx* h) {
+  if (h->ls_pinned) cudaFreeHost(h->ls_pinned);
+  if (h->ls_event) cudaEventDestroy(h->ls_event);
+  h->ls_pinned = nullptr;
+  h->ls_event = nullptr;
+  h->ls_pending = false;
   for (auto& a : h->grad_allocs) cudaFree(a.first);
   h->grad_allocs.clear();
   h->grad_list.clear();
@@ -416,8 +421,15 @@ int engine_update_weight(msclip_ctx* h, const char* key_c, const float* src, cud
     return launch_pack_op16(src, E, 1, nullptr, n, E, w, E, s);
   }
   if (key == "logit_scale") {
-    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(&h->logit_scale, src, sizeof(float), cudaMemcpyDeviceToHost, s));
-    MSCLIP_CHECK_CUDA(cudaStreamSynchronize(s));
+    // asynchronous read-back into pinned memory; whoever needs the value next waits for it (current_logit_scale)
+    if (!h->ls_pinned) {
+      MSCLIP_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->ls_pinned), sizeof(float), cudaHostAllocDefault));
+      MSCLIP_CHECK_CUDA(cudaEventCreateWithFlags(&h->ls_event, cudaEventDisableTiming));
+    }
+    if (h->ls_pending) MSCLIP_CHECK_CUDA(cudaEventSynchronize(h->ls_event));
+    MSCLIP_CHECK_CUDA(cudaMemcpyAsync(h->ls_pinned, src, sizeof(float), cudaMemcpyDeviceToHost, s));
+    MSCLIP_CHECK_CUDA(cudaEventRecord(h->ls_event, s));
+    h->ls_pending = true;
     return 0;
   }
   for (int j = 0; j < active_adapters(h); ++j) {

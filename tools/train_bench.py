@@ -157,6 +157,23 @@ def main():
         step_ms = time_ms(step, args.reps, warm=2)
         wall = time.time() - t0
 
+        # per-step device times + SM clock / power samples (a bimodal step time would otherwise hide in the mean)
+        import subprocess
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(13)]
+        samples = []
+        evs[0].record()
+        for i in range(12):
+            step()
+            evs[i + 1].record()
+            q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,"
+                                "clocks_event_reasons.sw_thermal_slowdown,temperature.gpu", "--format=csv,noheader,nounits", "-i", "0"],
+                               capture_output=True, text=True).stdout.strip()
+            samples.append(q)
+        torch.cuda.synchronize()
+        each = [evs[i].elapsed_time(evs[i + 1]) for i in range(12)]
+        print("per-step ms:", [round(x, 1) for x in each], flush=True)
+        print("nvidia-smi after each step (sm MHz, W, power cap, hw slowdown, thermal, C):", samples, flush=True)
+
         def fb():
             opt.zero_grad()
             model.loss_and_backward(img, tok)
@@ -170,7 +187,7 @@ def main():
                "forward_backward_ms": fb_ms, "step_ms": step_ms, "optimizer_and_repack_ms": step_ms - fb_ms,
                "pairs_per_s": pairs_s, "gflop_per_pair_step": gf_step, "tflops": pairs_s * gf_step / 1e3,
                "frac_sustained_tensor": pairs_s * gf_step / 1e3 / peaks["tflops_sustained"],
-               "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+               "ms_each_step": each, "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
                "device_bytes": int(L.msclip_device_bytes(model._handle)), "torch_allocated": int(torch.cuda.memory_allocated()),
                "wall_s": wall}
         out["train_step"] = res
