@@ -157,22 +157,16 @@ def main():
         step_ms = time_ms(step, args.reps, warm=2)
         wall = time.time() - t0
 
-        # per-step device times + SM clock / power samples (a bimodal step time would otherwise hide in the mean)
-        import subprocess
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(13)]
-        samples = []
+        # per-step device times (a bimodal step time would otherwise hide in the mean; no subprocesses here: forking a process
+        # that maps 50 GB of device memory stalls the launching thread for hundreds of milliseconds)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
         evs[0].record()
-        for i in range(12):
+        for i in range(8):
             step()
             evs[i + 1].record()
-            q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,"
-                                "clocks_event_reasons.sw_thermal_slowdown,temperature.gpu", "--format=csv,noheader,nounits", "-i", "0"],
-                               capture_output=True, text=True).stdout.strip()
-            samples.append(q)
         torch.cuda.synchronize()
-        each = [evs[i].elapsed_time(evs[i + 1]) for i in range(12)]
+        each = [evs[i].elapsed_time(evs[i + 1]) for i in range(8)]
         print("per-step ms:", [round(x, 1) for x in each], flush=True)
-        print("nvidia-smi after each step (sm MHz, W, power cap, hw slowdown, thermal, C):", samples, flush=True)
 
         def fb():
             opt.zero_grad()
