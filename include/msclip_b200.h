@@ -180,6 +180,20 @@ int msclip_preprocess_images(msclip_handle h, const uint8_t* pixels, const int64
                              int n, int out_size, const float* mean3, const float* std3, void* out, int out_dtype, uint8_t* out_u8,
                              void* stream);
 
+/* ---- native BPE tokenizer (host code, no GPU) -----------------------------------------------------
+ * lib/dataset/languages/simple_tokenizer.py:64-166 restated: whitespace_clean -> lower -> CLIP pattern -> byte alphabet ->
+ * greedy pair merges -> ids.  `merges_text` = the decompressed text of the reference's own bpe_simple_vocab_16e6.txt.gz
+ * (not shipped here).  basic_clean (ftfy + html.unescape, :53-56) is left to the caller. */
+int msclip_tokenizer_create(const char* merges_text, int64_t length, void** tokenizer_out);
+int msclip_tokenizer_destroy(void* tokenizer);
+int msclip_tokenizer_info(void* tokenizer, int* vocab_size, int* sot_token, int* eot_token);
+/* SimpleTokenizer.encode of one cleaned UTF-8 text: returns the number of ids (or -1), writes at most `capacity` of them. */
+int64_t msclip_tokenizer_encode(void* tokenizer, const char* text, int64_t length, int32_t* ids_out, int64_t capacity);
+/* SimpleTokenizer.tokenize for n texts (text i = texts[offsets[i] .. offsets[i + 1])): out [n, context_length] int64 =
+ * [SOT] + ids + [EOT] truncated to context_length and zero padded; `threads` <= 0: all host cores. */
+int msclip_tokenizer_tokenize(void* tokenizer, const char* texts, const int64_t* offsets, int n, int context_length, int64_t* out,
+                              int threads);
+
 /* Micro-batching (BASELINE.json: global batch 32 768 on 1 / 2 / 4 GPUs): run both towers
  * for b_micro pairs and keep their normalised embeddings as rows [row_offset, row_offset + b_micro) of this rank's
  * shard of the NEXT msclip_contrastive_loss.  row_offset must be 0 (new shard) or the number of rows encoded so far;

@@ -73,6 +73,11 @@ _SIGNATURES = {
     "msclip_contrastive_loss_backward": (_I, [_P, _P, _P, _P]),
     "msclip_contrastive_loss_features": (_I, [_P, _P, _P, _I, _F, _P, _P, _P]),
     "msclip_preprocess_images": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "msclip_tokenizer_create": (_I, [C.c_char_p, _L, C.POINTER(_P)]),
+    "msclip_tokenizer_destroy": (_I, [_P]),
+    "msclip_tokenizer_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "msclip_tokenizer_encode": (_L, [_P, C.c_char_p, _L, _P, _L]),
+    "msclip_tokenizer_tokenize": (_I, [_P, C.c_char_p, _P, _I, _I, _P, _I]),
     "msclip_train_enable": (_I, [_P, _I]),
     "msclip_backward": (_I, [_P, _P, _P, _P]),
     "msclip_zero_grad": (_I, [_P, _P]),

@@ -21,8 +21,8 @@ SUFFIX = os.environ.get("MSCLIP_LIB_SUFFIX", "")
 LIB_PATHS = {"bf16": os.path.join(HERE, f"libmsclip_b200{SUFFIX}.so"), "fp16": os.path.join(HERE, f"libmsclip_b200_fp16{SUFFIX}.so")}
 LIB_PATH = LIB_PATHS["bf16"]
 SOURCES = ["runtime.cu", "gemm.cu", "conv_gemm.cu", "elementwise.cu", "conv.cu", "front.cu", "attention.cu", "loss.cu", "engine.cu", "api.cu",
-           "backward.cu", "wgrad.cu", "attention_bwd.cu", "engine_train.cu", "preprocess.cu"]
-HEADERS = ["common.cuh", "gemm_common.cuh", "rowops.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
+           "backward.cu", "wgrad.cu", "attention_bwd.cu", "engine_train.cu", "preprocess.cu", "tokenizer.cu"]
+HEADERS = ["unicode_tables.inc", "common.cuh", "gemm_common.cuh", "rowops.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "msclip_b200.h"),
            os.path.join("..", "..", "include", "msclip_b200_ops.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
