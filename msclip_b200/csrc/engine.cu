@@ -499,6 +499,22 @@ float current_logit_scale(msclip_ctx* h) {
   return h->logit_scale;
 }
 
+// MSCLIP_TRAIN_KEEP=0: the tape keeps only the block inputs (3 KB per token and block) and the backward recomputes everything
+// else; default: the taped forward also writes every block's QKV, attention output and mid-block stream into tape slots
+// (+9 KB per token and block, zero copies), which removes the QKV / attention / out-proj recompute from the backward -
+// used when that much memory is free (plus a margin), silently skipped otherwise.
+static const bool g_train_keep = [] {
+  const char* e = getenv("MSCLIP_TRAIN_KEEP");
+  return e == nullptr || e[0] != '0';
+}();
+static bool tape_can_keep(msclip_ctx* h, const std::string& probe, size_t extra_bytes) {
+  if (!g_train_keep) return false;
+  if (h->ws.count(probe) && h->ws[probe].bytes > 0) return true;  // already allocated by an earlier step
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  return free_b > extra_bytes + (size_t(40) << 30);  // leave room for the backward's scratch and the other tower
+}
+
 int tape_save(msclip_ctx* h, const std::string& name, const void* src, size_t bytes, cudaStream_t s) {
   void* dst = nullptr;
   MSCLIP_TRY(ws_get(h, ("tape:" + name).c_str(), bytes, &dst));
@@ -648,10 +664,15 @@ static const bool g_ln_warps = [] {
 // h_ready: hbuf already holds ln_1(x) of this block - written by the LayerNorm warps of the previous block's fc2 kernel.
 // next: the block that follows with nothing in between (its ln_1 is then produced by this block's fc2 kernel), or null.
 // Returns (through h_ready) whether hbuf holds ln_1 of `next` on return.
+// x_mid / x_out (training tape, default kernels only): the stream after the attention half goes to x_mid and the block's
+// output to x_out instead of back into x, so that x (a tape slot) keeps the block's input without any copy.
 static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, op16* hbuf,
-                     op16* qkv, op16* attn, op16* fc1, float** rec, bool* h_ready, const BlockWeights* next, cudaStream_t s) {
+                     op16* qkv, op16* attn, op16* fc1, float** rec, bool* h_ready, const BlockWeights* next, cudaStream_t s,
+                     float* x_mid = nullptr, float* x_out = nullptr) {
   const int w = h->cfg.width;
   const int M = batch * L;
+  float* xm = x_mid ? x_mid : x;
+  float* xo = x_out ? x_out : x;
   if (!g_ln_fold && g_ln_warps && M >= 256 && w == 768) {
     // out-proj and fc2 update the residual stream AND emit the LayerNorm the next GEMM consumes (gemm.cu, LN = 3)
     int launches = 5;
@@ -697,10 +718,10 @@ static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch,
   if (!have_h) MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln1_w, bw.ln1_b, hbuf, M, s));
   MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, qkv, 3 * w, nullptr, 0, EPI_BF16, s));
   MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
-  MSCLIP_TRY(launch_gemm(attn, w, bw.w_o, w, M, w, w, bw.b_o, x, w, x, w, EPI_RESID_F32, s));
-  MSCLIP_TRY(launch_layernorm_op16(x, 1, bw.ln2_w, bw.ln2_b, hbuf, M, s));
+  MSCLIP_TRY(launch_gemm(attn, w, bw.w_o, w, M, w, w, bw.b_o, xm, w, x, w, EPI_RESID_F32, s));
+  MSCLIP_TRY(launch_layernorm_op16(xm, 1, bw.ln2_w, bw.ln2_b, hbuf, M, s));
   MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
-  MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, x, w, x, w, EPI_RESID_F32, s));
+  MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, xo, w, xm, w, EPI_RESID_F32, s));
   count_launch(have_h ? 6 : 7);
   return 0;
 }
@@ -919,34 +940,53 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     float* xc = x;
     float* xo = x2;
     float* gt = gridtmp + static_cast<size_t>(b0) * g * g * w;
+    // training: keep what the backward pass re-reads (engine_train.cu) - the stem output, every block's input, every
+    // adapter's input and top-path term, the final stream and the un-normalised features.  With the default kernels the
+    // residual stream LIVES in the tape slots (every producer writes the slot its consumer will read): no copies.
+    const bool tape = h->train && batch <= kTrainMaxBatch;
+    const bool slots = tape && !g_ln_fold && !g_ln_warps;
+    const size_t xbytes = static_cast<size_t>(nb) * L * w * sizeof(float), gbytes = static_cast<size_t>(nb) * g * g * w * sizeof(float);
+    h->tape_img.valid = false;
+    auto adapter_at = [&](int idx) {
+      for (int j = 0; j < n_active; ++j)
+        if (kLateral[j] == idx) return j;
+      return -1;
+    };
+    // slot that must receive the stream entering layer idx (its adapter's input if it has one, else the block's input)
+    auto entry_slot = [&](int idx, float** out) -> int {
+      const int j = idx < c.layers ? adapter_at(idx) : -1;
+      const std::string nm = j >= 0 ? "tape:v_ax" + std::to_string(j) : "tape:v_x" + std::to_string(std::min(idx, c.layers));
+      return ws_get(h, nm.c_str(), xbytes, reinterpret_cast<void**>(out));
+    };
+    if (slots) MSCLIP_TRY(entry_slot(1, &xc));
+    const size_t mrows = static_cast<size_t>(nb) * L;
+    const bool keep = slots && tape_can_keep(h, "tape:v_qkv1", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4));
+    h->tape_img.keep = keep;
     // the kernels that produce the residual stream also emit ln_1 of the block that consumes it next
-    bool adapter_first = false;
-    for (int j = 0; j < n_active; ++j) adapter_first |= kLateral[j] == 1;
+    const bool adapter_first = adapter_at(1) >= 0;
     const bool emit1 = !g_ln_fold && c.layers > 1 && !adapter_first;
     MSCLIP_TRY(launch_image_embed_ln_pre(gt, h->cls, h->vpos, h->ln_pre_w, h->ln_pre_b, xc, nb, L, xcen, rec[0],
                                          emit1 ? h->vblocks[1].ln1_w : nullptr, emit1 ? h->vblocks[1].ln1_b : nullptr,
                                          emit1 ? hbuf : nullptr, s));
     count_launch(1);
-    // training: keep what the backward pass re-reads (engine_train.cu) - the stem output, every block's input, every
-    // adapter's input and top-path term, the final stream and the un-normalised features
-    const bool tape = h->train && batch <= kTrainMaxBatch;
-    const size_t xbytes = static_cast<size_t>(nb) * L * w * sizeof(float), gbytes = static_cast<size_t>(nb) * g * g * w * sizeof(float);
-    h->tape_img.valid = false;
     if (tape) MSCLIP_TRY(tape_save(h, "v_grid", gt, gbytes, s));
     bool h_ready = emit1;
     for (int idx = 1; idx < c.layers; ++idx) {
-      for (int j = 0; j < n_active; ++j) {
-        if (kLateral[j] != idx) continue;
+      const int j = adapter_at(idx);
+      if (j >= 0) {
         const AdapterWeights& a = h->adapters[j];
         // t = pw_conv(BN(dw_conv(top)))  (M.py:1756-1759); the stem output in gridtmp is dead by now
+        float* tj = gt;
+        if (slots) MSCLIP_TRY(ws_get(h, ("tape:v_at" + std::to_string(j)).c_str(), gbytes, reinterpret_cast<void**>(&tj)));
         MSCLIP_TRY(launch_gemm(pooled[j] + static_cast<size_t>(b0) * g * g * a.C, a.C, a.pw, a.C, nb * g * g, w, a.C,
-                               nullptr, gt, w, nullptr, 0, EPI_F32, s));
-        if (tape) {
+                               nullptr, tj, w, nullptr, 0, EPI_F32, s));
+        if (tape && !slots) {
           MSCLIP_TRY(tape_save(h, "v_ax" + std::to_string(j), xc, xbytes, s));
           MSCLIP_TRY(tape_save(h, "v_at" + std::to_string(j), gt, gbytes, s));
         }
+        if (slots) MSCLIP_TRY(ws_get(h, ("tape:v_x" + std::to_string(idx)).c_str(), xbytes, reinterpret_cast<void**>(&xo)));
         const bool emit = !g_ln_fold;
-        MSCLIP_TRY(launch_adapter_fuse_ln(xc, gt, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, xcen, rec[0],
+        MSCLIP_TRY(launch_adapter_fuse_ln(xc, tj, a.bdw_w9, a.bdw_b, a.ln_w, a.ln_b, xo, nb, g, xcen, rec[0],
                                           emit ? h->vblocks[idx].ln1_w : nullptr, emit ? h->vblocks[idx].ln1_b : nullptr,
                                           emit ? hbuf : nullptr, s));
         count_launch(2);
@@ -954,13 +994,23 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         h_ready = emit;
       }
       // the next block's ln_1 can ride on this block's fc2 unless a lateral adapter rewrites x in between
-      bool adapter_next = false;
-      for (int j = 0; j < n_active; ++j) adapter_next |= kLateral[j] == idx + 1;
+      const bool adapter_next = adapter_at(idx + 1) >= 0;
       const BlockWeights* next = (idx + 1 < c.layers && !adapter_next) ? &h->vblocks[idx + 1] : nullptr;
-      if (tape) MSCLIP_TRY(tape_save(h, "v_x" + std::to_string(idx), xc, xbytes, s));
-      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv, attn, fc1, rec, &h_ready, next, s));
+      if (tape && !slots) MSCLIP_TRY(tape_save(h, "v_x" + std::to_string(idx), xc, xbytes, s));
+      float* x_next = nullptr;
+      if (slots) MSCLIP_TRY(entry_slot(idx + 1, &x_next));
+      op16 *qkv_i = qkv, *attn_i = attn;
+      float* xmid_i = slots ? x : nullptr;
+      if (keep) {
+        const std::string t = std::to_string(idx);
+        MSCLIP_TRY(ws_get(h, ("tape:v_qkv" + t).c_str(), mrows * 3 * w * sizeof(op16), reinterpret_cast<void**>(&qkv_i)));
+        MSCLIP_TRY(ws_get(h, ("tape:v_ctx" + t).c_str(), mrows * w * sizeof(op16), reinterpret_cast<void**>(&attn_i)));
+        MSCLIP_TRY(ws_get(h, ("tape:v_mid" + t).c_str(), mrows * w * sizeof(float), reinterpret_cast<void**>(&xmid_i)));
+      }
+      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv_i, attn_i, fc1, rec, &h_ready, next, s, xmid_i, x_next));
+      if (slots) xc = x_next;
     }
-    if (tape) MSCLIP_TRY(tape_save(h, "v_x" + std::to_string(c.layers), xc, xbytes, s));
+    if (tape && !slots) MSCLIP_TRY(tape_save(h, "v_x" + std::to_string(c.layers), xc, xbytes, s));
     // CLS -> ln_post -> proj -> L2 norm (M.py:2685-2690, 2982-2983)
     MSCLIP_TRY(launch_layernorm_op16(xc, L, h->ln_post_w, h->ln_post_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->vproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
@@ -1004,24 +1054,41 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
     const int nb = std::min(kTowerChunk, batch - b0);
     const int64_t* tk = tok + static_cast<size_t>(b0) * Lt;
     const bool emit0 = !g_ln_fold;
-    MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, x, nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0],
+    const bool tape = h->train && batch <= kTrainMaxBatch;  // see vision_tower
+    const bool slots = tape && !g_ln_fold && !g_ln_warps;   // the residual stream lives in the tape slots: no copies
+    const size_t xbytes = static_cast<size_t>(nb) * L * w * sizeof(float);
+    h->tape_txt.valid = false;
+    std::vector<float*> slot(c.layers + 1, x);
+    if (slots)
+      for (int i = 0; i <= c.layers; ++i)
+        MSCLIP_TRY(ws_get(h, ("tape:t_x" + std::to_string(i)).c_str(), xbytes, reinterpret_cast<void**>(&slot[i])));
+    const size_t mrows = static_cast<size_t>(nb) * L;
+    const bool keep = slots && tape_can_keep(h, "tape:t_qkv0", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4));
+    h->tape_txt.keep = keep;
+    MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, slot[0], nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0],
                                  emit0 ? h->tblocks[0].ln1_w : nullptr, emit0 ? h->tblocks[0].ln1_b : nullptr,
                                  emit0 ? hbuf : nullptr, s));
     count_launch(1);
     bool h_ready = emit0;
-    const bool tape = h->train && batch <= kTrainMaxBatch;  // see vision_tower
-    const size_t xbytes = static_cast<size_t>(nb) * L * w * sizeof(float);
-    h->tape_txt.valid = false;
     for (int idx = 0; idx < c.layers; ++idx) {
-      if (tape) MSCLIP_TRY(tape_save(h, "t_x" + std::to_string(idx), x, xbytes, s));
-      MSCLIP_TRY(run_block(h, h->tblocks[idx], x, nb, L, 1, hbuf, qkv, attn, fc1, rec, &h_ready,
-                           idx + 1 < c.layers ? &h->tblocks[idx + 1] : nullptr, s));
+      if (tape && !slots) MSCLIP_TRY(tape_save(h, "t_x" + std::to_string(idx), x, xbytes, s));
+      op16 *qkv_i = qkv, *attn_i = attn;
+      float* xmid_i = slots ? x : nullptr;
+      if (keep) {
+        const std::string t = std::to_string(idx);
+        MSCLIP_TRY(ws_get(h, ("tape:t_qkv" + t).c_str(), mrows * 3 * w * sizeof(op16), reinterpret_cast<void**>(&qkv_i)));
+        MSCLIP_TRY(ws_get(h, ("tape:t_ctx" + t).c_str(), mrows * w * sizeof(op16), reinterpret_cast<void**>(&attn_i)));
+        MSCLIP_TRY(ws_get(h, ("tape:t_mid" + t).c_str(), mrows * w * sizeof(float), reinterpret_cast<void**>(&xmid_i)));
+      }
+      MSCLIP_TRY(run_block(h, h->tblocks[idx], slot[idx], nb, L, 1, hbuf, qkv_i, attn_i, fc1, rec, &h_ready,
+                           idx + 1 < c.layers ? &h->tblocks[idx + 1] : nullptr, s, xmid_i, slots ? slot[idx + 1] : nullptr));
     }
+    float* x_final = slot[c.layers];
     if (tape) {
-      MSCLIP_TRY(tape_save(h, "t_x" + std::to_string(c.layers), x, xbytes, s));
+      if (!slots) MSCLIP_TRY(tape_save(h, "t_x" + std::to_string(c.layers), x, xbytes, s));
       MSCLIP_TRY(tape_save(h, "t_tok", tk, static_cast<size_t>(nb) * Lt * sizeof(int64_t), s));
     }
-    MSCLIP_TRY(launch_eot_layernorm_op16(x, L, tk, Lt, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
+    MSCLIP_TRY(launch_eot_layernorm_op16(x_final, L, tk, Lt, h->ln_final_w, h->ln_final_b, pool_ln, nb, s));
     MSCLIP_TRY(launch_gemm(pool_ln, w, h->tproj, w, nb, c.embed_dim, w, nullptr, feat_raw, c.embed_dim, nullptr, 0,
                            EPI_F32, s));
     if (tape) {

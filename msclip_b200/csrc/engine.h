@@ -135,6 +135,7 @@ struct msclip_ctx {
   struct TapeInfo {
     int batch = 0, L = 0, normalize = 1;
     bool valid = false;
+    bool keep = false;  // the tape also holds every block's QKV, attention output and mid-block stream (no recompute of those)
   } tape_txt, tape_img;
 
   ~msclip_ctx();

@@ -129,16 +129,30 @@ int get_scratch(msclip_ctx* h, int M, BwdScratch& b) {
 // g16_ready: b.g16 already holds op16(dx) and the fc2 bias gradient of this block has been taken (both were emitted by the
 // LayerNorm backward that ended the block above).  below: the block that consumes this block's dx next with nothing in
 // between (its fc2 bias gradient = column sums of our final dx), or null.
+// kept: QKV / attention output / mid-block stream of this block from the tape (all three or none): their recompute is skipped.
+struct KeptActs {
+  const op16* qkv = nullptr;
+  const op16* ctx = nullptr;
+  const float* x1 = nullptr;
+};
 int block_backward(msclip_ctx* h, const BlockWeights& bw, const BlockWeightsT& bt, const BlockGrads& bg, const float* x_in,
-                   float* dx, int batch, int L, int causal, const BwdScratch& b, bool g16_ready, const BlockGrads* below,
-                   cudaStream_t s) {
+                   float* dx, int batch, int L, int causal, const BwdScratch& b_in, bool g16_ready, const BlockGrads* below,
+                   const KeptActs& kept, cudaStream_t s) {
   const int w = kW, M = batch * L;
   const int rp = bwd_row_parts(M), sp = bwd_slab_parts(M);
+  BwdScratch b = b_in;
   // ---- recompute the block's intermediates (the forward's kernels; fc1 keeps the pre-activation u)
   MSCLIP_TRY(launch_layernorm_op16(x_in, 1, bw.ln1_w, bw.ln1_b, b.h1, M, s));
-  MSCLIP_TRY(launch_gemm(b.h1, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, b.qkv, 3 * w, nullptr, 0, EPI_BF16, s));
-  MSCLIP_TRY(launch_attention(b.qkv, b.ctx, batch, L, h->heads, causal, s));
-  MSCLIP_TRY(launch_gemm(b.ctx, w, bw.w_o, w, M, w, w, bw.b_o, b.x1, w, x_in, w, EPI_RESID_F32, s));
+  if (kept.qkv != nullptr) {
+    b.qkv = const_cast<op16*>(kept.qkv);
+    b.ctx = const_cast<op16*>(kept.ctx);
+    b.x1 = const_cast<float*>(kept.x1);
+    count_launch(-3);
+  } else {
+    MSCLIP_TRY(launch_gemm(b.h1, w, bw.w_qkv, w, M, 3 * w, w, bw.b_qkv, b.qkv, 3 * w, nullptr, 0, EPI_BF16, s));
+    MSCLIP_TRY(launch_attention(b.qkv, b.ctx, batch, L, h->heads, causal, s));
+    MSCLIP_TRY(launch_gemm(b.ctx, w, bw.w_o, w, M, w, w, bw.b_o, b.x1, w, x_in, w, EPI_RESID_F32, s));
+  }
   MSCLIP_TRY(launch_layernorm_op16(b.x1, 1, bw.ln2_w, bw.ln2_b, b.h2, M, s));
   MSCLIP_TRY(launch_gemm(b.h2, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, b.u, 4 * w, nullptr, 0, EPI_BF16, s));
   // ---- MLP (M.py:794-798, 1028)
@@ -219,8 +233,16 @@ int text_backward(msclip_ctx* h, const float* d_txt, cudaStream_t s) {
   for (int idx = c.layers - 1; idx >= 0; --idx) {
     const float* xin = static_cast<const float*>(tape_get(h, "t_x" + std::to_string(idx)));
     MSCLIP_REQUIRE(xin != nullptr, "backward: incomplete text tape");
+    KeptActs kept;
+    if (h->tape_txt.keep) {
+      const std::string t = std::to_string(idx);
+      kept.qkv = static_cast<const op16*>(tape_get(h, "t_qkv" + t));
+      kept.ctx = static_cast<const op16*>(tape_get(h, "t_ctx" + t));
+      kept.x1 = static_cast<const float*>(tape_get(h, "t_mid" + t));
+      MSCLIP_REQUIRE(kept.qkv && kept.ctx && kept.x1, "backward: incomplete text tape (kept activations)");
+    }
     MSCLIP_TRY(block_backward(h, h->tblocks[idx], h->tblocks_t[idx], h->tgrads[idx], xin, dx, B, L, 1, b, idx != c.layers - 1,
-                              idx > 0 ? &h->tgrads[idx - 1] : nullptr, s));
+                              idx > 0 ? &h->tgrads[idx - 1] : nullptr, kept, s));
   }
   MSCLIP_TRY(launch_text_embed_bwd(dx, tok, c.context_length, L, B, c.vocab_size, grad_find(h, "positional_embedding"),
                                    grad_find(h, "token_embedding.weight"), s));
@@ -251,8 +273,16 @@ int image_backward(msclip_ctx* h, const float* d_img, cudaStream_t s) {
     MSCLIP_REQUIRE(xin != nullptr, "backward: incomplete image tape");
     bool adapter_here = false;
     for (int j = 0; j < n_active; ++j) adapter_here |= kLateralLayers[j] == idx;
+    KeptActs kept;
+    if (h->tape_img.keep) {
+      const std::string t = std::to_string(idx);
+      kept.qkv = static_cast<const op16*>(tape_get(h, "v_qkv" + t));
+      kept.ctx = static_cast<const op16*>(tape_get(h, "v_ctx" + t));
+      kept.x1 = static_cast<const float*>(tape_get(h, "v_mid" + t));
+      MSCLIP_REQUIRE(kept.qkv && kept.ctx && kept.x1, "backward: incomplete image tape (kept activations)");
+    }
     MSCLIP_TRY(block_backward(h, h->vblocks[idx], h->vblocks_t[idx], h->vgrads[idx], xin, dx, B, L, 0, b, g16_ready,
-                              (idx > 1 && !adapter_here) ? &h->vgrads[idx - 1] : nullptr, s));
+                              (idx > 1 && !adapter_here) ? &h->vgrads[idx - 1] : nullptr, kept, s));
     g16_ready = idx > 1 && !adapter_here;
     for (int j = 0; j < n_active; ++j) {
       if (kLateralLayers[j] != idx) continue;
