@@ -44,10 +44,10 @@ METRIC = "image-text pairs/sec (forward + contrastive loss), MS-CLIP-S ViT-B/32"
 UNIT = "pairs/s"
 GF_PER_PAIR = {32: 23.549e9, 16: 49.617e9}        # BASELINE.md section 3 (2*m*n*k of every GEMM/bmm/conv)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-# `ncu --set full` capture (never measured inside a bench run): fc1 at the text-tower shape read 0.5169 GB and
-# wrote 1.8928 GB = its algorithmic bytes (A + W read once, bf16 output written once)
-NCU_DRAM_BYTES_PER_LAUNCH = {(4096 * 77, 3072, 768): 2409650000}
-NCU_TRAFFIC_SOURCE = "profiles/r01_gemm_ncu.md (ncu --set full, fc1 M=315392 N=3072 K=768, CTA pair)"
+# `ncu --set full` capture (never measured inside a bench run): fc1 at the text-tower shape read 0.4895 GB and
+# wrote 1.887 GB = its algorithmic bytes (A + W read once, bf16 output written once)
+NCU_DRAM_BYTES_PER_LAUNCH = {(4096 * 77, 3072, 768): 2376500000}
+NCU_TRAFFIC_SOURCE = "profiles/r02_gemm_ncu.md (ncu --set full, fc1 M=315392 N=3072 K=768, CTA pair)"
 
 
 def peaks():
