@@ -11,6 +11,10 @@ inherited by the subprocess that ``tools/eval_zeroshot.py`` spawns when it is in
 
     # sitecustomize.py
     import msclip_b200.dropin; msclip_b200.dropin.install()
+
+``install(tokenizer=True)`` (or MSCLIP_DROPIN_TOKENIZER=1) additionally swaps ``dataset.languages.SimpleTokenizer``
+(tools/zero_shot.py:34, 232) for the native tokenizer of the library (msclip_b200.tokenizer; identical ids, the reference's
+own merges file); methods the zero-shot path never calls (decode, *_with_idx) fall through to the reference's Python class.
 """
 from __future__ import annotations
 
@@ -18,8 +22,12 @@ import importlib.abc
 import importlib.machinery
 import sys
 
+import os
+
 TARGET = "models.clip_openai_pe_res_v1"
+TOKENIZER_TARGET = "dataset.languages.simple_tokenizer"
 _installed = False
+_patchers = {}
 
 
 def patch_module(module) -> None:
@@ -32,23 +40,50 @@ def patch_module(module) -> None:
     module._msclip_b200_patched = True
 
 
+def patch_tokenizer(module) -> None:
+    """Replace ``module.SimpleTokenizer`` (simple_tokenizer.py:64) by the native tokenizer with the same default merges file."""
+    from .tokenizer import SimpleTokenizer as Native
+    if getattr(module, "_msclip_b200_patched", False):
+        return
+    reference_cls = module.SimpleTokenizer
+    default_path = module.default_bpe()
+
+    class SimpleTokenizer(Native):
+        def __init__(self, bpe_path: str = default_path):
+            super().__init__(bpe_path)
+            self._bpe_path = bpe_path
+
+        def __getattr__(self, name):                      # decode / encode_with_idx / ...: the reference's own implementation
+            if name.startswith("_"):
+                raise AttributeError(name)
+            ref = self.__dict__.get("_ref")
+            if ref is None:
+                ref = self.__dict__["_ref"] = reference_cls(self.__dict__.get("_bpe_path", default_path))
+            return getattr(ref, name)
+
+    module._reference_SimpleTokenizer = reference_cls
+    module.SimpleTokenizer = SimpleTokenizer
+    module._msclip_b200_patched = True
+
+
 class _PatchingLoader(importlib.abc.Loader):
-    def __init__(self, wrapped):
+    def __init__(self, wrapped, patch):
         self._wrapped = wrapped
+        self._patch = patch
 
     def create_module(self, spec):
         return self._wrapped.create_module(spec)
 
     def exec_module(self, module):
         self._wrapped.exec_module(module)
-        patch_module(module)
+        self._patch(module)
 
 
 class _Finder(importlib.abc.MetaPathFinder):
     _busy = False
 
     def find_spec(self, fullname, path, target=None):
-        if fullname != TARGET or self._busy:
+        if fullname not in _patchers or self._busy:
             return None
         self._busy = True          # other wrapping finders on sys.meta_path delegate back to us: answer only once
         try:
@@ -57,18 +92,24 @@ class _Finder(importlib.abc.MetaPathFinder):
                     continue
                 spec = finder.find_spec(fullname, path, target)
                 if spec is not None and spec.loader is not None:
-                    spec.loader = _PatchingLoader(spec.loader)
+                    spec.loader = _PatchingLoader(spec.loader, _patchers[fullname])
                     return spec
             return None
         finally:
             self._busy = False
 
 
-def install() -> None:
-    """Idempotent.  Patches the module now if it is already imported, otherwise on import."""
+def install(tokenizer=None) -> None:
+    """Idempotent.  Patches the module(s) now if already imported, otherwise on import."""
     global _installed
-    if TARGET in sys.modules:
-        patch_module(sys.modules[TARGET])
+    _patchers[TARGET] = patch_module
+    if tokenizer is None:
+        tokenizer = os.environ.get("MSCLIP_DROPIN_TOKENIZER") == "1"
+    if tokenizer:
+        _patchers[TOKENIZER_TARGET] = patch_tokenizer
+    for name, patch in _patchers.items():
+        if name in sys.modules:
+            patch(sys.modules[name])
     if not _installed:
         sys.meta_path.insert(0, _Finder())
         _installed = True

@@ -68,6 +68,7 @@ def run_tool(ref_root: str, work: str, ckpt: str, data_root: str, layers: int, d
     env["PYTHONPATH"] = os.pathsep.join([REF_ENV, REPO] + ([env["PYTHONPATH"]] if env.get("PYTHONPATH") else []))
     env["MSCLIP_TOOL_DUMP"] = dump
     env["MSCLIP_DROPIN"] = "1" if dropin else "0"
+    env["MSCLIP_DROPIN_TOKENIZER"] = "1" if dropin else "0"   # the drop-in run also tokenises with the native tokenizer
     env.update(extra_env or {})
     # user-side configuration files (the tool itself and the shipped YAMLs stay untouched): the shipped model config
     # as BASE plus the checkpoint path / depth, and the ImageNet dataset config pointed at the synthetic folder

@@ -88,3 +88,27 @@ def test_zero_shot_prompt_set_is_identical_and_faster(pair):
     t2 = time.perf_counter()
     assert torch.equal(got, want)
     print(f"{len(texts)} prompts: reference {t1 - t0:.3f} s, native {t2 - t1:.3f} s")
+
+
+def test_dropin_swaps_the_tokenizer_class_of_the_reference_package(pair):
+    """dropin.install(tokenizer=True): `from dataset.languages import SimpleTokenizer` (tools/zero_shot.py:34) then yields the
+    native tokenizer with the reference's default merges file; methods outside the zero-shot path fall through."""
+    import subprocess
+    lib_dir = os.path.dirname(os.path.dirname(LANG_DIR))
+    code = f"""
+import sys, types
+stub = types.ModuleType('ftfy'); stub.fix_text = lambda t: t; sys.modules['ftfy'] = stub
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {lib_dir!r})
+import msclip_b200.dropin as d
+d.install(tokenizer=True)
+from dataset.languages import SimpleTokenizer
+import msclip_b200.tokenizer as T
+t = SimpleTokenizer()
+assert isinstance(t, T.SimpleTokenizer), type(t)
+ids = t('a photo of a dog')[0, :7].tolist()
+assert ids[0] == t.get_sot_token() and t.get_eot_token() in ids, ids
+assert t.decode(t.encode('hello world')).strip() == 'hello world'
+print('OK', ids)
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
