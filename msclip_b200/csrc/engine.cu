@@ -507,6 +507,11 @@ static const bool g_train_keep = [] {
   const char* e = getenv("MSCLIP_TRAIN_KEEP");
   return e == nullptr || e[0] != '0';
 }();
+// MSCLIP_TRAIN_KEEP_U=0: do not keep fc1's pre-activation (another 6 KB per token and block; the backward then re-runs fc1)
+static const bool g_train_keep_u = [] {
+  const char* e = getenv("MSCLIP_TRAIN_KEEP_U");
+  return e == nullptr || e[0] != '0';
+}();
 static bool tape_can_keep(msclip_ctx* h, const std::string& probe, size_t extra_bytes) {
   if (!g_train_keep) return false;
   if (h->ws.count(probe) && h->ws[probe].bytes > 0) return true;  // already allocated by an earlier step
@@ -668,7 +673,7 @@ static const bool g_ln_warps = [] {
 // output to x_out instead of back into x, so that x (a tape slot) keeps the block's input without any copy.
 static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch, int L, int causal, op16* hbuf,
                      op16* qkv, op16* attn, op16* fc1, float** rec, bool* h_ready, const BlockWeights* next, cudaStream_t s,
-                     float* x_mid = nullptr, float* x_out = nullptr) {
+                     float* x_mid = nullptr, float* x_out = nullptr, op16* u_out = nullptr) {
   const int w = h->cfg.width;
   const int M = batch * L;
   float* xm = x_mid ? x_mid : x;
@@ -720,7 +725,10 @@ static int run_block(msclip_ctx* h, const BlockWeights& bw, float* x, int batch,
   MSCLIP_TRY(launch_attention(qkv, attn, batch, L, h->heads, causal, s));
   MSCLIP_TRY(launch_gemm(attn, w, bw.w_o, w, M, w, w, bw.b_o, xm, w, x, w, EPI_RESID_F32, s));
   MSCLIP_TRY(launch_layernorm_op16(xm, 1, bw.ln2_w, bw.ln2_b, hbuf, M, s));
-  MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
+  if (u_out != nullptr)  // training tape: the same GEMM also leaves the pre-activation for the backward
+    MSCLIP_TRY(launch_gemm_qgelu_dual(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, u_out, s));
+  else
+    MSCLIP_TRY(launch_gemm(hbuf, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, fc1, 4 * w, nullptr, 0, EPI_QGELU_BF16, s));
   MSCLIP_TRY(launch_gemm(fc1, 4 * w, bw.w_fc2, 4 * w, M, w, 4 * w, bw.b_fc2, xo, w, xm, w, EPI_RESID_F32, s));
   count_launch(have_h ? 6 : 7);
   return 0;
@@ -962,6 +970,8 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     const size_t mrows = static_cast<size_t>(nb) * L;
     const bool keep = slots && tape_can_keep(h, "tape:v_qkv1", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4));
     h->tape_img.keep = keep;
+    const bool keep_u = keep && g_train_keep_u && tape_can_keep(h, "tape:v_u1", static_cast<size_t>(c.layers) * mrows * 4 * w * 2);
+    h->tape_img.keep_u = keep_u;
     // the kernels that produce the residual stream also emit ln_1 of the block that consumes it next
     const bool adapter_first = adapter_at(1) >= 0;
     const bool emit1 = !g_ln_fold && c.layers > 1 && !adapter_first;
@@ -1007,7 +1017,10 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
         MSCLIP_TRY(ws_get(h, ("tape:v_ctx" + t).c_str(), mrows * w * sizeof(op16), reinterpret_cast<void**>(&attn_i)));
         MSCLIP_TRY(ws_get(h, ("tape:v_mid" + t).c_str(), mrows * w * sizeof(float), reinterpret_cast<void**>(&xmid_i)));
       }
-      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv_i, attn_i, fc1, rec, &h_ready, next, s, xmid_i, x_next));
+      op16* u_i = nullptr;
+      if (keep_u)
+        MSCLIP_TRY(ws_get(h, ("tape:v_u" + std::to_string(idx)).c_str(), mrows * 4 * w * sizeof(op16), reinterpret_cast<void**>(&u_i)));
+      MSCLIP_TRY(run_block(h, h->vblocks[idx], xc, nb, L, 0, hbuf, qkv_i, attn_i, fc1, rec, &h_ready, next, s, xmid_i, x_next, u_i));
       if (slots) xc = x_next;
     }
     if (tape && !slots) MSCLIP_TRY(tape_save(h, "v_x" + std::to_string(c.layers), xc, xbytes, s));
@@ -1065,6 +1078,8 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
     const size_t mrows = static_cast<size_t>(nb) * L;
     const bool keep = slots && tape_can_keep(h, "tape:t_qkv0", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4));
     h->tape_txt.keep = keep;
+    const bool keep_u = keep && g_train_keep_u && tape_can_keep(h, "tape:t_u0", static_cast<size_t>(c.layers) * mrows * 4 * w * 2);
+    h->tape_txt.keep_u = keep_u;
     MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, slot[0], nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0],
                                  emit0 ? h->tblocks[0].ln1_w : nullptr, emit0 ? h->tblocks[0].ln1_b : nullptr,
                                  emit0 ? hbuf : nullptr, s));
@@ -1080,8 +1095,11 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
         MSCLIP_TRY(ws_get(h, ("tape:t_ctx" + t).c_str(), mrows * w * sizeof(op16), reinterpret_cast<void**>(&attn_i)));
         MSCLIP_TRY(ws_get(h, ("tape:t_mid" + t).c_str(), mrows * w * sizeof(float), reinterpret_cast<void**>(&xmid_i)));
       }
+      op16* u_i = nullptr;
+      if (keep_u)
+        MSCLIP_TRY(ws_get(h, ("tape:t_u" + std::to_string(idx)).c_str(), mrows * 4 * w * sizeof(op16), reinterpret_cast<void**>(&u_i)));
       MSCLIP_TRY(run_block(h, h->tblocks[idx], slot[idx], nb, L, 1, hbuf, qkv_i, attn_i, fc1, rec, &h_ready,
-                           idx + 1 < c.layers ? &h->tblocks[idx + 1] : nullptr, s, xmid_i, slots ? slot[idx + 1] : nullptr));
+                           idx + 1 < c.layers ? &h->tblocks[idx + 1] : nullptr, s, xmid_i, slots ? slot[idx + 1] : nullptr, u_i));
     }
     float* x_final = slot[c.layers];
     if (tape) {

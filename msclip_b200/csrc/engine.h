@@ -136,6 +136,7 @@ struct msclip_ctx {
     int batch = 0, L = 0, normalize = 1;
     bool valid = false;
     bool keep = false;  // the tape also holds every block's QKV, attention output and mid-block stream (no recompute of those)
+    bool keep_u = false;  // ... and fc1's pre-activation (written by the dual-output epilogue of the taped forward)
   } tape_txt, tape_img;
 
   ~msclip_ctx();

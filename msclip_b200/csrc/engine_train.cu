@@ -134,6 +134,7 @@ struct KeptActs {
   const op16* qkv = nullptr;
   const op16* ctx = nullptr;
   const float* x1 = nullptr;
+  const op16* u = nullptr;  // fc1 pre-activation (optional on top of the other three)
 };
 int block_backward(msclip_ctx* h, const BlockWeights& bw, const BlockWeightsT& bt, const BlockGrads& bg, const float* x_in,
                    float* dx, int batch, int L, int causal, const BwdScratch& b_in, bool g16_ready, const BlockGrads* below,
@@ -154,7 +155,12 @@ int block_backward(msclip_ctx* h, const BlockWeights& bw, const BlockWeightsT& b
     MSCLIP_TRY(launch_gemm(b.ctx, w, bw.w_o, w, M, w, w, bw.b_o, b.x1, w, x_in, w, EPI_RESID_F32, s));
   }
   MSCLIP_TRY(launch_layernorm_op16(b.x1, 1, bw.ln2_w, bw.ln2_b, b.h2, M, s));
-  MSCLIP_TRY(launch_gemm(b.h2, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, b.u, 4 * w, nullptr, 0, EPI_BF16, s));
+  if (kept.u != nullptr) {
+    b.u = const_cast<op16*>(kept.u);
+    count_launch(-1);
+  } else {
+    MSCLIP_TRY(launch_gemm(b.h2, w, bw.w_fc1, w, M, 4 * w, w, bw.b_fc1, b.u, 4 * w, nullptr, 0, EPI_BF16, s));
+  }
   // ---- MLP (M.py:794-798, 1028)
   if (!g16_ready) {
     MSCLIP_TRY(launch_cast_colsum(dx, b.g16, b.part, M, s));
@@ -240,6 +246,10 @@ int text_backward(msclip_ctx* h, const float* d_txt, cudaStream_t s) {
       kept.ctx = static_cast<const op16*>(tape_get(h, "t_ctx" + t));
       kept.x1 = static_cast<const float*>(tape_get(h, "t_mid" + t));
       MSCLIP_REQUIRE(kept.qkv && kept.ctx && kept.x1, "backward: incomplete text tape (kept activations)");
+      if (h->tape_txt.keep_u) {
+        kept.u = static_cast<const op16*>(tape_get(h, "t_u" + t));
+        MSCLIP_REQUIRE(kept.u != nullptr, "backward: incomplete text tape (kept pre-activations)");
+      }
     }
     MSCLIP_TRY(block_backward(h, h->tblocks[idx], h->tblocks_t[idx], h->tgrads[idx], xin, dx, B, L, 1, b, idx != c.layers - 1,
                               idx > 0 ? &h->tgrads[idx - 1] : nullptr, kept, s));
@@ -280,6 +290,10 @@ int image_backward(msclip_ctx* h, const float* d_img, cudaStream_t s) {
       kept.ctx = static_cast<const op16*>(tape_get(h, "v_ctx" + t));
       kept.x1 = static_cast<const float*>(tape_get(h, "v_mid" + t));
       MSCLIP_REQUIRE(kept.qkv && kept.ctx && kept.x1, "backward: incomplete image tape (kept activations)");
+      if (h->tape_img.keep_u) {
+        kept.u = static_cast<const op16*>(tape_get(h, "v_u" + t));
+        MSCLIP_REQUIRE(kept.u != nullptr, "backward: incomplete image tape (kept pre-activations)");
+      }
     }
     MSCLIP_TRY(block_backward(h, h->vblocks[idx], h->vblocks_t[idx], h->vgrads[idx], xin, dx, B, L, 0, b, g16_ready,
                               (idx > 1 && !adapter_here) ? &h->vgrads[idx - 1] : nullptr, kept, s));

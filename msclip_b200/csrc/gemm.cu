@@ -270,7 +270,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int half = (warp - 4) >> 2;    // which share of the tile's column chunks this warp drains
     constexpr int kParts = NE / 4;
     // more epilogue warps run under a tighter register cap: they drain the tile in 16-column pieces
-    constexpr int kCh = ((NE > 8 || LN == 3 || EPI == EPI_DGELU_BF16) && Cfg::kChunk == 32) ? 16 : Cfg::kChunk;
+    constexpr int kCh = ((NE > 8 || LN == 3 || EPI == EPI_DGELU_BF16 || EPI == EPI_QGELU_DUAL_BF16) && Cfg::kChunk == 32) ? 16 : Cfg::kChunk;
     constexpr int kNumCh = BN / kCh;
     static_assert(NE % 4 == 0 && kParts >= 1 && (LN != 2 || kParts == 2), "LN emit slots assume two column halves per tile");
     constexpr int kPerHalf = (kNumCh + kParts - 1) / kParts;
@@ -766,6 +766,34 @@ static int launch_gemm_impl(const op16* A, int64_t lda, const op16* W, int64_t l
     case 48: return launch_bn<48, 1, 1>(ta, tb, p, epi, stream);
   }
   return 2;
+}
+
+// Training forward of fc1: activation AND pre-activation from one epilogue (EPI_QGELU_DUAL_BF16, kernels.h)
+int launch_gemm_qgelu_dual(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, op16* a,
+                           op16* u, cudaStream_t stream) {
+  MSCLIP_REQUIRE(M > 0 && N % 256 == 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "launch_gemm_qgelu_dual: bad operand shapes");
+  MSCLIP_REQUIRE(a && u && bias && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+                 "launch_gemm_qgelu_dual: a, u and bias must be 16-byte aligned");
+  const int cg = (g_pair_mode >= 1 && M >= 256) ? 2 : 1;
+  CUtensorMap ta, tb;
+  MSCLIP_TRY(make_tmap_op16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), kBM));
+  MSCLIP_TRY(make_tmap_op16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+                               static_cast<uint32_t>(256 / cg)));
+  GemmParams p = {};
+  p.operand_fmt = kUmmaOperandFormat;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.tiles_n = N / 256;
+  p.alpha = 1.0f;
+  p.vec_ok = 1;
+  p.total_tiles = ((M + kBM * cg - 1) / (kBM * cg)) * p.tiles_n;
+  p.bias = bias;
+  p.out = a;
+  p.out2 = u;
+  p.ldo = N;
+  return cg == 2 ? launch_variant<256, EPI_QGELU_DUAL_BF16, 2, 1>(ta, tb, p, stream)
+                 : launch_variant<256, EPI_QGELU_DUAL_BF16, 1, 1>(ta, tb, p, stream);
 }
 
 // Backward of the MLP's activation on the dgrad GEMM's epilogue (EPI_DGELU_BF16, kernels.h)

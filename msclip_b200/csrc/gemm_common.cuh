@@ -218,7 +218,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
       const int col = col0 + j;
       if (col < p.N) {
         float x = v[j] + (p.bias ? p.bias[col] : 0.f);
-        if (EPI == EPI_QGELU_BF16) x = quick_gelu(x);
+        if (EPI == EPI_QGELU_BF16 || EPI == EPI_QGELU_DUAL_BF16) x = quick_gelu(x);
         if (EPI == EPI_RELU_BF16) x = fmaxf(x, 0.f);
         if (EPI == EPI_RESID_F32) x += p.resid[static_cast<long long>(row) * p.ldr + col];
         if (EPI == EPI_RESID_F32 || EPI == EPI_F32)
@@ -247,16 +247,22 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
     v[4 * j + 2] += o.bias[j].z;
     v[4 * j + 3] += o.bias[j].w;
   }
-  if (EPI == EPI_QGELU_BF16) {
+  const bool par = (threadIdx.x & 1) != 0;
+  const int row_e = row & ~1, row_o = row | 1;
+  const bool ok_e = row_e < p.M, ok_o = row_o < p.M;
+  if (EPI == EPI_QGELU_DUAL_BF16) {
+    uint32_t pre[CH / 2];
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) pre[j] = pack16(v[2 * j], v[2 * j + 1]);
+    store16_swapped<CH>(pre, p.out2, p.ldo, row_e, row_o, col0, ok_e, ok_o, par);
+  }
+  if (EPI == EPI_QGELU_BF16 || EPI == EPI_QGELU_DUAL_BF16) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = quick_gelu(v[j]);
   } else if (EPI == EPI_RELU_BF16) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
-  const bool par = (threadIdx.x & 1) != 0;
-  const int row_e = row & ~1, row_o = row | 1;
-  const bool ok_e = row_e < p.M, ok_o = row_o < p.M;
   if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
     // pieces = float4 (4 columns); lane parity selects pieces 2j + par of both rows
     float4* oe = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row_e) * p.ldo + col0);

@@ -63,6 +63,9 @@ enum GemmEpilogue {
   // (= d u) and op16 out2 = quickgelu(u) (the fc2 input the weight gradient needs): both QuickGELU passes of the backward
   // ride on the dgrad GEMM's epilogue instead of two more trips over the [M, 3072] tensors
   EPI_DGELU_BF16 = 5,
+  // training forward of fc1: op16 out = quickgelu(acc + bias) as EPI_QGELU_BF16, and op16 out2 = acc + bias (the
+  // pre-activation the backward needs) - saves the backward a whole fc1 GEMM
+  EPI_QGELU_DUAL_BF16 = 6,
 };
 int launch_gemm(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias,
                 void* out, int64_t ldo, const float* resid, int64_t ldr, int epi, cudaStream_t stream);
@@ -72,6 +75,9 @@ int launch_gemm_split(const op16* A, int64_t lda, const op16* W, int64_t ldw, in
 // fp16 operands in either build (only 16-bit-out / f32-out epilogues without bias or residual): the loss backward
 int launch_gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, float alpha, void* out, int64_t ldo,
                     int epi, cudaStream_t stream);
+// a = quickgelu(A . W^T + bias), u = A . W^T + bias   (EPI_QGELU_DUAL_BF16; N % 256 == 0, all pitches = N)
+int launch_gemm_qgelu_dual(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const float* bias, op16* a,
+                           op16* u, cudaStream_t stream);
 // du = (A . W^T) * quickgelu'(u), a = quickgelu(u)   (EPI_DGELU_BF16; N % 256 == 0, all pitches = N)
 int launch_gemm_dgelu(const op16* A, int64_t lda, const op16* W, int64_t ldw, int M, int N, int K, const op16* u, op16* du, op16* a,
                       cudaStream_t stream);
