@@ -386,3 +386,75 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     for (k, pa), (_k, pb) in zip(a.state_dict().items(), b.state_dict().items()):
         if pa.dtype == torch.float32 and "token_embedding" not in k:      # the embedding scatter uses fp32 atomics
             assert torch.equal(pa, pb), k
+
+
+def test_training_trajectory_tracks_torch_autograd_plus_adamw():
+    """End-to-end training dynamics: 12 optimiser steps of the drop-in (our forward, loss, backward, fused AdamW, re-packed
+    weights) against the same 12 steps done with torch - autograd through the CPU-oracle forward (moved to the GPU, fp32) and
+    torch.optim.AdamW with the same parameter groups, only our trainable keys receiving updates (the convolutional front is
+    frozen on both sides).  The per-step losses must track each other; both must fall."""
+    from msclip_b200.optim import AdamW, _is_shared, _no_decay
+    cfg = MSCLIPConfig(patch_size=32, layers=3)
+    sd_np = synth.synth_state_dict(cfg, seed=21, logit_scale=math.log(30.0))
+    img, tok = synth.correlated_pair_batch(cfg, 16, seed=5)
+    timg, ttok = torch.from_numpy(img).cuda(), torch.from_numpy(tok).cuda()
+    steps, lr, wd, lr_s, wd_s = 12, 2e-4, 0.05, 1e-4, 0.2
+    model = build_train_model(cfg, sd_np)
+    opt = AdamW(model, lr=lr, weight_decay=wd, lr_share=lr_s, wd_share=wd_s)
+    ours = []
+    for _ in range(steps):
+        opt.zero_grad()
+        ours.append(float(model.loss_and_backward(timg, ttok)))
+        opt.step()
+    # torch side
+    sd = O.to_torch(sd_np, device="cuda")
+    keys = [k for k in trainable_keys(cfg)]
+    groups, seen = [], set()
+    for k in keys:
+        t = sd[k]
+        if id(t) in seen:
+            continue
+        seen.add(id(t))
+        t.requires_grad_(True)
+        shared = _is_shared(k)
+        groups.append({"params": [t], "lr": lr_s if shared else lr,
+                       "weight_decay": 0.0 if _no_decay(k) else (wd_s if shared else wd)})
+    ref_opt = torch.optim.AdamW(groups, betas=(0.9, 0.999), eps=1e-8)
+    ref = []
+    for _ in range(steps):
+        ref_opt.zero_grad()
+        loss = O.contrastive_loss(O.forward(timg, ttok, sd, cfg))
+        loss.backward()
+        ref_opt.step()
+        ref.append(float(loss.detach()))
+    _record("training_trajectory", {"ours": ours, "torch_fp32": ref})
+    assert ours[-1] < ours[0] and ref[-1] < ref[0], (ours, ref)
+    for a, b in zip(ours, ref):
+        assert abs(a - b) <= 2e-2 * abs(b) + 2e-3, (ours, ref)
+
+
+def test_backward_error_paths():
+    """Loud failures instead of silent wrong gradients: backward without training mode, without a taped forward, and for a
+    batch larger than one tape holds."""
+    cfg = MSCLIPConfig(patch_size=32, layers=2)
+    sd_np = synth.synth_state_dict(cfg, seed=3)
+    plain = CLIP(cfg, precision="bf16")
+    plain.load_state_dict({k: torch.as_tensor(v) for k, v in sd_np.items()}, strict=True)
+    plain = plain.cuda().eval()
+    tok = torch.from_numpy(synth.synth_tokens(4, 1, cfg.context_length, cfg.vocab_size)).cuda()
+    plain.encode_text(tok)
+    with pytest.raises(_lib.MsclipError, match="training is not enabled"):
+        plain.backward_features(None, torch.zeros(4, cfg.embed_dim, device="cuda"))
+    with pytest.raises(_lib.MsclipError, match="enable_training"):
+        plain.trainable_parameters()
+    model = build_train_model(cfg, sd_np)
+    with pytest.raises(_lib.MsclipError, match="no taped encode_text"):
+        model.backward_features(None, torch.zeros(4, cfg.embed_dim, device="cuda"))
+    model.encode_text(tok)
+    with pytest.raises(_lib.MsclipError, match="no taped encode_image"):
+        model.backward_features(torch.zeros(4, cfg.embed_dim, device="cuda"), None)
+    fp16 = CLIP(cfg, precision="fp16")
+    fp16.load_state_dict({k: torch.as_tensor(v) for k, v in sd_np.items()}, strict=True)
+    fp16 = fp16.cuda().eval()
+    with pytest.raises(_lib.MsclipError, match="bf16 build"):
+        fp16.enable_training()
