@@ -96,8 +96,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
     }
+    // causal: key groups entirely above this warp's last query row are fully masked - neither their scores nor their dP are
+    // needed (P = dS = 0 there, and phase 2 never reads a [query tile][key tile] block with key tile > query tile)
+    const int jp_end = CAUSAL ? min(NT / 2, m0 / 16 + 1) : NT / 2;
 #pragma unroll
     for (int jp = 0; jp < NT / 2; ++jp) {
+      if (jp >= jp_end) continue;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         uint32_t kf[4], vf[4];
@@ -162,6 +166,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     // dS = P * (dP - D); P and dS -> shared memory [query][key] for phase 2
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
+      if (j >= 2 * jp_end) continue;   // masked key groups: nothing to store (never read)
 #pragma unroll
       for (int e = 0; e < 4; ++e) dp[j][e] = s[j][e] * (dp[j][e] - dsum[e >> 1]);
       const uint32_t off_lo = static_cast<uint32_t>(row_lo) * kPitch + (8 * j + 2 * t) * 2;
@@ -177,6 +182,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 #pragma unroll
     for (int kk2 = 0; kk2 < NT / 2; ++kk2) {
+      if (kk2 >= jp_end) continue;
       uint32_t pa[4];
       pa[0] = pack16(dp[2 * kk2][0], dp[2 * kk2][1]);
       pa[1] = pack16(dp[2 * kk2][2], dp[2 * kk2][3]);

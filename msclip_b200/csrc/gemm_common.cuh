@@ -310,13 +310,18 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[CH], const Ep
       const op162* uu = reinterpret_cast<const op162*>(o.aux);
 #pragma unroll
       for (int j = 0; j < CH / 2; ++j) {
+        // with t = tanh(0.851 x): sigmoid s = (1 + t) / 2, quickgelu(x) = x s = hx + hx t (hx = x / 2, as in quick_gelu()),
+        // quickgelu'(x) = s + 1.702 x s (1 - s) = (1 + t) / 2 + (0.851 x / 2) (1 - t^2)
         const float2 x = op162_to_float2(uu[j]);
+        const float q0 = 0.851f * x.x, q1 = 0.851f * x.y;
         float t0, t1;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.851f * x.x));
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.851f * x.y));
-        const float s0 = fmaf(0.5f, t0, 0.5f), s1 = fmaf(0.5f, t1, 0.5f);
-        act[j] = pack16(x.x * s0, x.y * s1);
-        u[j] = pack16(v[2 * j] * s0 * fmaf(1.702f * x.x, 1.0f - s0, 1.0f), v[2 * j + 1] * s1 * fmaf(1.702f * x.y, 1.0f - s1, 1.0f));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(q0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(q1));
+        const float h0 = 0.5f * x.x, h1 = 0.5f * x.y;
+        act[j] = pack16(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
+        const float g0 = fmaf(0.5f * q0, fmaf(-t0, t0, 1.0f), fmaf(0.5f, t0, 0.5f));
+        const float g1 = fmaf(0.5f * q1, fmaf(-t1, t1, 1.0f), fmaf(0.5f, t1, 0.5f));
+        u[j] = pack16(v[2 * j] * g0, v[2 * j + 1] * g1);
       }
       store16_swapped<CH>(act, p.out2, p.ldo, row_e, row_o, col0, ok_e, ok_o, par);
     } else {
