@@ -263,7 +263,7 @@ int text_backward(msclip_ctx* h, const float* d_txt, cudaStream_t s) {
 int image_backward(msclip_ctx* h, const float* d_img, cudaStream_t s) {
   const msclip_config& c = h->cfg;
   MSCLIP_REQUIRE(h->tape_img.valid, "backward: no taped encode_image (enable training, then encode at most 4096 images per call)");
-  MSCLIP_REQUIRE(h->l_img <= 80, "backward: the B/16 image tower (L = 197) has no attention backward in this build");
+  MSCLIP_REQUIRE(h->l_img <= 208, "backward: image sequences longer than 208 tokens have no attention backward");
   const int B = h->tape_img.batch, L = h->l_img, M = B * L, g = h->grid;
   BwdScratch b;
   MSCLIP_TRY(get_scratch(h, M, b));

@@ -34,7 +34,7 @@ def rel_err(a, b):
 
 
 # ---- gradient fixtures (oracle/make_golden_grads.py): backward of the symmetric CE through the REAL reference ----------
-GRAD_CASES = ["b32_l2_b8", "b32_l3_b4", "b32_l12_b8"]
+GRAD_CASES = ["b32_l2_b8", "b32_l3_b4", "b32_l12_b8", "b16_l3_b2"]
 GRAD_SAMPLE = 2048
 
 

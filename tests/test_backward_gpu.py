@@ -110,7 +110,8 @@ def test_wgrad(name, tokens, n, k):
 
 
 # ------------------------------------------------------------------------------------------------ attention backward
-ATT_CASES = [(3, 50, False), (2, 77, True), (5, 64, False), (3, 80, True), (1, 7, True), (2, 33, False), (64, 77, True)]
+ATT_CASES = [(3, 50, False), (2, 77, True), (5, 64, False), (3, 80, True), (1, 7, True), (2, 33, False), (64, 77, True),
+             (2, 197, False), (1, 197, True), (3, 130, False), (2, 96, True), (1, 208, False), (1, 81, True)]   # > 80: three-pass kernel
 
 
 @pytest.mark.parametrize("batch,L,causal", ATT_CASES)
@@ -270,9 +271,9 @@ def test_text_tower_backward_matches_oracle_autograd(layers, batch, ragged):
     compare_grads(model, {k: sd[k].grad for k in keys}, keys, f"text_tower/l{layers}_b{batch}")
 
 
-@pytest.mark.parametrize("layers,batch", [(2, 3), (3, 4), (5, 2)])
-def test_image_tower_backward_matches_oracle_autograd(layers, batch):
-    cfg = MSCLIPConfig(patch_size=32, layers=layers)
+@pytest.mark.parametrize("layers,batch,patch", [(2, 3, 32), (3, 4, 32), (5, 2, 32), (3, 2, 16)])
+def test_image_tower_backward_matches_oracle_autograd(layers, batch, patch):
+    cfg = MSCLIPConfig(patch_size=patch, layers=layers)
     sd_np = synth.synth_state_dict(cfg, seed=6)
     img = synth.synth_images(batch, 22, cfg.image_resolution)
     model = build_train_model(cfg, sd_np)
@@ -285,7 +286,7 @@ def test_image_tower_backward_matches_oracle_autograd(layers, batch):
     sd = oracle_leaves(sd_np)
     O.encode_image(torch.from_numpy(img), sd, cfg).backward(d_feat)
     keys = [k for k in trainable_keys(cfg) if k.startswith("visual.")]
-    compare_grads(model, {k: sd[k].grad for k in keys}, keys, f"image_tower/l{layers}_b{batch}")
+    compare_grads(model, {k: sd[k].grad for k in keys}, keys, f"image_tower/p{patch}_l{layers}_b{batch}")
 
 
 # ------------------------------------------------------------------------------------------------ whole step vs the reference
