@@ -512,12 +512,19 @@ static const bool g_train_keep_u = [] {
   const char* e = getenv("MSCLIP_TRAIN_KEEP_U");
   return e == nullptr || e[0] != '0';
 }();
-static bool tape_can_keep(msclip_ctx* h, const std::string& probe, size_t extra_bytes) {
+// May the tape grow by `extra_bytes` (slots named like `probe`)?  Only if, after that, enough stays free for what the step
+// still has to allocate: the OTHER tower's basic tape when it does not exist yet (`other_probe`, `other_bytes`), the backward's
+// scratch for the larger tower (44 bytes per token and channel: d-activations, 16-bit copies, fp32 streams) and 24 GB of slack
+// (gradient buffers, optimiser state held by the caller, allocator granularity).
+static bool tape_can_keep(msclip_ctx* h, const std::string& probe, size_t extra_bytes, const std::string& other_probe,
+                          size_t other_bytes, size_t max_rows) {
   if (!g_train_keep) return false;
   if (h->ws.count(probe) && h->ws[probe].bytes > 0) return true;  // already allocated by an earlier step
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
-  return free_b > extra_bytes + (size_t(40) << 30);  // leave room for the backward's scratch and the other tower
+  size_t need = extra_bytes + (size_t(24) << 30) + max_rows * static_cast<size_t>(h->cfg.width) * 44;
+  if (!(h->ws.count(other_probe) && h->ws[other_probe].bytes > 0)) need += other_bytes;
+  return free_b > need;
 }
 
 int tape_save(msclip_ctx* h, const std::string& name, const void* src, size_t bytes, cudaStream_t s) {
@@ -968,9 +975,13 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     };
     if (slots) MSCLIP_TRY(entry_slot(1, &xc));
     const size_t mrows = static_cast<size_t>(nb) * L;
-    const bool keep = slots && tape_can_keep(h, "tape:v_qkv1", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4));
+    const size_t rows_txt = static_cast<size_t>(nb) * c.context_length, rows_max = std::max(mrows, rows_txt);
+    const size_t other_base = static_cast<size_t>(c.layers + 1) * rows_txt * w * sizeof(float);   // the text tower's basic tape
+    const bool keep = slots && tape_can_keep(h, "tape:v_qkv1", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4), "tape:t_x0",
+                                             other_base, rows_max);
     h->tape_img.keep = keep;
-    const bool keep_u = keep && g_train_keep_u && tape_can_keep(h, "tape:v_u1", static_cast<size_t>(c.layers) * mrows * 4 * w * 2);
+    const bool keep_u = keep && g_train_keep_u &&
+                        tape_can_keep(h, "tape:v_u1", static_cast<size_t>(c.layers) * mrows * 4 * w * 2, "tape:t_x0", other_base, rows_max);
     h->tape_img.keep_u = keep_u;
     // the kernels that produce the residual stream also emit ln_1 of the block that consumes it next
     const bool adapter_first = adapter_at(1) >= 0;
@@ -1076,9 +1087,13 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
       for (int i = 0; i <= c.layers; ++i)
         MSCLIP_TRY(ws_get(h, ("tape:t_x" + std::to_string(i)).c_str(), xbytes, reinterpret_cast<void**>(&slot[i])));
     const size_t mrows = static_cast<size_t>(nb) * L;
-    const bool keep = slots && tape_can_keep(h, "tape:t_qkv0", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4));
+    const size_t rows_img = static_cast<size_t>(nb) * h->l_img, rows_max = std::max(mrows, rows_img);
+    const size_t other_base = static_cast<size_t>(c.layers) * rows_img * w * sizeof(float);   // the image tower's basic tape
+    const bool keep = slots && tape_can_keep(h, "tape:t_qkv0", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4), "tape:v_x1",
+                                             other_base, rows_max);
     h->tape_txt.keep = keep;
-    const bool keep_u = keep && g_train_keep_u && tape_can_keep(h, "tape:t_u0", static_cast<size_t>(c.layers) * mrows * 4 * w * 2);
+    const bool keep_u = keep && g_train_keep_u &&
+                        tape_can_keep(h, "tape:t_u0", static_cast<size_t>(c.layers) * mrows * 4 * w * 2, "tape:v_x1", other_base, rows_max);
     h->tape_txt.keep_u = keep_u;
     MSCLIP_TRY(launch_text_embed(tk, Lt, h->tok_emb, h->tpos, slot[0], nb, L, c.vocab_size, g_ln_fold ? hbuf : nullptr, rec[0],
                                  emit0 ? h->tblocks[0].ln1_w : nullptr, emit0 ? h->tblocks[0].ln1_b : nullptr,

@@ -46,6 +46,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=12)
+    ap.add_argument("--patch", type=int, default=32, choices=[16, 32])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--skip-step", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
@@ -120,7 +121,7 @@ def main():
     if not args.skip_step:
         from msclip_b200.model import CLIP
         from msclip_b200.optim import AdamW
-        cfg = MSCLIPConfig(patch_size=32, layers=args.layers)
+        cfg = MSCLIPConfig(patch_size=args.patch, layers=args.layers)
         sd = synth.synth_state_dict(cfg, seed=0, logit_scale=2.6593)
         model = CLIP(cfg, precision="bf16")
         model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
@@ -173,8 +174,7 @@ def main():
             model.loss_and_backward(img, tok)
         fb_ms = time_ms(fb, args.reps, warm=1)
         # algorithmic work: transformer part forward + dgrad + wgrad (3 x), convolutional front forward only
-        gf_pair = 23.549
-        gf_conv = 2.379
+        gf_pair, gf_conv = (23.549, 2.379) if args.patch == 32 else (49.617, 4.330)
         gf_step = 3.0 * (gf_pair - gf_conv) + gf_conv
         pairs_s = B / step_ms * 1e3
         res = {"batch": B, "layers": args.layers, "forward_loss_ms": fwd_ms, "forward_loss_taped_ms": fwd_tape_ms,
