@@ -977,11 +977,14 @@ static int vision_tower(msclip_ctx* h, const void* img, int dtype, int batch, fl
     const size_t mrows = static_cast<size_t>(nb) * L;
     const size_t rows_txt = static_cast<size_t>(nb) * c.context_length, rows_max = std::max(mrows, rows_txt);
     const size_t other_base = static_cast<size_t>(c.layers + 1) * rows_txt * w * sizeof(float);   // the text tower's basic tape
-    const bool keep = slots && tape_can_keep(h, "tape:v_qkv1", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4), "tape:t_x0",
-                                             other_base, rows_max);
+    // (this tower's adapter slots are allocated lazily further down: count them as still to come)
+    const size_t own_pending = (h->ws.count("tape:v_ax0") && h->ws["tape:v_ax0"].bytes > 0) ? 0 : static_cast<size_t>(11) * mrows * w * sizeof(float);
+    const bool keep = slots && tape_can_keep(h, "tape:v_qkv1", own_pending + static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4),
+                                             "tape:t_x0", other_base, rows_max);
     h->tape_img.keep = keep;
     const bool keep_u = keep && g_train_keep_u &&
-                        tape_can_keep(h, "tape:v_u1", static_cast<size_t>(c.layers) * mrows * 4 * w * 2, "tape:t_x0", other_base, rows_max);
+                        tape_can_keep(h, "tape:v_u1", own_pending + static_cast<size_t>(c.layers) * mrows * 4 * w * 2, "tape:t_x0", other_base,
+                                      rows_max);
     h->tape_img.keep_u = keep_u;
     // the kernels that produce the residual stream also emit ln_1 of the block that consumes it next
     const bool adapter_first = adapter_at(1) >= 0;
@@ -1088,7 +1091,8 @@ static int text_tower(msclip_ctx* h, const int64_t* tok, int batch, int L, float
         MSCLIP_TRY(ws_get(h, ("tape:t_x" + std::to_string(i)).c_str(), xbytes, reinterpret_cast<void**>(&slot[i])));
     const size_t mrows = static_cast<size_t>(nb) * L;
     const size_t rows_img = static_cast<size_t>(nb) * h->l_img, rows_max = std::max(mrows, rows_img);
-    const size_t other_base = static_cast<size_t>(c.layers) * rows_img * w * sizeof(float);   // the image tower's basic tape
+    // the image tower's basic tape: every block's input + the five adapters' inputs and top-path terms + the stem output
+    const size_t other_base = static_cast<size_t>(c.layers + 11) * rows_img * w * sizeof(float);
     const bool keep = slots && tape_can_keep(h, "tape:t_qkv0", static_cast<size_t>(c.layers) * mrows * w * (3 * 2 + 2 + 4), "tape:v_x1",
                                              other_base, rows_max);
     h->tape_txt.keep = keep;
