@@ -514,7 +514,7 @@ static const bool g_train_keep_u = [] {
 }();
 // May the tape grow by `extra_bytes` (slots named like `probe`)?  Only if, after that, enough stays free for what the step
 // still has to allocate: the OTHER tower's basic tape when it does not exist yet (`other_probe`, `other_bytes`), the backward's
-// scratch for the larger tower (44 bytes per token and channel: d-activations, 16-bit copies, fp32 streams) and 24 GB of slack
+// scratch for the larger tower (44 bytes per token and channel: d-activations, 16-bit copies, fp32 streams) and 40 GB of slack
 // (gradient buffers, optimiser state held by the caller, allocator granularity).
 static bool tape_can_keep(msclip_ctx* h, const std::string& probe, size_t extra_bytes, const std::string& other_probe,
                           size_t other_bytes, size_t max_rows) {
@@ -522,7 +522,7 @@ static bool tape_can_keep(msclip_ctx* h, const std::string& probe, size_t extra_
   if (h->ws.count(probe) && h->ws[probe].bytes > 0) return true;  // already allocated by an earlier step
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
-  size_t need = extra_bytes + (size_t(24) << 30) + max_rows * static_cast<size_t>(h->cfg.width) * 44;
+  size_t need = extra_bytes + (size_t(40) << 30) + max_rows * static_cast<size_t>(h->cfg.width) * 44;
   if (!(h->ws.count(other_probe) && h->ws[other_probe].bytes > 0)) need += other_bytes;
   return free_b > need;
 }

@@ -183,6 +183,7 @@ def main():
                "frac_sustained_tensor": pairs_s * gf_step / 1e3 / peaks["tflops_sustained"],
                "ms_each_step": each, "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
                "device_bytes": int(L.msclip_device_bytes(model._handle)), "torch_allocated": int(torch.cuda.memory_allocated()),
+               "free_bytes": int(torch.cuda.mem_get_info()[0]), "total_bytes": int(torch.cuda.mem_get_info()[1]),
                "wall_s": wall}
         out["train_step"] = res
         print(json.dumps(res), flush=True)
