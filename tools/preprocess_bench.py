@@ -18,7 +18,10 @@ import numpy as np                              # noqa: E402
 import torch                                    # noqa: E402
 from msclip_b200.config import MSCLIPConfig     # noqa: E402
 from msclip_b200.model import CLIP              # noqa: E402
-from oracle import preprocess_oracle as P       # noqa: E402
+
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)      # lib/config/default.py:84-85
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
 def main():
@@ -54,7 +57,7 @@ def main():
     n = args.n
     call = lambda: _lib.check(L.msclip_preprocess_images(
         model._ensure_handle(), C.c_void_p(packed.data_ptr()), (C.c_int64 * n)(*offs), (C.c_int * n)(*[im.shape[0] for im in imgs]),
-        (C.c_int * n)(*[im.shape[1] for im in imgs]), n, 224, (C.c_float * 3)(*P.CLIP_MEAN), (C.c_float * 3)(*P.CLIP_STD),
+        (C.c_int * n)(*[im.shape[1] for im in imgs]), n, 224, (C.c_float * 3)(*CLIP_MEAN), (C.c_float * 3)(*CLIP_STD),
         C.c_void_p(res.data_ptr()), _lib.F32, None, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     call()
     torch.cuda.synchronize()
@@ -70,7 +73,7 @@ def main():
     from PIL import Image
     from torchvision import transforms
     t = transforms.Compose([transforms.Resize(224, interpolation=Image.BICUBIC), transforms.CenterCrop((224, 224)), transforms.ToTensor(),
-                            transforms.Normalize(mean=P.CLIP_MEAN, std=P.CLIP_STD)])
+                            transforms.Normalize(mean=CLIP_MEAN, std=CLIP_STD)])
     pil = [Image.fromarray(im) for im in imgs[:64]]
     t0 = time.perf_counter()
     for im in pil:
