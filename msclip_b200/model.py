@@ -527,16 +527,35 @@ class CLIP(nn.Module):
                         "msclip_backward")
 
     @torch.no_grad()
-    def loss_and_backward(self, image: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
+    def loss_and_backward(self, image: torch.Tensor, text: torch.Tensor, micro_batch: Optional[int] = None) -> torch.Tensor:
         """One training forward + backward: the fused global-batch loss (``contrastive_loss``), its backward to the local
         embeddings (second in-kernel peer pass) and the backward of both towers.  Gradients accumulate in ``.grad``;
-        with more than one rank they are LOCAL (all-reduce them like DDP would).  Returns the loss."""
-        loss = self.contrastive_loss(image, text)
+        with more than one rank they are LOCAL (all-reduce them like DDP would).  Returns the loss.
+
+        ``micro_batch``: local batches beyond what one tape holds (4096 pairs) - e.g. the metric's global batch of 32 768 on
+        one GPU - are processed GradCache-style: every micro-batch is encoded without a tape and its embeddings retained
+        (``encode_pairs``), ONE loss and ONE loss backward run over the whole global batch, then every micro-batch is encoded
+        again with the tape and back-propagated with its rows of the embedding gradient.  Same gradients as the one-shot
+        call (needs ``setup_data_parallel(len(image))`` first, like ``contrastive_loss(micro_batch=...)``)."""
+        b = image.shape[0]
+        if micro_batch is None or micro_batch >= b:
+            loss = self.contrastive_loss(image, text)
+            gi, gt = self.contrastive_loss_backward()
+            self.backward_features(gi, gt)
+            # d loss / d logit_scale = s * d loss / d s = sum_i I_i . dI_i  (dI_i = s / 2G * sum_j w_ij T_j)
+            fi = self.last_image_features()
+            self.logit_scale.grad += (gi * fi).sum().to(self.logit_scale.dtype)
+            return loss
+        loss = self.contrastive_loss(image, text, micro_batch=micro_batch)
         gi, gt = self.contrastive_loss_backward()
-        self.backward_features(gi, gt)
-        # d loss / d logit_scale = s * d loss / d s = sum_i I_i . dI_i  (dI_i = s / 2G * sum_j w_ij T_j)
-        fi = self.last_image_features()
-        self.logit_scale.grad += (gi * fi).sum().to(self.logit_scale.dtype)
+        acc = torch.zeros((), dtype=torch.float32, device=self.device)
+        for lo in range(0, b, micro_batch):
+            hi = min(b, lo + micro_batch)
+            fi = self.encode_image(image[lo:hi])          # taped (training is enabled): the tape holds this micro-batch
+            self.encode_text(text[lo:hi])
+            self.backward_features(gi[lo:hi], gt[lo:hi])
+            acc += (gi[lo:hi] * fi).sum()
+        self.logit_scale.grad += acc.to(self.logit_scale.dtype)
         return loss
 
     @torch.no_grad()

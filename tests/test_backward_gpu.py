@@ -459,3 +459,34 @@ def test_backward_error_paths():
     fp16 = fp16.cuda().eval()
     with pytest.raises(_lib.MsclipError, match="bf16 build"):
         fp16.enable_training()
+
+
+def test_micro_batched_training_step_equals_one_shot():
+    """GradCache-style step (micro-batches encoded twice, one loss over all of them) against the one-shot step on the same
+    16 pairs: same loss, same gradients up to summation order (the towers see 3 x 6-, 6-, 4-row batches instead of 16 rows)."""
+    cfg = MSCLIPConfig(patch_size=32, layers=3)
+    sd_np = synth.synth_state_dict(cfg, seed=31, logit_scale=math.log(25.0))
+    img, tok = synth.correlated_pair_batch(cfg, 16, seed=6)
+    timg, ttok = torch.from_numpy(img).cuda(), torch.from_numpy(tok).cuda()
+    one = build_train_model(cfg, sd_np)
+    one.zero_grad()
+    loss_one = float(one.loss_and_backward(timg, ttok))
+    mb = build_train_model(cfg, sd_np)
+    mb.setup_data_parallel(16)
+    mb.zero_grad()
+    loss_mb = float(mb.loss_and_backward(timg, ttok, micro_batch=6))
+    torch.cuda.synchronize()
+    assert abs(loss_one - loss_mb) <= 2e-6 * abs(loss_one), (loss_one, loss_mb)
+    ref, got = one.trainable_parameters(), mb.trainable_parameters()
+    num = den = 0.0
+    worst = ("", 0.0)
+    for k, p in ref.items():
+        d = float((got[k].grad - p.grad).double().norm())
+        r = float(p.grad.double().norm())
+        num += d * d
+        den += r * r
+        if r > 0 and d / r > worst[1]:
+            worst = (k, d / r)
+    agg = math.sqrt(num / max(den, 1e-300))
+    _record("micro_batched_training", {"loss_one_shot": loss_one, "loss_micro": loss_mb, "aggregate": agg, "worst": list(worst)})
+    assert agg < 2e-3 and worst[1] < 2e-2, (agg, worst)
