@@ -47,6 +47,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--patch", type=int, default=32, choices=[16, 32])
+    ap.add_argument("--global-batch", type=int, default=0, help="training step over this many pairs on ONE GPU in micro-batches of "
+                    "--batch pairs (GradCache-style: two forwards per micro-batch, one loss over all pairs); images held as bf16")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--skip-step", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
@@ -128,6 +130,31 @@ def main():
         model = model.cuda().eval()
         img = torch.randn(B, 3, 224, 224, device="cuda")
         tok = torch.from_numpy(synth.synth_tokens(B, 1234, cfg.context_length, cfg.vocab_size)).cuda()
+        if args.global_batch:
+            G = args.global_batch
+            del img, tok
+            img = torch.randn(G, 3, 224, 224, device="cuda", dtype=torch.bfloat16)
+            tok = torch.from_numpy(synth.synth_tokens(G, 1234, cfg.context_length, cfg.vocab_size)).cuda()
+            model.enable_training()
+            model.setup_data_parallel(G)
+            opt = AdamW(model, lr=1e-4, weight_decay=0.05, lr_share=1e-4, wd_share=0.2)
+            losses = []
+
+            def gstep():
+                opt.zero_grad()
+                losses.append(model.loss_and_backward(img, tok, micro_batch=B))
+                opt.step()
+            ms = time_ms(gstep, max(1, args.reps // 2), warm=1)
+            gf_pair, gf_conv = (23.549, 2.379) if args.patch == 32 else (49.617, 4.330)
+            gf_step = 4.0 * (gf_pair - gf_conv) + 2.0 * gf_conv      # two forwards + dgrad + wgrad of the transformer part, two of the front
+            res = {"global_batch": G, "micro_batch": B, "step_ms": ms, "pairs_per_s": G / ms * 1e3, "gflop_per_pair_executed": gf_step,
+                   "tflops_executed": G / ms * gf_step, "loss_first": float(losses[0]), "loss_last": float(losses[-1]), "ln_G": __import__("math").log(G),
+                   "device_bytes": int(L.msclip_device_bytes(model._handle)), "free_bytes": int(torch.cuda.mem_get_info()[0])}
+            out["train_step_global_batch"] = res
+            print(json.dumps(res), flush=True)
+            with open(os.path.join(ROOT, "gpurun_out", "train_bench_global.json"), "w") as f:
+                json.dump(out, f, indent=1)
+            return
         if args.profile_step:
             model.enable_training()
             opt = AdamW(model, lr=1e-4, weight_decay=0.05, lr_share=1e-4, wd_share=0.2)
