@@ -17,6 +17,9 @@ timed region), `roofline` times the dominant kernel (the shared-block fc1 GEMM) 
 absent) on this box's host cores, `comparators` holds the same reference forward run eagerly on this GPU
 (fp32 / TF32 / autocast bf16) and, at N > 1, NCCL all-gather + logits + CE against the fused loss stage.
 `--global-batch 32768` is BASELINE.json's metric configuration on any N (micro-batches, one loss).
+`train_step` (N = 1, bf16 build; `--no-train` skips it) is a secondary, device-timed figure: the same batch through one
+TRAINING step - taped forward + fused loss, loss backward, backward of both towers, fused AdamW, weight re-pack
+ - with its own algorithmic FLOP count; the headline `value` / `e2e` stay the forward metric.
 """
 from __future__ import annotations
 
