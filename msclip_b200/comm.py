@@ -62,6 +62,44 @@ def exchange_bytes(payload: bytes, group=None) -> bytes:
     return b"".join(bytes(p.cpu().tolist()) for p in parts)
 
 
+def allreduce_gradients(tensors, group=None, bucket_bytes: int = 256 << 20, average: bool = False) -> int:
+    """Sum (or average) gradient tensors over the ranks of ``group`` in place, like DistributedDataParallel would: the
+    tensors are packed into flat buckets of at most ``bucket_bytes`` so that a model's ~150 gradient buffers travel in a
+    handful of collectives (NVSwitch makes the cost latency-, not link-bound: few large messages).  Tensors that share
+    storage (parameters shared by the two towers, M.py:2786-2830) are reduced once.  Returns the number of collectives."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return 0
+    uniq, seen = [], set()
+    for t in tensors:
+        if t is None or t.data_ptr() in seen:
+            continue
+        seen.add(t.data_ptr())
+        uniq.append(t)
+    calls, i = 0, 0
+    while i < len(uniq):
+        bucket, size = [], 0
+        while i < len(uniq) and (not bucket or size + uniq[i].numel() * uniq[i].element_size() <= bucket_bytes) \
+                and (not bucket or (uniq[i].dtype == bucket[0].dtype and uniq[i].device == bucket[0].device)):
+            bucket.append(uniq[i])
+            size += uniq[i].numel() * uniq[i].element_size()
+            i += 1
+        flat = torch.cat([t.reshape(-1) for t in bucket]) if len(bucket) > 1 else bucket[0].reshape(-1)
+        dist.all_reduce(flat, group=group)
+        if average:
+            flat /= world
+        if len(bucket) > 1:
+            off = 0
+            for t in bucket:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t))
+                off += n
+        elif average or flat.data_ptr() != bucket[0].data_ptr():
+            bucket[0].copy_(flat.view_as(bucket[0]))
+        calls += 1
+    return calls
+
+
 MAX_P2P_WORLD = 64     # publish-flag slots of the exchange buffer (msclip_comm_init refuses more)
 
 

@@ -559,6 +559,15 @@ class CLIP(nn.Module):
         return loss
 
     @torch.no_grad()
+    def allreduce_grads(self, average: bool = False) -> int:
+        """Sum the LOCAL parameter gradients of ``loss_and_backward`` over the ranks (what DistributedDataParallel does), in a
+        handful of bucketed collectives (``comm.allreduce_gradients``).  The global-batch loss is already normalised by the
+        global batch, so the SUM is the gradient of the global loss (``average`` stays False)."""
+        from .comm import allreduce_gradients
+        return allreduce_gradients([p.grad for p in self.trainable_parameters().values()], getattr(self, "_group", None),
+                                   average=average)
+
+    @torch.no_grad()
     def last_image_features(self) -> torch.Tensor:
         """Normalised image features of the last taped image-tower call (read back from the library's tape)."""
         if not getattr(self, "_train_keys", None):

@@ -90,8 +90,7 @@ def main():
         uniq = {}
         for k, p in params.items():
             uniq.setdefault(p.data_ptr(), (k, p))
-        for _k, p in uniq.values():
-            dist.all_reduce(p.grad)
+        out["grad_allreduce_collectives"] = model.allreduce_grads()      # bucketed NCCL all-reduce of the library's gradient buffers
         if rank == 0:
             solo.enable_training()
             solo.zero_grad()

@@ -33,7 +33,17 @@ def _worker(rank, world, port, out):
         # per-rank partial losses combine like the fused kernel's partial sums
         parts = torch.tensor([1.0 + rank, 2.0 + rank])
         dist.all_reduce(parts)
-        out.put((rank, ok_gather, ok_bytes, parts.tolist()))
+        # bucketed gradient all-reduce (what CLIP.allreduce_grads runs over NCCL): shared storage reduced once, several buckets
+        g = torch.Generator().manual_seed(7)
+        base = [torch.randn(n, generator=g) for n in (5, 300, 1, 64, 1000)]
+        grads = [(b * (rank + 1)).clone() for b in base]
+        grads.append(grads[1])                                   # an aliased parameter: same tensor twice
+        calls = comm.allreduce_gradients(grads, bucket_bytes=1300)
+        ok_grads = all(torch.allclose(x, b * 3.0) for x, b in zip(grads[:5], base)) and calls >= 2
+        avg = [(b * (rank + 1)).clone() for b in base]
+        comm.allreduce_gradients(avg, average=True)
+        ok_grads = ok_grads and all(torch.allclose(x, b * 1.5) for x, b in zip(avg, base))
+        out.put((rank, ok_gather, ok_bytes and ok_grads, parts.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -59,5 +69,6 @@ def test_single_process_degrades_to_world_1():
     assert comm.gather_tensors(t) is t
     assert comm.exchange_bytes(b"abc") == b"abc"
     assert comm.shard_range(3, 8, 32768) == (12288, 16384)
+    assert comm.allreduce_gradients([torch.ones(3)]) == 0
     with pytest.raises(ValueError):
         comm.shard_range(0, 3, 8)
