@@ -97,3 +97,35 @@ class AdamW:
                                                      float(self.betas[1]), float(self.eps), int(self.steps), mdl._stream()),
                        "msclip_op_adamw")
         mdl.refresh_weights([e[0] for e in self.entries])
+
+
+class CosineSchedule:
+    """Learning-rate schedule named by the reference's configuration (experiments/model/b32.yaml:37-46: timm 'cosine' with
+    warmup_epochs 5, warmup_lr 1e-6, min_lr 1e-5, cooldown_epochs 10) - the reference ships no loop that runs it, so this restates
+    the published rule of timm's CosineLRScheduler (t_in_epochs, single cycle): linear warm-up from ``warmup_lr`` to the base rate
+    over ``warmup`` epochs, then ``min_lr + 0.5 (base - min_lr)(1 + cos(pi t / t_initial))`` with t counted from epoch 0 as timm
+    does (``warmup_prefix`` False), ``min_lr`` from ``t_initial`` on (cool-down epochs run at ``min_lr``).  Every parameter
+    group keeps its own base rate (LR / LR_SHARE)."""
+
+    def __init__(self, optimizer: AdamW, epochs: int, warmup_epochs: int = 5, warmup_lr: float = 1e-6, min_lr: float = 1e-5,
+                 cooldown_epochs: int = 10):
+        self.opt = optimizer
+        self.t_initial = int(epochs)
+        self.warmup, self.warmup_lr, self.min_lr, self.cooldown = int(warmup_epochs), float(warmup_lr), float(min_lr), int(cooldown_epochs)
+        self.base = [e[2] for e in optimizer.entries]
+
+    def total_epochs(self) -> int:
+        return self.t_initial + self.cooldown
+
+    def lr_at(self, epoch: float, base: float) -> float:
+        import math
+        if epoch < self.warmup:
+            return self.warmup_lr + epoch * (base - self.warmup_lr) / self.warmup
+        if epoch < self.t_initial:
+            return self.min_lr + 0.5 * (base - self.min_lr) * (1.0 + math.cos(math.pi * epoch / self.t_initial))
+        return self.min_lr
+
+    def step(self, epoch: float) -> None:
+        """Set every group's rate for ``epoch`` (fractional epochs allowed: per-iteration updates)."""
+        for e, b in zip(self.opt.entries, self.base):
+            e[2] = self.lr_at(epoch, b)
